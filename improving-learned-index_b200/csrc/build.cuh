@@ -1,0 +1,303 @@
+// build.cuh — index build kernels: K1 quantization, K2 term->document inversion + byte-exact
+// serialisation, and the re-layout of a shard into document tiles (DESIGN.md "HBM layout").
+#pragma once
+
+#include "common.cuh"
+#include "scan_sort.cuh"
+
+namespace di {
+
+// ============================================================================ K1: quantize
+// quantize.py:17-24 — max over all scores, seeded with 0.0. Doubles compare like their bit
+// patterns when non-negative, so a 64-bit integer atomicMax on the bits of max(v, 0) is exact.
+__global__ void max_f64_kernel(const double *__restrict__ x, int64_t n, unsigned long long *__restrict__ out_bits)
+{
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v > m) m = v;  // NaN never wins, as in Python's max(max_val, nan) with max_val first
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double t = __shfl_xor_sync(0xffffffffu, m, o);
+        if (t > m) m = t;
+    }
+    if (lane_id() == 0 && m > 0.0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// quantize.py:13-14 — int(value * scale): ONE float64 multiply (no FMA to contract with: the
+// product is the only operation) and truncation toward zero, saturated to int32.
+__global__ void quantize_f64_kernel(const double *__restrict__ x, int64_t n, double scale, int32_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double p = __dmul_rn(x[i], scale);
+        out[i] = __double2int_rz(p);  // saturating; NaN -> 0
+    }
+}
+
+// ============================================================================ K2: inversion
+// key = [term:24 | 255-impact:8 | docid:32]; the input is doc-major, i.e. docid ascending, so
+// a STABLE sort on the top 32 bits yields term asc, impact desc, docid asc == create.py:33-41.
+constexpr int kInvTermShift = 40;
+constexpr uint32_t kMaxTerms = 1u << 24;
+
+__device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t *a, uint64_t n, uint64_t v)
+{
+    // first index with a[idx] > v, over a[0..n)
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void invert_keys_kernel(const uint32_t *__restrict__ term_ids, const uint8_t *__restrict__ impacts,
+                                   const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, uint64_t n_post,
+                                   uint32_t n_terms, uint64_t *__restrict__ keys, int *__restrict__ err)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t doc = upper_bound_u64(doc_offsets, n_docs + 1, i) - 1;  // doc_offsets[doc] <= i < [doc+1]
+        const uint32_t t = term_ids[i];
+        if (t >= n_terms) *err = 1;
+        keys[i] = ((uint64_t)t << kInvTermShift) | ((uint64_t)(255u - impacts[i]) << 32) | (uint64_t)(uint32_t)doc;
+    }
+}
+
+__global__ void invert_extract_kernel(const uint64_t *__restrict__ keys, uint64_t n_post, uint32_t n_terms,
+                                      uint64_t *__restrict__ term_offsets, uint32_t *__restrict__ docids,
+                                      uint8_t *__restrict__ impacts)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        docids[i] = (uint32_t)k;
+        impacts[i] = (uint8_t)(255u - ((uint32_t)(k >> 32) & 255u));
+        const int64_t t = (int64_t)(k >> kInvTermShift);
+        const int64_t tprev = i ? (int64_t)(keys[i - 1] >> kInvTermShift) : -1;
+        for (int64_t tt = tprev + 1; tt <= t; ++tt) term_offsets[tt] = i;  // also covers empty terms
+        if (i == n_post - 1)
+            for (int64_t tt = t + 1; tt <= (int64_t)n_terms; ++tt) term_offsets[tt] = n_post;
+    }
+}
+
+// create.py:44-51 — 5-byte records and (start,end) byte offsets
+__global__ void serialize_dat_kernel(const uint32_t *__restrict__ docids, const uint8_t *__restrict__ impacts,
+                                     uint64_t n_post, uint8_t *__restrict__ dat)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t d = docids[i];
+        uint8_t *p = dat + 5 * i;
+        p[0] = (uint8_t)d; p[1] = (uint8_t)(d >> 8); p[2] = (uint8_t)(d >> 16); p[3] = (uint8_t)(d >> 24);
+        p[4] = impacts[i];
+    }
+}
+
+__global__ void serialize_idx_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms, uint64_t *__restrict__ idx)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_terms; t += gridDim.x * blockDim.x) {
+        idx[2 * (uint64_t)t] = 5 * term_offsets[t];
+        idx[2 * (uint64_t)t + 1] = 5 * term_offsets[t + 1];
+    }
+}
+
+inline int invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
+                      uint64_t n_docs, uint32_t n_terms, uint64_t n_post, uint64_t *d_term_offsets,
+                      uint32_t *d_out_docids, uint8_t *d_out_impacts, cudaStream_t st)
+{
+    if (n_terms > kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24", n_terms);
+    if (n_docs >= (1ull << 32)) return set_error(DI_ERR_ARG, "n_docs exceeds 2^32-1");
+    if (n_post == 0) {
+        DI_CUDA(cudaMemsetAsync(d_term_offsets, 0, ((size_t)n_terms + 1) * sizeof(uint64_t), st));
+        return DI_OK;
+    }
+    DevBuf ka, kb, err;
+    RadixSortScratch ws;
+    DI_TRY(ka.alloc(n_post * sizeof(uint64_t)));
+    DI_TRY(kb.alloc(n_post * sizeof(uint64_t)));
+    DI_TRY(err.alloc(sizeof(int)));
+    DI_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+    invert_keys_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(d_term_ids, d_impacts, d_doc_offsets, n_docs, n_post,
+                                                              n_terms, ka.as<uint64_t>(), err.as<int>());
+    DI_KERNEL_CHECK();
+    int h_err = 0;
+    DI_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaStreamSynchronize(st));
+    if (h_err) return set_error(DI_ERR_RANGE, "term id >= n_terms (%u) in the collection", n_terms);
+    int term_bits = 1;
+    while ((1ull << term_bits) < n_terms) ++term_bits;
+    uint64_t *sorted = nullptr;
+    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, 32, kInvTermShift + term_bits, ws, st, &sorted));
+    invert_extract_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(sorted, n_post, n_terms, d_term_offsets, d_out_docids,
+                                                                 d_out_impacts);
+    DI_KERNEL_CHECK();
+    DI_CUDA(cudaStreamSynchronize(st));  // scratch is freed on return
+    return DI_OK;
+}
+
+// ============================================================================ tiled shard layout
+// tile key = [tile:16 | term:24 | local docid:16 | impact:8]; hidden postings get ~0 and sort last.
+constexpr int kTkTermShift = 24, kTkTileShift = 48, kTkLocalShift = 8;
+constexpr uint32_t kDenseFlag = 0x80000000u;
+
+struct SegDesc {        // one per (tile, term)
+    uint32_t off16;     // payload offset in 16-byte units
+    uint32_t n_flag;    // postings in the segment | kDenseFlag
+};
+
+// inverted_index.py:50-51 — the reader stops at the FIRST zero impact of a term's list
+__global__ void first_zero_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
+                                  const uint8_t *__restrict__ impacts, uint64_t n_post,
+                                  unsigned long long *__restrict__ first_zero)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (impacts[i] == 0) {
+            const uint64_t t = upper_bound_u64(term_offsets, (uint64_t)n_terms + 1, i) - 1;
+            atomicMin(&first_zero[t], (unsigned long long)i);
+        }
+    }
+}
+
+__global__ void init_first_zero_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
+                                       unsigned long long *__restrict__ first_zero)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_terms; t += gridDim.x * blockDim.x)
+        first_zero[t] = term_offsets[t + 1];
+}
+
+struct TileStats {
+    unsigned long long n_visible;
+    unsigned long long n_dense_segments, n_sparse_segments, n_dense_postings;
+    unsigned int max_docid_plus1;
+    unsigned int bad_docid;
+};
+
+__global__ void tile_keys_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
+                                 const uint32_t *__restrict__ docids, const uint8_t *__restrict__ impacts,
+                                 uint64_t n_post, const unsigned long long *__restrict__ first_zero,
+                                 uint32_t doc_lo, uint32_t doc_hi, int tile_shift,
+                                 uint64_t *__restrict__ keys, TileStats *__restrict__ stats)
+{
+    unsigned long long vis = 0;
+    unsigned int mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = upper_bound_u64(term_offsets, (uint64_t)n_terms + 1, i) - 1;
+        const uint32_t d = docids[i];
+        uint64_t key = ~0ull;
+        if (i < first_zero[t] && d >= doc_lo && d < doc_hi) {
+            const uint32_t rel = d - doc_lo;
+            const uint64_t tile = rel >> tile_shift;
+            if (tile >= 0xFFFFu) {
+                stats->bad_docid = 1;
+            } else {
+                const uint32_t local = rel & ((1u << tile_shift) - 1u);
+                key = (tile << kTkTileShift) | ((uint64_t)t << kTkTermShift) | ((uint64_t)local << kTkLocalShift) | impacts[i];
+                ++vis;
+                if (d + 1 > mx) mx = d + 1;  // d < doc_hi <= 2^32-1
+            }
+        }
+        keys[i] = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vis += __shfl_xor_sync(0xffffffffu, vis, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane_id() == 0) {
+        if (vis) atomicAdd(&stats->n_visible, vis);
+        if (mx) atomicMax(&stats->max_docid_plus1, mx);
+    }
+}
+
+__device__ __forceinline__ uint64_t seg_index(uint64_t key, uint32_t n_terms)
+{
+    const uint64_t tile = key >> kTkTileShift;
+    const uint64_t term = (key >> kTkTermShift) & 0xFFFFFFu;
+    return tile * n_terms + term;
+}
+
+// `seg_dup[s]` is set when a segment holds the same document twice (possible in hand-made CSR or
+// a model that lists a term twice): such a segment cannot be stored densely (one byte per doc).
+__global__ void seg_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t n_vis, uint32_t n_terms,
+                                  uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ seg_end,
+                                  uint32_t *__restrict__ seg_dup)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t id = keys[i] >> kTkTermShift;
+        if (i && (keys[i - 1] >> kTkLocalShift) == (keys[i] >> kTkLocalShift)) seg_dup[seg_index(keys[i], n_terms)] = 1u;
+        if (i == 0 || (keys[i - 1] >> kTkTermShift) != id) seg_begin[seg_index(keys[i], n_terms)] = (uint32_t)i;
+        if (i == n_vis - 1 || (keys[i + 1] >> kTkTermShift) != id) seg_end[seg_index(keys[i], n_terms)] = (uint32_t)(i + 1);
+    }
+}
+
+// per (tile, term): choose dense (u8 per doc of the tile) or sparse (u32 per posting) storage.
+// On entry size16[s] holds the duplicate flag written by seg_bounds_kernel.
+__global__ void seg_size_kernel(const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ seg_end,
+                                uint64_t n_segs, uint32_t n_terms, uint32_t tile_docs, uint32_t dense_ratio,
+                                uint32_t *__restrict__ size16, uint32_t *__restrict__ n_flag,
+                                unsigned long long *__restrict__ df, TileStats *__restrict__ stats)
+{
+    unsigned long long nd = 0, ns = 0, ndp = 0;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_segs; s += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t n = seg_end[s] - seg_begin[s];
+        uint32_t sz = 0, nf = 0;
+        if (n) {
+            const bool dense = dense_ratio != 0xFFFFFFFFu && (uint64_t)n * dense_ratio >= tile_docs && size16[s] == 0;
+            sz = dense ? tile_docs / 16u : (n + 3u) / 4u;
+            nf = n | (dense ? kDenseFlag : 0u);
+            if (dense) { ++nd; ndp += n; } else ++ns;
+            atomicAdd(&df[s % n_terms], (unsigned long long)n);
+        }
+        size16[s] = sz;
+        n_flag[s] = nf;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nd += __shfl_xor_sync(0xffffffffu, nd, o);
+        ns += __shfl_xor_sync(0xffffffffu, ns, o);
+        ndp += __shfl_xor_sync(0xffffffffu, ndp, o);
+    }
+    if (lane_id() == 0) {
+        if (nd) atomicAdd(&stats->n_dense_segments, nd);
+        if (ns) atomicAdd(&stats->n_sparse_segments, ns);
+        if (ndp) atomicAdd(&stats->n_dense_postings, ndp);
+    }
+}
+
+__global__ void seg_desc_kernel(const uint32_t *__restrict__ off16, const uint32_t *__restrict__ n_flag, uint64_t n_segs,
+                                SegDesc *__restrict__ desc)
+{
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_segs; s += (uint64_t)gridDim.x * blockDim.x)
+        desc[s] = SegDesc{off16[s], n_flag[s]};
+}
+
+__global__ void fill_payload_kernel(const uint64_t *__restrict__ keys, uint64_t n_vis, uint32_t n_terms,
+                                    const SegDesc *__restrict__ desc, const uint32_t *__restrict__ seg_begin,
+                                    uint8_t *__restrict__ payload)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[i];
+        const uint64_t s = seg_index(key, n_terms);
+        const SegDesc d = desc[s];
+        const uint32_t local = (uint32_t)(key >> kTkLocalShift) & 0xFFFFu;
+        const uint32_t imp = (uint32_t)key & 0xFFu;
+        if (d.n_flag & kDenseFlag)
+            payload[(size_t)d.off16 * 16 + local] = (uint8_t)imp;
+        else
+            reinterpret_cast<uint32_t *>(payload)[(size_t)d.off16 * 4 + (i - seg_begin[s])] = (imp << 16) | local;
+    }
+}
+
+// raw .dat image -> docids / impacts arrays (records may start at any byte offset)
+__global__ void decode_dat_kernel(const uint8_t *__restrict__ dat, const uint64_t *__restrict__ term_offsets,
+                                  const uint64_t *__restrict__ term_start_byte, uint32_t n_terms, uint64_t n_post,
+                                  uint32_t *__restrict__ docids, uint8_t *__restrict__ impacts)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = upper_bound_u64(term_offsets, (uint64_t)n_terms + 1, i) - 1;
+        const uint8_t *p = dat + term_start_byte[t] + 5 * (i - term_offsets[t]);
+        docids[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        impacts[i] = p[4];
+    }
+}
+
+}  // namespace di

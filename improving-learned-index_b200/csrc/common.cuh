@@ -1,0 +1,120 @@
+// common.cuh — error plumbing and small device helpers shared by every kernel file.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/di_b200.h"
+
+namespace di {
+
+// ----------------------------------------------------------------------------- errors
+inline char *err_buf()
+{
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+inline int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DI_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return di::set_error(e__ == cudaErrorMemoryAllocation ? DI_ERR_NOMEM : DI_ERR_CUDA,    \
+                                 "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                                 __LINE__);                                                        \
+    } while (0)
+
+#define DI_TRY(call)                    \
+    do {                                \
+        int rc__ = (call);              \
+        if (rc__ != DI_OK) return rc__; \
+    } while (0)
+
+#define DI_KERNEL_CHECK() DI_CUDA(cudaGetLastError())
+
+// RAII device buffer used for build-time scratch (freed on scope exit, also on error paths).
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t n)
+    {
+        release();
+        bytes = n ? n : 16;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return set_error(DI_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        return DI_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ----------------------------------------------------------------------------- device helpers
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// 128-bit streaming load through the read-only path, not allocating in L1: postings are read
+// once per (query, tile) work item; reuse across queries happens in L2.
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint4 *ptr)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(ptr));
+    return r;
+}
+
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *ptr)
+{
+    uint64_t r;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(ptr));
+    return r;
+}
+
+// ranked-result key: larger is better. score in the high word, bit-inverted docid in the low
+// word, so that equal scores order by ASCENDING docid under a descending key sort.
+__host__ __device__ __forceinline__ uint64_t make_key(uint32_t score, uint32_t docid)
+{
+    return (static_cast<uint64_t>(score) << 32) | static_cast<uint64_t>(~docid);
+}
+__host__ __device__ __forceinline__ uint32_t key_score(uint64_t k) { return static_cast<uint32_t>(k >> 32); }
+__host__ __device__ __forceinline__ uint32_t key_docid(uint64_t k) { return ~static_cast<uint32_t>(k); }
+
+inline unsigned grid_for(uint64_t n, unsigned block, unsigned max_blocks = 148u * 32u)
+{
+    uint64_t g = (n + block - 1) / block;
+    if (g == 0) g = 1;
+    return static_cast<unsigned>(g > max_blocks ? max_blocks : g);
+}
+
+}  // namespace di

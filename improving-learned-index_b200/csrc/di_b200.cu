@@ -1,0 +1,639 @@
+// di_b200.cu — the C ABI declared in include/di_b200.h. Host-side orchestration only; the
+// kernels live in build.cuh / search.cuh / scan_sort.cuh. Compiled for sm_100a.
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "build.cuh"
+#include "common.cuh"
+#include "scan_sort.cuh"
+#include "search.cuh"
+
+using namespace di;
+
+// ============================================================================ handle
+struct di_index {
+    int device = 0;
+    uint32_t n_terms = 0, doc_lo = 0, doc_hi = 0;
+    uint32_t n_tiles = 0, tile_docs = 0, tile_shift = 0, max_docid_plus1 = 0;
+    uint32_t dense_ratio = 4, cand_slack = 0;
+    uint64_t n_postings = 0, payload_bytes = 0, table_bytes = 0;
+    uint64_t n_dense_segments = 0, n_sparse_segments = 0, n_dense_postings = 0;
+    SegDesc *d_desc = nullptr;
+    uint8_t *d_payload = nullptr;
+    unsigned long long *d_df = nullptr;
+
+    // search workspace (grown on demand)
+    cudaStream_t stream = nullptr;
+    DevBuf ws_cand, ws_cnt, ws_theta;
+    DevBuf st_qterms, st_qoffs, st_keys, st_counts, st_docids, st_scores;
+    int smem_opt_in = 0;
+    bool attr_set16 = false, attr_set32 = false, attr_setfin = false;
+
+    // timing of the last search
+    static constexpr int kMaxBatches = 64;
+    cudaEvent_t ev[kMaxBatches][3] = {};
+    int n_batches = 0;
+    uint32_t score_launches = 0, other_launches = 0;
+
+    ~di_index()
+    {
+        if (d_desc) cudaFree(d_desc);
+        if (d_payload) cudaFree(d_payload);
+        if (d_df) cudaFree(d_df);
+        for (auto &b : ev)
+            for (auto &e : b)
+                if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static int ensure_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(DI_ERR_NODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    return DI_OK;
+}
+
+extern "C" const char *di_last_error(void) { return err_buf(); }
+extern "C" int di_version(void) { return 100; }
+
+extern "C" int di_device_count(int *count)
+{
+    if (!count) return set_error(DI_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return DI_OK;
+}
+
+extern "C" int di_set_device(int device)
+{
+    DI_TRY(ensure_device());
+    DI_CUDA(cudaSetDevice(device));
+    return DI_OK;
+}
+
+// ============================================================================ K1
+extern "C" int di_find_max_f64_dev(const double *d_scores, int64_t n, double *d_max_out, void *stream)
+{
+    if (n < 0 || !d_max_out) return set_error(DI_ERR_ARG, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    DI_CUDA(cudaMemsetAsync(d_max_out, 0, sizeof(double), st));  // bits of +0.0
+    if (n) {
+        max_f64_kernel<<<grid_for((uint64_t)n, 256, 148 * 8), 256, 0, st>>>(d_scores, n, (unsigned long long *)d_max_out);
+        DI_KERNEL_CHECK();
+    }
+    return DI_OK;
+}
+
+extern "C" int di_quantize_f64_dev(const double *d_scores, int64_t n, double max_val, int32_t *d_out, void *stream)
+{
+    if (n < 0) return set_error(DI_ERR_ARG, "n < 0");
+    if (n == 0) return DI_OK;
+    const double scale = 255.0 / max_val;  // quantize.py:37, float64 division on the host
+    quantize_f64_kernel<<<grid_for((uint64_t)n, 256), 256, 0, (cudaStream_t)stream>>>(d_scores, n, scale, d_out);
+    DI_KERNEL_CHECK();
+    return DI_OK;
+}
+
+extern "C" int di_find_max_f64(const double *scores, int64_t n, double *max_out)
+{
+    if (n < 0 || !max_out) return set_error(DI_ERR_ARG, "bad arguments");
+    DI_TRY(ensure_device());
+    DevBuf d_x, d_m;
+    DI_TRY(d_x.alloc((size_t)n * sizeof(double)));
+    DI_TRY(d_m.alloc(sizeof(double)));
+    if (n) DI_CUDA(cudaMemcpy(d_x.p, scores, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    DI_TRY(di_find_max_f64_dev(d_x.as<double>(), n, d_m.as<double>(), nullptr));
+    DI_CUDA(cudaMemcpy(max_out, d_m.p, sizeof(double), cudaMemcpyDeviceToHost));
+    return DI_OK;
+}
+
+extern "C" int di_quantize_f64(const double *scores, int64_t n, double max_val, int32_t *out)
+{
+    if (n < 0) return set_error(DI_ERR_ARG, "n < 0");
+    DI_TRY(ensure_device());
+    if (n == 0) return DI_OK;
+    DevBuf d_x, d_o;
+    DI_TRY(d_x.alloc((size_t)n * sizeof(double)));
+    DI_TRY(d_o.alloc((size_t)n * sizeof(int32_t)));
+    DI_CUDA(cudaMemcpy(d_x.p, scores, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    DI_TRY(di_quantize_f64_dev(d_x.as<double>(), n, max_val, d_o.as<int32_t>(), nullptr));
+    DI_CUDA(cudaMemcpy(out, d_o.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return DI_OK;
+}
+
+// ============================================================================ K2
+extern "C" int di_invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
+                             uint64_t n_docs, uint32_t n_terms, uint64_t n_postings, uint64_t *d_term_offsets,
+                             uint32_t *d_out_docids, uint8_t *d_out_impacts, void *stream)
+{
+    return invert_dev(d_term_ids, d_impacts, d_doc_offsets, n_docs, n_terms, n_postings, d_term_offsets, d_out_docids,
+                      d_out_impacts, (cudaStream_t)stream);
+}
+
+extern "C" int di_invert(const uint32_t *term_ids, const uint8_t *impacts, const uint64_t *doc_offsets, uint64_t n_docs,
+                         uint32_t n_terms, uint64_t *term_offsets, uint32_t *out_docids, uint8_t *out_impacts)
+{
+    if (!doc_offsets || !term_offsets) return set_error(DI_ERR_ARG, "NULL argument");
+    DI_TRY(ensure_device());
+    const uint64_t P = doc_offsets[n_docs];
+    DevBuf d_t, d_v, d_o, d_to, d_od, d_ov;
+    DI_TRY(d_t.alloc(P * sizeof(uint32_t)));
+    DI_TRY(d_v.alloc(P));
+    DI_TRY(d_o.alloc((n_docs + 1) * sizeof(uint64_t)));
+    DI_TRY(d_to.alloc(((size_t)n_terms + 1) * sizeof(uint64_t)));
+    DI_TRY(d_od.alloc(P * sizeof(uint32_t)));
+    DI_TRY(d_ov.alloc(P));
+    if (P) {
+        DI_CUDA(cudaMemcpy(d_t.p, term_ids, P * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        DI_CUDA(cudaMemcpy(d_v.p, impacts, P, cudaMemcpyHostToDevice));
+    }
+    DI_CUDA(cudaMemcpy(d_o.p, doc_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    DI_TRY(invert_dev(d_t.as<uint32_t>(), d_v.as<uint8_t>(), d_o.as<uint64_t>(), n_docs, n_terms, P, d_to.as<uint64_t>(),
+                      d_od.as<uint32_t>(), d_ov.as<uint8_t>(), nullptr));
+    DI_CUDA(cudaMemcpy(term_offsets, d_to.p, ((size_t)n_terms + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (P) {
+        DI_CUDA(cudaMemcpy(out_docids, d_od.p, P * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        DI_CUDA(cudaMemcpy(out_impacts, d_ov.p, P, cudaMemcpyDeviceToHost));
+    }
+    return DI_OK;
+}
+
+extern "C" int di_serialize_dev(const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
+                                uint32_t n_terms, uint64_t n_postings, uint8_t *d_dat, uint64_t *d_idx, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_postings) {
+        serialize_dat_kernel<<<grid_for(n_postings, 256), 256, 0, st>>>(d_docids, d_impacts, n_postings, d_dat);
+        DI_KERNEL_CHECK();
+    }
+    if (n_terms) {
+        serialize_idx_kernel<<<grid_for(n_terms, 256), 256, 0, st>>>(d_term_offsets, n_terms, d_idx);
+        DI_KERNEL_CHECK();
+    }
+    return DI_OK;
+}
+
+extern "C" int di_serialize(const uint64_t *term_offsets, const uint32_t *docids, const uint8_t *impacts, uint32_t n_terms,
+                            uint8_t *dat, uint64_t *idx)
+{
+    if (!term_offsets) return set_error(DI_ERR_ARG, "NULL argument");
+    DI_TRY(ensure_device());
+    const uint64_t P = term_offsets[n_terms];
+    DevBuf d_to, d_d, d_v, d_dat, d_idx;
+    DI_TRY(d_to.alloc(((size_t)n_terms + 1) * sizeof(uint64_t)));
+    DI_TRY(d_d.alloc(P * sizeof(uint32_t)));
+    DI_TRY(d_v.alloc(P));
+    DI_TRY(d_dat.alloc(P * 5));
+    DI_TRY(d_idx.alloc((size_t)n_terms * 16));
+    DI_CUDA(cudaMemcpy(d_to.p, term_offsets, ((size_t)n_terms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (P) {
+        DI_CUDA(cudaMemcpy(d_d.p, docids, P * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        DI_CUDA(cudaMemcpy(d_v.p, impacts, P, cudaMemcpyHostToDevice));
+    }
+    DI_TRY(di_serialize_dev(d_to.as<uint64_t>(), d_d.as<uint32_t>(), d_v.as<uint8_t>(), n_terms, P, d_dat.as<uint8_t>(),
+                            d_idx.as<uint64_t>(), nullptr));
+    if (P) DI_CUDA(cudaMemcpy(dat, d_dat.p, P * 5, cudaMemcpyDeviceToHost));
+    if (n_terms) DI_CUDA(cudaMemcpy(idx, d_idx.p, (size_t)n_terms * 16, cudaMemcpyDeviceToHost));
+    return DI_OK;
+}
+
+// ============================================================================ index create
+static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
+                       uint64_t n_post, cudaStream_t st)
+{
+    const uint32_t V = ix->n_terms;
+    if (V > kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24", V);
+    if (n_post >= (1ull << 32)) return set_error(DI_ERR_ARG, "more than 2^32-1 postings in one shard");
+
+    DevBuf d_stats, d_fz, ka, kb;
+    RadixSortScratch ws;
+    DI_TRY(d_stats.alloc(sizeof(TileStats)));
+    DI_CUDA(cudaMemsetAsync(d_stats.p, 0, sizeof(TileStats), st));
+    TileStats stats{};
+    uint64_t *sorted = nullptr;
+    if (n_post) {
+        DI_TRY(d_fz.alloc((size_t)V * sizeof(unsigned long long)));
+        DI_TRY(ka.alloc(n_post * sizeof(uint64_t)));
+        DI_TRY(kb.alloc(n_post * sizeof(uint64_t)));
+        init_first_zero_kernel<<<grid_for(V, 256), 256, 0, st>>>(d_term_offsets, V, d_fz.as<unsigned long long>());
+        DI_KERNEL_CHECK();
+        first_zero_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(d_term_offsets, V, d_impacts, n_post,
+                                                                 d_fz.as<unsigned long long>());
+        DI_KERNEL_CHECK();
+        tile_keys_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(d_term_offsets, V, d_docids, d_impacts, n_post,
+                                                                d_fz.as<unsigned long long>(), ix->doc_lo, ix->doc_hi,
+                                                                (int)ix->tile_shift, ka.as<uint64_t>(),
+                                                                d_stats.as<TileStats>());
+        DI_KERNEL_CHECK();
+        DI_CUDA(cudaMemcpyAsync(&stats, d_stats.p, sizeof stats, cudaMemcpyDeviceToHost, st));
+        DI_CUDA(cudaStreamSynchronize(st));
+        if (stats.bad_docid)
+            return set_error(DI_ERR_RANGE, "shard spans more than 65535 tiles of %u docs; raise tile_docs or shard further",
+                             ix->tile_docs);
+        d_fz.release();
+        // hidden postings carry ~0 and sort to the end; the (tile, term, local) order is total
+        DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, kTkLocalShift, 64, ws, st, &sorted));
+    }
+    const uint64_t n_vis = stats.n_visible;
+    ix->n_postings = n_vis;
+    ix->max_docid_plus1 = stats.max_docid_plus1;
+    ix->n_tiles = n_vis ? ((stats.max_docid_plus1 - ix->doc_lo) + ix->tile_docs - 1) / ix->tile_docs : 0;
+    if (ix->n_tiles == 0) return DI_OK;
+
+    const uint64_t n_segs = (uint64_t)ix->n_tiles * V;
+    if (n_segs * sizeof(SegDesc) > (48ull << 30))
+        return set_error(DI_ERR_NOMEM, "segment table of %llu entries is too large; use larger tiles",
+                         (unsigned long long)n_segs);
+    DevBuf d_begin, d_end, d_size, d_nflag, d_scan;
+    DI_TRY(d_begin.alloc(n_segs * 4));
+    DI_TRY(d_end.alloc(n_segs * 4));
+    DI_TRY(d_size.alloc((n_segs + 1) * 4));
+    DI_TRY(d_nflag.alloc(n_segs * 4));
+    DI_TRY(d_scan.alloc(scan_scratch_words(n_segs + 1) * 4));
+    DI_CUDA(cudaMalloc(&ix->d_df, (size_t)V * sizeof(unsigned long long)));
+    DI_CUDA(cudaMemsetAsync(ix->d_df, 0, (size_t)V * sizeof(unsigned long long), st));
+    DI_CUDA(cudaMemsetAsync(d_begin.p, 0, n_segs * 4, st));
+    DI_CUDA(cudaMemsetAsync(d_end.p, 0, n_segs * 4, st));
+    DI_CUDA(cudaMemsetAsync(d_size.p, 0, (n_segs + 1) * 4, st));
+    seg_bounds_kernel<<<grid_for(n_vis, 256), 256, 0, st>>>(sorted, n_vis, V, d_begin.as<uint32_t>(), d_end.as<uint32_t>(),
+                                                          d_size.as<uint32_t>());
+    DI_KERNEL_CHECK();
+    seg_size_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_begin.as<uint32_t>(), d_end.as<uint32_t>(), n_segs, V,
+                                                          ix->tile_docs, ix->dense_ratio, d_size.as<uint32_t>(),
+                                                          d_nflag.as<uint32_t>(), ix->d_df, d_stats.as<TileStats>());
+    DI_KERNEL_CHECK();
+    // exclusive scan over n_segs + 1 entries: the last output is the total payload size
+    DI_TRY(exclusive_scan_u32(d_size.as<uint32_t>(), d_size.as<uint32_t>(), n_segs + 1, d_scan.as<uint32_t>(), st));
+    uint32_t total16 = 0;
+    DI_CUDA(cudaMemcpyAsync(&total16, d_size.as<uint32_t>() + n_segs, 4, cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaMemcpyAsync(&stats, d_stats.p, sizeof stats, cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaStreamSynchronize(st));
+    ix->n_dense_segments = stats.n_dense_segments;
+    ix->n_sparse_segments = stats.n_sparse_segments;
+    ix->n_dense_postings = stats.n_dense_postings;
+    ix->payload_bytes = (uint64_t)total16 * 16;
+    ix->table_bytes = n_segs * sizeof(SegDesc);
+    DI_CUDA(cudaMalloc(&ix->d_desc, ix->table_bytes));
+    DI_CUDA(cudaMalloc(&ix->d_payload, ix->payload_bytes ? ix->payload_bytes : 16));
+    DI_CUDA(cudaMemsetAsync(ix->d_payload, 0, ix->payload_bytes ? ix->payload_bytes : 16, st));
+    seg_desc_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_size.as<uint32_t>(), d_nflag.as<uint32_t>(), n_segs, ix->d_desc);
+    DI_KERNEL_CHECK();
+    fill_payload_kernel<<<grid_for(n_vis, 256), 256, 0, st>>>(sorted, n_vis, V, ix->d_desc, d_begin.as<uint32_t>(),
+                                                              ix->d_payload);
+    DI_KERNEL_CHECK();
+    DI_CUDA(cudaStreamSynchronize(st));
+    return DI_OK;
+}
+
+static int new_index(uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const di_index_params *params, di_index **out)
+{
+    if (!out) return set_error(DI_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    DI_TRY(ensure_device());
+    if (doc_hi <= doc_lo) return set_error(DI_ERR_ARG, "empty doc range [%u, %u)", doc_lo, doc_hi);
+    uint32_t tile_docs = params && params->tile_docs ? params->tile_docs : 32768u;
+    if (tile_docs < 256 || tile_docs > 65536 || (tile_docs & (tile_docs - 1)))
+        return set_error(DI_ERR_ARG, "tile_docs must be a power of two in [256, 65536], got %u", tile_docs);
+    di_index *ix = new (std::nothrow) di_index();
+    if (!ix) return set_error(DI_ERR_NOMEM, "host allocation failed");
+    cudaGetDevice(&ix->device);
+    ix->n_terms = n_terms;
+    ix->doc_lo = doc_lo;
+    ix->doc_hi = doc_hi;
+    ix->tile_docs = tile_docs;
+    while ((1u << ix->tile_shift) < tile_docs) ++ix->tile_shift;
+    ix->dense_ratio = params && params->dense_ratio ? params->dense_ratio : 4u;
+    ix->cand_slack = params ? params->cand_slack : 0u;
+    cudaDeviceGetAttribute(&ix->smem_opt_in, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device);
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ix;
+        return set_error(DI_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = ix;
+    return DI_OK;
+}
+
+extern "C" int di_index_create_csr_dev(const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
+                                       uint32_t n_terms, uint64_t n_postings, uint32_t doc_lo, uint32_t doc_hi,
+                                       const di_index_params *params, di_index_t **out)
+{
+    di_index *ix = nullptr;
+    DI_TRY(new_index(n_terms, doc_lo, doc_hi, params, &ix));
+    int rc = build_tiled(ix, d_term_offsets, d_docids, d_impacts, n_postings, ix->stream);
+    if (rc != DI_OK) {
+        delete ix;
+        *out = nullptr;
+        return rc;
+    }
+    *out = ix;
+    return DI_OK;
+}
+
+extern "C" int di_index_create_csr(const uint64_t *term_offsets, const uint32_t *docids, const uint8_t *impacts,
+                                   uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const di_index_params *params,
+                                   di_index_t **out)
+{
+    if (!term_offsets || !out) return set_error(DI_ERR_ARG, "NULL argument");
+    DI_TRY(ensure_device());
+    const uint64_t P = term_offsets[n_terms];
+    DevBuf d_to, d_d, d_v;
+    DI_TRY(d_to.alloc(((size_t)n_terms + 1) * sizeof(uint64_t)));
+    DI_TRY(d_d.alloc(P * sizeof(uint32_t)));
+    DI_TRY(d_v.alloc(P));
+    DI_CUDA(cudaMemcpy(d_to.p, term_offsets, ((size_t)n_terms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (P) {
+        DI_CUDA(cudaMemcpy(d_d.p, docids, P * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        DI_CUDA(cudaMemcpy(d_v.p, impacts, P, cudaMemcpyHostToDevice));
+    }
+    return di_index_create_csr_dev(d_to.as<uint64_t>(), d_d.as<uint32_t>(), d_v.as<uint8_t>(), n_terms, P, doc_lo, doc_hi,
+                                   params, out);
+}
+
+extern "C" int di_index_create_files(const uint8_t *dat, uint64_t dat_bytes, const uint64_t *idx_pairs, uint32_t n_terms,
+                                     uint32_t doc_lo, uint32_t doc_hi, const di_index_params *params, di_index_t **out)
+{
+    if ((!dat && dat_bytes) || (!idx_pairs && n_terms) || !out) return set_error(DI_ERR_ARG, "NULL argument");
+    DI_TRY(ensure_device());
+    // inverted_index.py:47 — records are read while tell() < end: ceil((end - start) / 5) of them
+    std::vector<uint64_t> offs((size_t)n_terms + 1, 0), starts((size_t)n_terms ? n_terms : 1, 0);
+    for (uint32_t t = 0; t < n_terms; ++t) {
+        const uint64_t s = idx_pairs[2 * (size_t)t], e = idx_pairs[2 * (size_t)t + 1];
+        const uint64_t cnt = e > s ? (e - s + 4) / 5 : 0;
+        if (cnt && s + 5 * cnt > dat_bytes)
+            return set_error(DI_ERR_FORMAT, "term %u: records [%llu, %llu) run past the end of the .dat image (%llu bytes)", t,
+                             (unsigned long long)s, (unsigned long long)(s + 5 * cnt), (unsigned long long)dat_bytes);
+        offs[t + 1] = offs[t] + cnt;
+        starts[t] = s;
+    }
+    const uint64_t P = offs[n_terms];
+    DevBuf d_dat, d_to, d_st, d_d, d_v;
+    DI_TRY(d_dat.alloc(dat_bytes));
+    DI_TRY(d_to.alloc(((size_t)n_terms + 1) * sizeof(uint64_t)));
+    DI_TRY(d_st.alloc((size_t)(n_terms ? n_terms : 1) * sizeof(uint64_t)));
+    DI_TRY(d_d.alloc(P * sizeof(uint32_t)));
+    DI_TRY(d_v.alloc(P));
+    if (dat_bytes) DI_CUDA(cudaMemcpy(d_dat.p, dat, dat_bytes, cudaMemcpyHostToDevice));
+    DI_CUDA(cudaMemcpy(d_to.p, offs.data(), ((size_t)n_terms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (n_terms) DI_CUDA(cudaMemcpy(d_st.p, starts.data(), (size_t)n_terms * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (P) {
+        decode_dat_kernel<<<grid_for(P, 256), 256>>>(d_dat.as<uint8_t>(), d_to.as<uint64_t>(), d_st.as<uint64_t>(), n_terms, P,
+                                                     d_d.as<uint32_t>(), d_v.as<uint8_t>());
+        DI_KERNEL_CHECK();
+        DI_CUDA(cudaDeviceSynchronize());
+    }
+    d_dat.release();
+    return di_index_create_csr_dev(d_to.as<uint64_t>(), d_d.as<uint32_t>(), d_v.as<uint8_t>(), n_terms, P, doc_lo, doc_hi,
+                                   params, out);
+}
+
+extern "C" void di_index_destroy(di_index_t *index)
+{
+    if (!index) return;
+    cudaSetDevice(index->device);
+    cudaDeviceSynchronize();
+    delete index;
+}
+
+extern "C" int di_index_get_info(const di_index_t *ix, di_index_info *info)
+{
+    if (!ix || !info) return set_error(DI_ERR_ARG, "NULL argument");
+    info->n_postings = ix->n_postings;
+    info->payload_bytes = ix->payload_bytes;
+    info->table_bytes = ix->table_bytes;
+    info->n_dense_segments = ix->n_dense_segments;
+    info->n_sparse_segments = ix->n_sparse_segments;
+    info->n_dense_postings = ix->n_dense_postings;
+    info->n_terms = ix->n_terms;
+    info->doc_lo = ix->doc_lo;
+    info->doc_hi = ix->doc_hi;
+    info->n_tiles = ix->n_tiles;
+    info->tile_docs = ix->tile_docs;
+    info->max_docid_plus1 = ix->max_docid_plus1;
+    return DI_OK;
+}
+
+extern "C" int di_index_term_df(const di_index_t *ix, const uint32_t *term_ids, uint64_t n, uint64_t *df_out)
+{
+    if (!ix || (!term_ids && n) || (!df_out && n)) return set_error(DI_ERR_ARG, "NULL argument");
+    std::vector<unsigned long long> df((size_t)ix->n_terms, 0);
+    if (ix->d_df && ix->n_terms) {
+        DI_CUDA(cudaSetDevice(ix->device));
+        DI_CUDA(cudaMemcpy(df.data(), ix->d_df, (size_t)ix->n_terms * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    for (uint64_t i = 0; i < n; ++i) df_out[i] = term_ids[i] < ix->n_terms ? df[term_ids[i]] : 0;
+    return DI_OK;
+}
+
+// ============================================================================ search
+static uint32_t pow2_ceil(uint32_t x)
+{
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+static int ensure(DevBuf &b, size_t bytes)
+{
+    if (b.bytes >= bytes && b.p) return DI_OK;
+    return b.alloc(bytes + bytes / 8);
+}
+
+extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const uint64_t *d_q_offsets, uint32_t n_queries,
+                             uint32_t max_query_len, uint32_t top_k, uint64_t *d_out_keys, uint32_t *d_out_counts,
+                             void *stream)
+{
+    if (!ix) return set_error(DI_ERR_ARG, "index is NULL");
+    if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
+    if (max_query_len > 65535) return set_error(DI_ERR_ARG, "queries longer than 65535 terms are not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    DI_CUDA(cudaSetDevice(ix->device));
+    ix->n_batches = 0;
+    ix->score_launches = ix->other_launches = 0;
+    if (n_queries == 0) return DI_OK;
+
+    const bool acc32 = max_query_len > 257;  // 257 * 255 = 65535 still fits a u16 accumulator
+    const size_t acc_bytes = (size_t)ix->tile_docs * (acc32 ? 4 : 2);
+    if ((int)acc_bytes + 4096 > ix->smem_opt_in)
+        return set_error(DI_ERR_ARG, "tile of %u docs needs %zu B of shared memory for %d-bit accumulators (limit %d); "
+                         "rebuild the index with smaller tiles for queries of %u terms",
+                         ix->tile_docs, acc_bytes, acc32 ? 32 : 16, ix->smem_opt_in, max_query_len);
+    uint32_t c0 = ix->cand_slack ? ix->cand_slack : std::max(4u * top_k, 4096u);
+    c0 = std::max(c0, top_k);
+    const uint32_t cap = std::max(c0 + ix->tile_docs, pow2_ceil(top_k));
+    const int top_shift = acc32 ? 48 : 40;
+
+    if (acc32 && !ix->attr_set32) {
+        DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+        ix->attr_set32 = true;
+    }
+    if (!acc32 && !ix->attr_set16) {
+        DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+        DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+        ix->attr_set16 = true;
+    }
+
+    // candidate workspace: at most ~6 GB, queries are processed in batches that fit
+    const uint64_t per_query = (uint64_t)cap * 8;
+    uint32_t batch = (uint32_t)std::min<uint64_t>(n_queries, std::max<uint64_t>(1, (6ull << 30) / per_query));
+    if ((n_queries + batch - 1) / batch > (uint32_t)di_index::kMaxBatches)
+        batch = (n_queries + di_index::kMaxBatches - 1) / di_index::kMaxBatches;
+    DI_TRY(ensure(ix->ws_cand, (size_t)batch * per_query));
+    DI_TRY(ensure(ix->ws_cnt, (size_t)batch * 4));
+    DI_TRY(ensure(ix->ws_theta, (size_t)batch * 8));
+
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += batch) {
+        const uint32_t nq = std::min(batch, n_queries - q0);
+        const int b = ix->n_batches++;
+        for (int e = 0; e < 3; ++e)
+            if (!ix->ev[b][e]) DI_CUDA(cudaEventCreate(&ix->ev[b][e]));
+        SearchArgs a{};
+        a.desc = ix->d_desc;
+        a.payload = ix->d_payload;
+        a.q_terms = d_q_terms;
+        a.q_offsets = d_q_offsets + q0;
+        a.cand = ix->ws_cand.as<uint64_t>();
+        a.cnt = ix->ws_cnt.as<uint32_t>();
+        a.theta = ix->ws_theta.as<uint64_t>();
+        a.n_terms = ix->n_terms;
+        a.tile_docs = ix->tile_docs;
+        a.tile_shift = ix->tile_shift;
+        a.doc_lo = ix->doc_lo;
+        a.cap = cap;
+        a.c0 = c0;
+        a.k = top_k;
+        a.top_shift = top_shift;
+        DI_CUDA(cudaMemsetAsync(a.cnt, 0, (size_t)nq * 4, st));
+        DI_CUDA(cudaMemsetAsync(a.theta, 0, (size_t)nq * 8, st));
+        DI_CUDA(cudaEventRecord(ix->ev[b][0], st));
+        for (uint32_t tile = 0; tile < ix->n_tiles; ++tile) {
+            if (acc32)
+                score_tile_kernel<true><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
+            else
+                score_tile_kernel<false><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
+            ++ix->score_launches;
+        }
+        DI_KERNEL_CHECK();
+        DI_CUDA(cudaEventRecord(ix->ev[b][1], st));
+        finalize_topk_kernel<<<nq, kScoreThreads, kSortSmemKeys * 8, st>>>(a.cand, a.cnt, cap, top_k, top_shift,
+                                                                          d_out_keys + (uint64_t)q0 * top_k, d_out_counts + q0);
+        DI_KERNEL_CHECK();
+        ++ix->other_launches;
+        DI_CUDA(cudaEventRecord(ix->ev[b][2], st));
+    }
+    return DI_OK;
+}
+
+extern "C" int di_unpack_keys_dev(const uint64_t *d_keys, uint64_t n, uint32_t *d_docids, int32_t *d_scores, void *stream)
+{
+    if (n == 0) return DI_OK;
+    unpack_keys_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_keys, n, d_docids, d_scores);
+    DI_KERNEL_CHECK();
+    return DI_OK;
+}
+
+extern "C" int di_search(di_index_t *ix, const uint32_t *q_terms, const uint64_t *q_offsets, uint32_t n_queries,
+                         uint32_t top_k, uint32_t *out_docids, int32_t *out_scores, uint32_t *out_counts)
+{
+    if (!ix || !q_offsets) return set_error(DI_ERR_ARG, "NULL argument");
+    if (n_queries == 0) return DI_OK;
+    if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
+    uint64_t max_len = 0;
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        if (q_offsets[q + 1] < q_offsets[q]) return set_error(DI_ERR_ARG, "q_offsets is not non-decreasing at %u", q);
+        max_len = std::max(max_len, q_offsets[q + 1] - q_offsets[q]);
+    }
+    if (max_len > 65535) return set_error(DI_ERR_ARG, "queries longer than 65535 terms are not supported");
+    const uint64_t base = q_offsets[0], n_terms_total = q_offsets[n_queries] - base;
+    DI_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const uint64_t n_out = (uint64_t)n_queries * top_k;
+    DI_TRY(ensure(ix->st_qterms, std::max<uint64_t>(n_terms_total, 1) * 4));
+    DI_TRY(ensure(ix->st_qoffs, ((size_t)n_queries + 1) * 8));
+    DI_TRY(ensure(ix->st_keys, n_out * 8));
+    DI_TRY(ensure(ix->st_counts, (size_t)n_queries * 4));
+    DI_TRY(ensure(ix->st_docids, n_out * 4));
+    DI_TRY(ensure(ix->st_scores, n_out * 4));
+    if (n_terms_total)
+        DI_CUDA(cudaMemcpyAsync(ix->st_qterms.p, q_terms + base, n_terms_total * 4, cudaMemcpyHostToDevice, st));
+    if (base == 0) {
+        DI_CUDA(cudaMemcpyAsync(ix->st_qoffs.p, q_offsets, ((size_t)n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        std::vector<uint64_t> rel((size_t)n_queries + 1);
+        for (uint32_t q = 0; q <= n_queries; ++q) rel[q] = q_offsets[q] - base;
+        DI_CUDA(cudaMemcpyAsync(ix->st_qoffs.p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, st));
+        DI_CUDA(cudaStreamSynchronize(st));
+    }
+    if (ix->n_tiles == 0) {  // empty shard: nothing can match
+        memset(out_counts, 0, (size_t)n_queries * 4);
+        ix->n_batches = 0;
+        DI_CUDA(cudaStreamSynchronize(st));
+        return DI_OK;
+    }
+    DI_TRY(di_search_dev(ix, ix->st_qterms.as<uint32_t>(), ix->st_qoffs.as<uint64_t>(), n_queries, (uint32_t)max_len, top_k,
+                         ix->st_keys.as<uint64_t>(), ix->st_counts.as<uint32_t>(), st));
+    DI_TRY(di_unpack_keys_dev(ix->st_keys.as<uint64_t>(), n_out, ix->st_docids.as<uint32_t>(), ix->st_scores.as<int32_t>(), st));
+    ++ix->other_launches;
+    DI_CUDA(cudaMemcpyAsync(out_docids, ix->st_docids.p, n_out * 4, cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaMemcpyAsync(out_scores, ix->st_scores.p, n_out * 4, cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaMemcpyAsync(out_counts, ix->st_counts.p, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaStreamSynchronize(st));
+    return DI_OK;
+}
+
+extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_counts_in, uint32_t n_shards,
+                                 uint32_t n_queries, uint32_t top_k, uint64_t *d_keys_out, uint32_t *d_counts_out,
+                                 void *stream)
+{
+    if (n_queries == 0 || n_shards == 0) return DI_OK;
+    if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t cap = pow2_ceil(n_shards * top_k);
+    DevBuf cand, cnt;  // freed after the stream is drained below
+    DI_TRY(cand.alloc((size_t)n_queries * cap * 8));
+    DI_TRY(cnt.alloc((size_t)n_queries * 4));
+    merge_gather_kernel<<<n_queries, 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, top_k, cand.as<uint64_t>(),
+                                                  cnt.as<uint32_t>(), cap);
+    DI_KERNEL_CHECK();
+    finalize_topk_kernel<<<n_queries, kScoreThreads, kSortSmemKeys * 8, st>>>(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k,
+                                                                            48, d_keys_out, d_counts_out);
+    DI_KERNEL_CHECK();
+    DI_CUDA(cudaStreamSynchronize(st));
+    return DI_OK;
+}
+
+extern "C" int di_get_timings(di_index_t *ix, di_timings *out)
+{
+    if (!ix || !out) return set_error(DI_ERR_ARG, "NULL argument");
+    memset(out, 0, sizeof *out);
+    DI_CUDA(cudaSetDevice(ix->device));
+    for (int b = 0; b < ix->n_batches; ++b) {
+        float s = 0, f = 0;
+        DI_CUDA(cudaEventSynchronize(ix->ev[b][2]));
+        DI_CUDA(cudaEventElapsedTime(&s, ix->ev[b][0], ix->ev[b][1]));
+        DI_CUDA(cudaEventElapsedTime(&f, ix->ev[b][1], ix->ev[b][2]));
+        out->score_ms += s;
+        out->finalize_ms += f;
+    }
+    if (ix->n_batches) {
+        float t = 0;
+        DI_CUDA(cudaEventElapsedTime(&t, ix->ev[0][0], ix->ev[ix->n_batches - 1][2]));
+        out->total_ms = t;
+    }
+    out->score_launches = ix->score_launches;
+    out->other_launches = ix->other_launches;
+    return DI_OK;
+}

@@ -1,0 +1,193 @@
+"""Thin array-level wrappers over the C ABI: quantize / invert / serialize, and DeviceIndex,
+the handle of one HBM-resident index shard. The reference-shaped classes (InvertedIndex,
+InvertedIndexCreator, SparseSearch, Ranker ...) are built on these.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+
+# --------------------------------------------------------------------------- K1
+def find_max(scores) -> float:
+    """quantize.py:17-24 on the GPU: max over all scores, seeded with 0."""
+    s = N.np_c(scores, np.float64).reshape(-1)
+    out = ctypes.c_double(0.0)
+    N.check(N.lib().di_find_max_f64(N.ptr(s), s.size, ctypes.byref(out)))
+    return out.value
+
+
+def quantize(scores, max_val: Optional[float] = None) -> np.ndarray:
+    """quantize.py:13-14,37 on the GPU: int(score * (255 / max_val)) as int32 (caller drops <= 0)."""
+    s = N.np_c(scores, np.float64).reshape(-1)
+    if max_val is None:
+        max_val = find_max(s)
+    out = np.empty(s.size, dtype=np.int32)
+    N.check(N.lib().di_quantize_f64(N.ptr(s), s.size, float(max_val), N.ptr(out)))
+    return out
+
+
+# --------------------------------------------------------------------------- K2
+def invert(term_ids, impacts, doc_offsets, n_terms: int):
+    """create.py:31-46 on the GPU: doc-major postings -> term-major CSR in the reference's
+    order (term asc, impact desc, docid asc). Returns (term_offsets u64, docids u32, impacts u8)."""
+    t = N.np_c(term_ids, np.uint32).reshape(-1)
+    v = N.np_c(impacts, np.uint8).reshape(-1)
+    o = N.np_c(doc_offsets, np.uint64).reshape(-1)
+    if o.size < 1 or int(o[-1]) != t.size or v.size != t.size:
+        raise ValueError("doc_offsets[-1] must equal the number of postings")
+    toff = np.zeros(n_terms + 1, dtype=np.uint64)
+    docs = np.empty(t.size, dtype=np.uint32)
+    imps = np.empty(t.size, dtype=np.uint8)
+    N.check(N.lib().di_invert(N.ptr(t), N.ptr(v), N.ptr(o), o.size - 1, n_terms, N.ptr(toff), N.ptr(docs), N.ptr(imps)))
+    return toff, docs, imps
+
+
+def serialize(term_offsets, docids, impacts):
+    """create.py:44-51 on the GPU: CSR -> (.dat image u8[5P], .idx image u64[2V])."""
+    toff = N.np_c(term_offsets, np.uint64).reshape(-1)
+    d = N.np_c(docids, np.uint32).reshape(-1)
+    v = N.np_c(impacts, np.uint8).reshape(-1)
+    n_terms = toff.size - 1
+    dat = np.empty(5 * d.size, dtype=np.uint8)
+    idx = np.empty(2 * n_terms, dtype=np.uint64)
+    N.check(N.lib().di_serialize(N.ptr(toff), N.ptr(d), N.ptr(v), n_terms, N.ptr(dat), N.ptr(idx)))
+    return dat, idx
+
+
+# --------------------------------------------------------------------------- queries
+def flatten_queries(queries: Sequence[Iterable[int]]):
+    """List of term-id lists -> (flat u32 terms, u64 offsets). Negative / None ids become OOV."""
+    offs = np.zeros(len(queries) + 1, dtype=np.uint64)
+    flat = []
+    for i, q in enumerate(queries):
+        for t in q:
+            flat.append(N.OOV if (t is None or t < 0) else int(t))
+        offs[i + 1] = len(flat)
+    return np.asarray(flat, dtype=np.uint32).reshape(-1), offs
+
+
+class DeviceIndex:
+    """One index shard resident in HBM (docids in [doc_lo, doc_hi), docids stay global)."""
+
+    def __init__(self, handle: int):
+        self._h = ctypes.c_void_p(handle)
+
+    # ---- constructors -------------------------------------------------------
+    @staticmethod
+    def _params(tile_docs, dense_ratio, cand_slack):
+        return N.IndexParams(tile_docs or 0, dense_ratio or 0, cand_slack or 0, 0)
+
+    @classmethod
+    def from_csr(cls, term_offsets, docids, impacts, doc_lo: int = 0, doc_hi: int = N.ALL_DOCS,
+                 tile_docs: int = 0, dense_ratio: int = 0, cand_slack: int = 0) -> "DeviceIndex":
+        toff = N.np_c(term_offsets, np.uint64).reshape(-1)
+        d = N.np_c(docids, np.uint32).reshape(-1)
+        v = N.np_c(impacts, np.uint8).reshape(-1)
+        if int(toff[-1]) != d.size or d.size != v.size:
+            raise ValueError("term_offsets[-1] must equal len(docids) == len(impacts)")
+        h = ctypes.c_void_p()
+        p = cls._params(tile_docs, dense_ratio, cand_slack)
+        N.check(N.lib().di_index_create_csr(N.ptr(toff), N.ptr(d), N.ptr(v), toff.size - 1, doc_lo, doc_hi,
+                                            ctypes.byref(p), ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_csr_device(cls, d_term_offsets, d_docids, d_impacts, n_terms: int, n_postings: int,
+                        doc_lo: int = 0, doc_hi: int = N.ALL_DOCS, tile_docs: int = 0, dense_ratio: int = 0,
+                        cand_slack: int = 0) -> "DeviceIndex":
+        """CSR already in device memory (torch CUDA tensors or raw device addresses). The caller
+        must have synchronised the stream that produced them."""
+        h = ctypes.c_void_p()
+        p = cls._params(tile_docs, dense_ratio, cand_slack)
+        N.check(N.lib().di_index_create_csr_dev(N.ptr(d_term_offsets), N.ptr(d_docids), N.ptr(d_impacts), n_terms,
+                                                n_postings, doc_lo, doc_hi, ctypes.byref(p), ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_files(cls, dat, idx_pairs, doc_lo: int = 0, doc_hi: int = N.ALL_DOCS, tile_docs: int = 0,
+                   dense_ratio: int = 0, cand_slack: int = 0) -> "DeviceIndex":
+        """From the reference's file images: inverted_index.dat bytes and inverted_index.idx as u64 pairs."""
+        dat = N.np_c(dat, np.uint8).reshape(-1)
+        idx = N.np_c(idx_pairs, np.uint64).reshape(-1)
+        if idx.size % 2:
+            raise ValueError(".idx image must hold (start, end) pairs")
+        h = ctypes.c_void_p()
+        p = cls._params(tile_docs, dense_ratio, cand_slack)
+        N.check(N.lib().di_index_create_files(N.ptr(dat), dat.size, N.ptr(idx), idx.size // 2, doc_lo, doc_hi,
+                                              ctypes.byref(p), ctypes.byref(h)))
+        return cls(h.value)
+
+    # ---- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().di_index_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __reduce__(self):
+        raise TypeError("a DeviceIndex lives in GPU memory and cannot be pickled (the reference's "
+                        "multiprocessing.Pool fan-out, ranker.py:44-46, is replaced by batched search)")
+
+    # ---- queries ------------------------------------------------------------
+    def info(self) -> dict:
+        i = N.IndexInfo()
+        N.check(N.lib().di_index_get_info(self._h, ctypes.byref(i)))
+        return {f: getattr(i, f) for f, _ in N.IndexInfo._fields_}
+
+    def term_df(self, term_ids) -> np.ndarray:
+        t = N.np_c(term_ids, np.uint32).reshape(-1)
+        out = np.zeros(t.size, dtype=np.uint64)
+        N.check(N.lib().di_index_term_df(self._h, N.ptr(t), t.size, N.ptr(out)))
+        return out
+
+    def search_flat(self, q_terms, q_offsets, top_k: int, out_docids=None, out_scores=None, out_counts=None):
+        """Host-buffer entry point (H2D + kernels + D2H inside the call). Buffers may be numpy arrays
+        or pinned torch tensors; outputs are allocated when not given."""
+        n_q = len(q_offsets) - 1
+        if out_docids is None:
+            out_docids = np.empty((n_q, top_k), dtype=np.uint32)
+            out_scores = np.empty((n_q, top_k), dtype=np.int32)
+            out_counts = np.zeros(n_q, dtype=np.uint32)
+        N.check(N.lib().di_search(self._h, N.ptr(q_terms), N.ptr(q_offsets), n_q, top_k,
+                                  N.ptr(out_docids), N.ptr(out_scores), N.ptr(out_counts)))
+        return out_docids, out_scores, out_counts
+
+    def search(self, queries: Sequence[Iterable[int]], top_k: int):
+        """queries: list of term-id lists. Returns (docids[Q,k], scores[Q,k], counts[Q])."""
+        flat, offs = flatten_queries(queries)
+        if flat.size == 0:
+            flat = np.zeros(1, dtype=np.uint32)
+        return self.search_flat(flat, offs, top_k)
+
+    def search_device(self, d_q_terms, d_q_offsets, n_queries: int, max_query_len: int, top_k: int,
+                      d_out_keys, d_out_counts, stream: int = 0):
+        """Device-buffer entry point, asynchronous on `stream`; outputs are packed keys
+        (score << 32 | ~docid) sorted descending — the form the cross-shard merge consumes."""
+        N.check(N.lib().di_search_dev(self._h, N.ptr(d_q_terms), N.ptr(d_q_offsets), n_queries, max_query_len, top_k,
+                                      N.ptr(d_out_keys), N.ptr(d_out_counts), stream))
+
+    def timings(self) -> dict:
+        t = N.Timings()
+        N.check(N.lib().di_get_timings(self._h, ctypes.byref(t)))
+        return {f: getattr(t, f) for f, _ in N.Timings._fields_}
+
+
+def unpack_keys_device(d_keys, n: int, d_docids, d_scores, stream: int = 0):
+    N.check(N.lib().di_unpack_keys_dev(N.ptr(d_keys), n, N.ptr(d_docids), N.ptr(d_scores), stream))
+
+
+def merge_topk_device(d_keys_in, d_counts_in, n_shards: int, n_queries: int, top_k: int, d_keys_out, d_counts_out,
+                      stream: int = 0):
+    """K5: [n_shards][n_queries][k] gathered keys -> global top-k per query."""
+    N.check(N.lib().di_merge_topk_dev(N.ptr(d_keys_in), N.ptr(d_counts_in), n_shards, n_queries, top_k,
+                                      N.ptr(d_keys_out), N.ptr(d_counts_out), stream))

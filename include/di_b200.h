@@ -1,0 +1,172 @@
+/*
+ * di_b200.h — C ABI of the B200-native DeeperImpact inverted-index path.
+ *
+ * The reference (Tommachilez/improving-learned-index) is pure Python and has no FFI; the
+ * only callers of this ABI are the Python classes in improving-learned-index_b200/ that
+ * mirror the reference's class surface. Each entry point names the reference code it
+ * replaces (file:line relative to the reference root). INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types; every buffer is caller-owned; `*_dev` variants take DEVICE pointers and a
+ *     cudaStream_t (passed as void*) and are asynchronous on that stream; the others take HOST
+ *     pointers and return when the result is in the output buffers.
+ *   - return value: 0 = DI_OK, otherwise an error code; di_last_error() gives the message of
+ *     the last failure on the calling thread.
+ *   - no global mutable state besides the handles; a handle must not be used from two threads
+ *     at once.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     DI_ERR_CUDA / DI_ERR_NODEVICE.
+ */
+#ifndef DI_B200_H
+#define DI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DI_OK 0
+#define DI_ERR_CUDA 1      /* a CUDA runtime call failed */
+#define DI_ERR_ARG 2       /* invalid argument */
+#define DI_ERR_RANGE 3     /* a value does not fit the index format (impact > 255, docid out of range, ...) */
+#define DI_ERR_NOMEM 4     /* device or host allocation failed */
+#define DI_ERR_NODEVICE 5  /* no CUDA device present */
+#define DI_ERR_FORMAT 6    /* malformed index file image (short read) */
+
+#define DI_OOV_TERM 0xFFFFFFFFu /* query term id meaning "not in vocabulary" (inverted_index.py:43-44) */
+
+typedef struct di_index di_index_t; /* opaque, device-resident index shard */
+
+const char *di_last_error(void);
+int di_version(void);
+int di_device_count(int *count);
+int di_set_device(int device);
+
+/* ------------------------------------------------------------------ K1: quantization
+ * Replaces src/deep_impact/indexing/quantize.py:
+ *   find_max_value :17-24  -> di_find_max_f64   (max seeded with 0.0)
+ *   quantize       :13-14  -> di_quantize_f64   out[i] = (int)trunc(scores[i] * (255.0 / max_val)), float64
+ * The caller applies quantize.py:45 (keep iff out[i] > 0). Results are saturated to the
+ * int32 range, not to 255 (the reference does not clamp either).
+ */
+int di_find_max_f64(const double *scores, int64_t n, double *max_out);
+int di_quantize_f64(const double *scores, int64_t n, double max_val, int32_t *out);
+int di_find_max_f64_dev(const double *d_scores, int64_t n, double *d_max_out, void *stream);
+int di_quantize_f64_dev(const double *d_scores, int64_t n, double max_val, int32_t *d_out, void *stream);
+
+/* ------------------------------------------------------------------ K2: term -> document inversion
+ * Replaces src/deep_impact/inverted_index/create.py:31-51 (InvertedIndexCreator._inverted_index).
+ * Input is a doc-major collection already mapped to term ids (create.py:19-29: id = rank in
+ * sorted() order; that string sort stays on the host): doc d owns postings
+ * [doc_offsets[d], doc_offsets[d+1]).  Output is term-major CSR in the reference's order —
+ * term ascending, impact descending, docid ascending (stable sort of create.py:41).
+ *   term_offsets : n_terms + 1 entries;  out_docids / out_impacts : doc_offsets[n_docs] entries.
+ * di_serialize produces the reference's on-disk images (create.py:44-51, utils/defaults.py:22-37):
+ *   dat = 5-byte records pack('I', doc) + pack('B', impact);  idx = per term (start_byte, end_byte) as 2 x u64.
+ */
+int di_invert(const uint32_t *term_ids, const uint8_t *impacts, const uint64_t *doc_offsets,
+              uint64_t n_docs, uint32_t n_terms,
+              uint64_t *term_offsets, uint32_t *out_docids, uint8_t *out_impacts);
+int di_invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
+                  uint64_t n_docs, uint32_t n_terms, uint64_t n_postings,
+                  uint64_t *d_term_offsets, uint32_t *d_out_docids, uint8_t *d_out_impacts, void *stream);
+int di_serialize(const uint64_t *term_offsets, const uint32_t *docids, const uint8_t *impacts,
+                 uint32_t n_terms, uint8_t *dat, uint64_t *idx);
+int di_serialize_dev(const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
+                     uint32_t n_terms, uint64_t n_postings, uint8_t *d_dat, uint64_t *d_idx, void *stream);
+
+/* ------------------------------------------------------------------ index shard (device resident)
+ * Replaces the reader half of src/deep_impact/inverted_index/inverted_index.py:24-53: instead of
+ * re-opening .idx/.dat per term per query, the whole shard is re-laid out once in HBM as
+ * document tiles. Reader semantics kept: within one term's list, postings at
+ * or after the first impact == 0 are invisible (inverted_index.py:50-51).
+ *
+ * A shard holds the postings whose docid lies in [doc_lo, doc_hi); docids stay GLOBAL, so
+ * results of different shards merge with the same deterministic order.
+ */
+typedef struct di_index_params {
+    uint32_t tile_docs;      /* documents per tile: power of two in [256, 65536]; 0 = default (32768) */
+    uint32_t dense_ratio;    /* a (term, tile) segment with n postings is stored as a dense u8 array
+                                when n * dense_ratio >= tile_docs; 0 = default (4); 0xFFFFFFFF = never */
+    uint32_t cand_slack;     /* per-query candidate slots kept between tiles; 0 = default (max(4k, 4096)) */
+    uint32_t reserved;
+} di_index_params;
+
+typedef struct di_index_info {
+    uint64_t n_postings;      /* visible postings in the shard */
+    uint64_t payload_bytes;   /* bytes of tiled posting payload in HBM */
+    uint64_t table_bytes;     /* bytes of the (tile, term) segment table */
+    uint64_t n_dense_segments;
+    uint64_t n_sparse_segments;
+    uint64_t n_dense_postings; /* postings held in dense segments */
+    uint32_t n_terms;
+    uint32_t doc_lo, doc_hi;
+    uint32_t n_tiles, tile_docs;
+    uint32_t max_docid_plus1; /* 1 + largest docid seen (0 if the shard is empty) */
+} di_index_info;
+
+/* from term-major CSR in host memory (any order inside a term's list is accepted) */
+int di_index_create_csr(const uint64_t *term_offsets, const uint32_t *docids, const uint8_t *impacts,
+                        uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi,
+                        const di_index_params *params, di_index_t **out);
+/* same, CSR already in device memory */
+int di_index_create_csr_dev(const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
+                            uint32_t n_terms, uint64_t n_postings, uint32_t doc_lo, uint32_t doc_hi,
+                            const di_index_params *params, di_index_t **out);
+/* from the reference's file images: inverted_index.dat bytes + inverted_index.idx as (start,end) u64 pairs */
+int di_index_create_files(const uint8_t *dat, uint64_t dat_bytes, const uint64_t *idx_pairs,
+                          uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi,
+                          const di_index_params *params, di_index_t **out);
+void di_index_destroy(di_index_t *index);
+int di_index_get_info(const di_index_t *index, di_index_info *info);
+/* visible posting count (document frequency) of each given term id in this shard; OOV -> 0 */
+int di_index_term_df(const di_index_t *index, const uint32_t *term_ids, uint64_t n, uint64_t *df_out);
+
+/* ------------------------------------------------------------------ K3 + K4: scoring and top-k
+ * Replaces InvertedIndex.score (inverted_index.py:55-62) for a BATCH of queries, and the
+ * scoring loop of SparseSearch.search (evaluation/nano_beir_evaluator.py:113-133):
+ *   score[q][doc] = sum over the query's term occurrences of the doc's impact (duplicates count
+ *   again, inverted_index.py:58-60); result = the top_k docs with score > 0 ordered by score
+ *   descending, TIES BY ASCENDING DOCID (the canonical order of SURVEY.md §8a; the reference's
+ *   own tie order depends on PYTHONHASHSEED).
+ * Query q owns term ids q_terms[q_offsets[q] .. q_offsets[q+1]); DI_OOV_TERM entries are skipped.
+ * Outputs are row-major [n_queries][top_k]; rows are valid up to out_counts[q].
+ * top_k <= 65536.
+ */
+int di_search(di_index_t *index, const uint32_t *q_terms, const uint64_t *q_offsets,
+              uint32_t n_queries, uint32_t top_k,
+              uint32_t *out_docids, int32_t *out_scores, uint32_t *out_counts);
+/* device variant: packed keys (score << 32 | ~docid), sorted descending, for the multi-GPU merge.
+ * max_query_len = longest query in the batch (chooses 16- or 32-bit accumulators). */
+int di_search_dev(di_index_t *index, const uint32_t *d_q_terms, const uint64_t *d_q_offsets,
+                  uint32_t n_queries, uint32_t max_query_len, uint32_t top_k,
+                  uint64_t *d_out_keys, uint32_t *d_out_counts, void *stream);
+int di_unpack_keys_dev(const uint64_t *d_keys, uint64_t n, uint32_t *d_docids, int32_t *d_scores, void *stream);
+
+/* ------------------------------------------------------------------ K5: cross-shard top-k merge
+ * New functionality (the reference is single-host): d_keys_in holds n_shards blocks of
+ * [n_queries][top_k] sorted keys (as gathered over NCCL), d_counts_in n_shards x [n_queries].
+ * Output: the global top_k per query in the same deterministic order.
+ */
+int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_counts_in,
+                      uint32_t n_shards, uint32_t n_queries, uint32_t top_k,
+                      uint64_t *d_keys_out, uint32_t *d_counts_out, void *stream);
+
+/* ------------------------------------------------------------------ measurement hooks
+ * Device time (CUDA events on the launching stream) of the last di_search / di_search_dev call. */
+typedef struct di_timings {
+    float score_ms;      /* all score_tile launches */
+    float finalize_ms;   /* final select + sort */
+    float total_ms;      /* first kernel to last kernel */
+    uint32_t score_launches;
+    uint32_t other_launches;
+} di_timings;
+int di_get_timings(di_index_t *index, di_timings *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DI_B200_H */

@@ -1,0 +1,331 @@
+"""GPU parity tests: every call goes through the C ABI (libdi_b200.so) and is compared bit for bit
+with (a) the golden vectors recorded from the reference and (b) the CPU oracle on seeded inputs."""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from improving_learned_index_b200 import engine, synthetic as syn
+from improving_learned_index_b200 import InvertedIndex, InvertedIndexCreator, quantize_file, find_max_value
+from improving_learned_index_b200.evaluation import Metrics, Ranker, SparseSearch
+from oracle import oracle
+from helpers import assert_same_results, canonical, quantized_csr, write_index_dir
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------ K1 quantize
+def test_quantize_golden_cases(golden):
+    g = golden("quantize")
+    for case in g["cases"]:
+        got = engine.quantize(case["values"], case["max"])
+        assert got.tolist() == case["quantized"], case["max"]
+        assert engine.find_max(case["values"]) == max(case["values"])
+
+
+def test_quantize_self_max_sweep(golden):
+    """max * (255 / max) lands on 254 for exactly the maxima the reference says (fp64, truncation)."""
+    g = golden("quantize")
+    vals = np.arange(1, 20001) / 1000
+    got = np.array([engine.quantize([v], v)[0] for v in vals[::37]])
+    want = np.array([oracle.quantize([v], v)[0] for v in vals[::37]])
+    assert np.array_equal(got, want)
+    sel = np.array(g["sweep_254"][:200])
+    assert all(engine.quantize([m / 1000], m / 1000)[0] == 254 for m in sel[:50])
+
+
+def test_quantize_random_matches_oracle():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.lognormal(0, 2, 200_000), rng.uniform(0, 1e-3, 1000), [0.0, 1e300, 5e-324]])
+    x = np.round(x, 3)
+    for mx in (None, 7.0, 0.013):
+        assert np.array_equal(engine.quantize(x, mx).astype(np.int64),
+                              np.clip(oracle.quantize(x, mx), -2**31, 2**31 - 1))
+    assert engine.find_max(x) == oracle.find_max(x)
+    assert engine.find_max([]) == 0.0 and engine.find_max([-1.0, -2.0]) == 0.0
+
+
+def test_quantize_file_golden(golden, tmp_path):
+    g = golden("quantize")["file"]
+    src = tmp_path / "in"
+    src.write_text(''.join(l + '\n' for l in g["lines"]))
+    assert find_max_value(src) == 1.0
+    for key, mx in (("auto", None), ("max2", 2.0), ("max05", 0.5)):
+        quantize_file(src, tmp_path / key, mx)
+        assert (tmp_path / key).read_text().split('\n')[:-1] == g[key]
+    bad = tmp_path / "blank"
+    bad.write_text("a: 1.0\n\nb: 2.0\n")
+    with pytest.raises(ValueError):          # quantize.py:22,43 — blank line cannot be unpacked
+        quantize_file(bad, tmp_path / "out")
+
+
+# ------------------------------------------------------------------ K2 inversion, byte-identical files
+@pytest.mark.parametrize("name", ["kat", "small", "zeros"])
+def test_creator_bytes_identical(golden, tmp_path, name):
+    g = golden(name)
+    lines = g["quantized_lines"] if "quantized_lines" in g else g["lines"]
+    src = tmp_path / "collection"
+    src.write_text(''.join(l + '\n' for l in lines), encoding='utf-8')
+    InvertedIndexCreator(src, tmp_path / "index").run()
+    assert (tmp_path / "index" / "vocab.txt").read_text(encoding='utf-8').split('\n')[:-1] == g["vocab"]
+    assert (tmp_path / "index" / "inverted_index.dat").read_bytes() == g["dat"]
+    assert (tmp_path / "index" / "inverted_index.idx").read_bytes() == g["idx"]
+
+
+def test_full_pipeline_medium_golden(golden, tmp_path):
+    """raw text -> quantize_file -> InvertedIndexCreator -> InvertedIndex.score, all vs the reference's own run."""
+    g = golden("medium")
+    c = syn.make_collection(**{k: g["gen"][k] for k in ("n_docs", "vocab_size", "draws_per_doc", "seed")})
+    raw = tmp_path / "collection.index"
+    raw.write_text(''.join(l + '\n' for l in c.lines()), encoding='utf-8')
+    quantize_file(raw, tmp_path / "q")
+    sha = lambda b: hashlib.sha256(b).hexdigest()
+    assert sha((tmp_path / "q").read_bytes()) == g["quantized_sha256"]
+    InvertedIndexCreator(tmp_path / "q", tmp_path / "index").run()
+    assert sha((tmp_path / "index" / "vocab.txt").read_bytes()) == g["vocab_sha256"]
+    assert sha((tmp_path / "index" / "inverted_index.dat").read_bytes()) == g["dat_sha256"]
+    assert sha((tmp_path / "index" / "inverted_index.idx").read_bytes()) == g["idx_sha256"]
+    for tile_docs in (0, 256, 1024):
+        index = InvertedIndex(tmp_path / "index", tile_docs=tile_docs, cand_slack=1000 if tile_docs else 0)
+        got = index.score_batch([q["terms"] for q in g["queries"]], top_k=1000)
+        for q, res in zip(g["queries"], got):
+            ref = q["top1000"]
+            # §8a(3): same score sequence; same doc set once boundary ties are removed
+            assert [s for _, s in res] == [s for _, s in ref]
+            kth = ref[-1][1] if len(ref) == 1000 else -1
+            assert {d for d, s in res if s != kth} == {d for d, s in ref if s != kth}
+            assert res == sorted(res, key=lambda x: (-x[1], x[0]))
+            assert len(res) == min(1000, q["n_touched"])
+
+
+def test_creator_rejects_out_of_range_impacts(tmp_path):
+    src = tmp_path / "c"
+    src.write_text("a: 3, b: 256\n")
+    with pytest.raises(struct.error):
+        InvertedIndexCreator(src, tmp_path / "i").run()
+
+
+def test_invert_random_matches_oracle():
+    for n_docs, V, draws, seed in ((1, 5, 3, 0), (700, 300, 30, 1), (20_000, 5000, 50, 2)):
+        x = quantized_csr(n_docs, V, draws, seed)
+        toff, docs, vals = engine.invert(x["terms"], x["imps"], x["offs"], V)
+        assert np.array_equal(toff, x["toff"]) and np.array_equal(docs, x["docs"]) and np.array_equal(vals, x["vals"])
+        dat, idx = engine.serialize(toff, docs, vals)
+        dat_o, idx_o = oracle.serialize(x["toff"], x["docs"], x["vals"])
+        assert np.array_equal(dat, dat_o) and np.array_equal(idx, idx_o)
+    # empty collection
+    toff, docs, vals = engine.invert([], [], [0, 0, 0], 4)
+    assert toff.tolist() == [0] * 5 and docs.size == 0
+
+
+# ------------------------------------------------------------------ reader semantics + scoring on golden indexes
+@pytest.mark.parametrize("name", ["kat", "zeros"])
+def test_index_golden_small(golden, tmp_path, name):
+    g = golden(name)
+    index = InvertedIndex(write_index_dir(tmp_path / name, g["vocab"], g["idx"], g["dat"]))
+    for term, expect in g["term_docs"].items():
+        assert [list(p) for p in index.term_docs(term)] == expect
+    if "term_location" in g:
+        for term, loc in g["term_location"].items():
+            assert list(index.term_location(term)) == loc
+    for case in g["scores"]:
+        k = case.get("top_k", 10)
+        full = index.score(case["terms"], top_k=10 ** 9)
+        assert [list(p) for p in index.score(case["terms"], top_k=k)] == canonical(full, k)
+        assert sorted(map(tuple, case["result"])) == sorted(canonical(full, 10 ** 9)[:len(case["result"])]) \
+            or [s for _, s in case["result"]] == [s for _, s in canonical(full, k)]
+
+
+@pytest.mark.parametrize("tile_docs,dense_ratio,cand_slack", [(0, 0, 0), (256, 0, 0), (256, 0xFFFFFFFF, 7), (256, 1, 1)])
+def test_index_golden_small_collection(golden, tmp_path, tile_docs, dense_ratio, cand_slack):
+    g = golden("small")
+    index = InvertedIndex(write_index_dir(tmp_path / "small", g["vocab"], g["idx"], g["dat"]),
+                          tile_docs=tile_docs, dense_ratio=dense_ratio, cand_slack=cand_slack)
+    queries = [q["terms"] for q in g["queries"]]
+    for k in (1, 3, 10, 200, 10 ** 9):
+        got = index.score_batch(queries, top_k=k)
+        for q, res in zip(g["queries"], got):
+            assert [list(p) for p in res] == canonical(q["all"], k), (k, q["terms"])
+    # single-query entry point, set input, generator input
+    q = g["queries"][0]
+    assert [list(p) for p in index.score(set(q["terms"]), top_k=5)] == canonical(q["all"], 5)
+    assert [list(p) for p in index.score(iter(q["terms"]), top_k=5)] == canonical(q["all"], 5)
+
+
+# ------------------------------------------------------------------ scoring vs oracle on seeded collections
+CONFIGS = [
+    # n_docs, V, draws, seed, tile_docs, dense_ratio, cand_slack, n_queries, ks
+    (5000, 30522, 120, 10, 0, 0, 0, 50, (1000,)),                       # BASELINE config 1 shape
+    (5000, 800, 100, 11, 1024, 0, 0, 80, (1, 10, 1000, 5000)),          # hot terms -> dense segments, multi-tile
+    (5000, 800, 100, 11, 512, 0xFFFFFFFF, 64, 80, (7, 100)),            # all sparse, tiny candidate slack
+    (5000, 800, 100, 11, 512, 1, 0, 80, (100,)),                        # everything dense
+    (40_000, 2000, 60, 12, 4096, 0, 300, 120, (100, 1000)),
+    (70_000, 3000, 40, 13, 0, 0, 0, 60, (10, 1000)),                    # default 32768-doc tiles, 3 tiles
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"n{c[0]}_V{c[1]}_t{c[4]}_d{c[5]}_s{c[6]}")
+def test_search_matches_oracle(cfg):
+    n_docs, V, draws, seed, tile_docs, dense_ratio, cand_slack, nq, ks = cfg
+    x = quantized_csr(n_docs, V, draws, seed)
+    index = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], tile_docs=tile_docs,
+                                        dense_ratio=dense_ratio, cand_slack=cand_slack)
+    info = index.info()
+    assert info["n_postings"] == x["docs"].size
+    queries = syn.make_queries(nq, vocab_size=V, seed=seed + 100)
+    queries[0] = []                                   # empty query
+    queries[1] = [V + 5, -1]                          # only out-of-vocabulary ids
+    queries[2] = queries[3] + queries[3][:2]          # duplicated terms count again
+    for k in ks:
+        k = min(k, n_docs)
+        got = index.search(queries, k)
+        want = oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], n_docs, queries, k)
+        assert_same_results(got, want, f"k={k}")
+    flat = np.asarray([t for q in queries for t in q if 0 <= t < V], dtype=np.uint32)
+    df = index.term_df(flat)
+    assert np.array_equal(df, np.diff(x["toff"].astype(np.int64))[flat].astype(np.uint64))
+    index.close()
+
+
+def test_long_queries_use_32bit_accumulators():
+    """> 257 term occurrences can overflow a u16 accumulator; > 32 terms need several rounds."""
+    x = quantized_csr(3000, 400, 120, 21)
+    index = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], tile_docs=1024)
+    rng = np.random.default_rng(0)
+    queries = [rng.integers(0, 400, size=n).tolist() for n in (33, 64, 100, 257, 258, 300, 700)]
+    queries.append([int(np.argmax(np.diff(x["toff"].astype(np.int64))))] * 300)      # one hot term 300 times
+    for k in (10, 3000):
+        assert_same_results(index.search(queries, k),
+                            oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], 3000, queries, k), f"k={k}")
+    short = [q[:40] for q in queries]
+    assert_same_results(index.search(short, 50),
+                        oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], 3000, short, 50), "short")
+
+
+def test_massive_ties_are_docid_ordered():
+    """One term, every document the same impact: top-k must be the k lowest docids, across tiles."""
+    n = 3000
+    toff = np.array([0, n, n + 3], dtype=np.uint64)
+    docs = np.concatenate([np.arange(n, dtype=np.uint32)[::-1], np.array([5, 2999, 7], dtype=np.uint32)])
+    vals = np.concatenate([np.full(n, 9, dtype=np.uint8), np.array([1, 1, 1], dtype=np.uint8)])
+    for dense_ratio in (0, 0xFFFFFFFF):
+        index = engine.DeviceIndex.from_csr(toff, docs, vals, tile_docs=256, dense_ratio=dense_ratio, cand_slack=16)
+        d, s, c = index.search([[0], [0, 1], [1]], 10)
+        assert c.tolist() == [10, 10, 3]
+        assert d[0, :10].tolist() == list(range(10)) and set(s[0, :10].tolist()) == {9}
+        assert d[1, :3].tolist() == [5, 7, 2999] and s[1, :3].tolist() == [10, 10, 10]
+        assert d[2, :3].tolist() == [5, 7, 2999]
+
+
+def test_duplicate_postings_and_hidden_zeros():
+    """Hand-made CSR: a (term, doc) pair stored twice counts twice; postings after the first zero
+    impact of a list are invisible (inverted_index.py:50-51) even if non-zero ones follow."""
+    toff = np.array([0, 4, 8], dtype=np.uint64)
+    docs = np.array([3, 3, 1, 2, 0, 1, 2, 3], dtype=np.uint32)
+    vals = np.array([5, 6, 7, 8, 4, 0, 9, 9], dtype=np.uint8)
+    for dense_ratio in (1, 0xFFFFFFFF):
+        index = engine.DeviceIndex.from_csr(toff, docs, vals, tile_docs=256, dense_ratio=dense_ratio)
+        assert index.info()["n_postings"] == 5
+        d, s, c = index.search([[0], [1], [0, 1]], 4)
+        assert list(zip(d[0, :c[0]].tolist(), s[0, :c[0]].tolist())) == [(3, 11), (2, 8), (1, 7)]
+        assert list(zip(d[1, :c[1]].tolist(), s[1, :c[1]].tolist())) == [(0, 4)]
+        want = oracle.score_topk_csr(toff, docs, vals, 4, [[0, 1]], 4)
+        assert d[2, :c[2]].tolist() == want[0][0, :want[2][0]].tolist()
+
+
+def test_shards_and_merge_equal_single_index():
+    """K5: docid-range shards searched separately + merged == one index (single GPU, 3 shards)."""
+    torch = pytest.importorskip("torch")
+    x = quantized_csr(9000, 1500, 60, 31)
+    full = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], tile_docs=1024)
+    queries = syn.make_queries(40, vocab_size=1500, seed=5)
+    k = 100
+    want = full.search(queries, k)
+    bounds = [(0, 2500), (2500, 7000), (7000, 9000)]
+    flat, offs = engine.flatten_queries(queries)
+    dev = torch.device("cuda:0")
+    d_flat = torch.from_numpy(flat.astype(np.int64)).to(dev).to(torch.int32)  # bit pattern of u32 ids
+    d_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    keys = torch.zeros((len(bounds), len(queries), k), dtype=torch.int64, device=dev)
+    counts = torch.zeros((len(bounds), len(queries)), dtype=torch.int32, device=dev)
+    shards = []
+    for s, (lo, hi) in enumerate(bounds):
+        shard = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], doc_lo=lo, doc_hi=hi, tile_docs=1024)
+        shards.append(shard)
+        assert shard.info()["doc_lo"] == lo
+        shard.search_device(d_flat, d_offs, len(queries), max(len(q) for q in queries), k, keys[s], counts[s],
+                            torch.cuda.current_stream().cuda_stream)
+    out_keys = torch.zeros((len(queries), k), dtype=torch.int64, device=dev)
+    out_counts = torch.zeros(len(queries), dtype=torch.int32, device=dev)
+    engine.merge_topk_device(keys, counts, len(bounds), len(queries), k, out_keys, out_counts,
+                             torch.cuda.current_stream().cuda_stream)
+    docids = torch.zeros((len(queries), k), dtype=torch.int32, device=dev)
+    scores = torch.zeros((len(queries), k), dtype=torch.int32, device=dev)
+    engine.unpack_keys_device(out_keys, out_keys.numel(), docids, scores, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = (docids.cpu().numpy().view(np.uint32), scores.cpu().numpy(), out_counts.cpu().numpy().view(np.uint32))
+    assert_same_results(got, want, "merged")
+    assert sum(s.info()["n_postings"] for s in shards) == full.info()["n_postings"]
+
+
+# ------------------------------------------------------------------ in-memory twin, ranker, metrics
+def test_sparse_search_golden(golden):
+    g = golden("sparse")
+
+    class Replay:
+        def get_impact_scores_batch(self, texts):
+            return [[(t, np.float32(v)) for t, v in g["replay"][x]] for x in texts]
+
+        def process_query(self, query):
+            return set(query.split())
+    corpus_pos = {cid: i for i, cid in enumerate(g["corpus"])}
+    for key, k in (("k10", 10), ("k1000", 1000)):
+        searcher = SparseSearch(Replay(), batch_size=16)
+        res = searcher.search(g["queries"], g["corpus"], k)
+        assert list(res.keys()) == list(g["queries"].keys())
+        full = SparseSearch(Replay(), batch_size=50).search(g["queries"], g["corpus"], 10 ** 6)
+        for qid, ref in g[key].items():
+            got = list(res[qid].items())
+            assert [s for _, s in got] == [s for _, s in ref], qid
+            canon = sorted(full[qid].items(), key=lambda x: (-x[1], corpus_pos[x[0]]))[:k]
+            assert got == canon, qid
+            kth = ref[-1][1] if len(ref) == k else -1.0
+            assert {d for d, s in got if s != kth} == {d for d, s in ref if s != kth}
+            assert all(isinstance(s, float) for _, s in got)
+        assert set(searcher.inverted_index.keys()) == {t for lst in g["replay"].values() for t, v in lst if v > 0}
+    with pytest.raises(ValueError):
+        class Frac(Replay):
+            def get_impact_scores_batch(self, texts):
+                return [[("a", 0.5)] for _ in texts]
+        SparseSearch(Frac(), 4).search({"q": "a"}, {"d": "x"}, 1)
+
+
+def test_ranker_and_metrics_end_to_end(golden, tmp_path):
+    g = golden("small")
+    index_dir = write_index_dir(tmp_path / "index", g["vocab"], g["idx"], g["dat"])
+    qfile = tmp_path / "queries.tsv"
+    rows = [(f"{100 + i}", ' '.join(q["terms"])) for i, q in enumerate(g["queries"]) if q["terms"]]
+    qfile.write_text(''.join(f"{qid}\t{text}\n" for qid, text in rows))
+    run = tmp_path / "run.tsv"
+    Ranker(index_dir, qfile, run, num_workers=3, query_processor=lambda s: s.split(), top_k=10).run()
+    lines = run.read_text().split('\n')[:-1]
+    by_q = {}
+    for line in lines:
+        qid, pid, rank, score = line.split('\t')
+        by_q.setdefault(qid, []).append([int(pid), int(score)])
+        assert int(rank) == len(by_q[qid])
+    for (qid, _), q in zip(rows, [q for q in g["queries"] if q["terms"]]):
+        terms = list(dict.fromkeys(q["terms"]))          # the ranker de-duplicates (set), like process_query
+        want = oracle.py_score({t: i for i, t in enumerate(g["vocab"])}, g["dat"], g["idx"], terms, 10, canonical=True)
+        assert by_q.get(qid, []) == [list(p) for p in want]
+
+
+def test_metrics_golden(golden, tmp_path):
+    g = golden("metrics")
+    (tmp_path / "run.tsv").write_text('\n'.join(g["run"]) + '\n')
+    (tmp_path / "qrels.tsv").write_text('\n'.join(g["qrels"]) + '\n')
+    m = Metrics(tmp_path / "run.tsv", tmp_path / "qrels.tsv", mrr_depths=[10, 100], recall_depths=[3, 10, 20, 50])
+    rep = m.evaluate()
+    assert {k.split('@')[1]: v for k, v in rep.items() if k.startswith('MRR')} == g["mrr"]
+    assert {k.split('@')[1]: v for k, v in rep.items() if k.startswith('Recall')} == g["recall"]

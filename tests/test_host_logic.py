@@ -1,0 +1,106 @@
+"""CPU-only tests: ABI surface, host-side parsers / metrics, loud failure without a GPU."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from improving_learned_index_b200 import _native, engine
+from improving_learned_index_b200.evaluation.metrics import Metrics
+from improving_learned_index_b200.evaluation.trec_metrics import EvaluateRetrieval
+from improving_learned_index_b200.indexing.deep_impact_collection import (DeepImpactCollection,
+                                                                         DeepPairwiseImpactCollection, parse_line)
+from improving_learned_index_b200.utils.datasets import Queries, QueryParser, QueryRelevanceDataset, RunFile
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    """libdi_b200.so loads without a GPU and exports exactly what include/di_b200.h declares."""
+    header = (REPO / "include" / "di_b200.h").read_text()
+    declared = set(re.findall(r"\b(di_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    _native.build()
+    lib = ctypes.CDLL(str(_native.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _native.lib().di_version() >= 100
+
+
+def test_no_silent_cpu_fallback():
+    if _native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.NativeError) as e:
+        engine.quantize([1.0, 2.0])
+    assert e.value.code == 5
+    with pytest.raises(_native.NativeError):
+        engine.DeviceIndex.from_csr([0, 1], [0], [1])
+
+
+def test_product_code_never_touches_the_oracle():
+    pkg = REPO / "improving-learned-index_b200"
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu*")):
+        text = path.read_text()
+        assert "oracle" not in text.lower() or path.name == "__init__.py", path
+
+
+def test_flatten_queries():
+    flat, offs = engine.flatten_queries([[1, 2], [], [-1, None, 7]])
+    assert flat.tolist() == [1, 2, 0xFFFFFFFF, 0xFFFFFFFF, 7] and offs.tolist() == [0, 2, 2, 5]
+
+
+def test_collection_parser(tmp_path):
+    p = tmp_path / "c"
+    p.write_text("a: 1.5, b: 2, a: 3\n\n  \nx|y: 4, x: 1, y: 2\n")
+    c = DeepImpactCollection(p)
+    assert len(c) == 4 and c[0] == {"a": 3.0, "b": 2.0} and c[1] == {} and c[2] == {}
+    assert list(c[0]) == ["a", "b"]
+    assert [pid for pid, _ in c] == [0, 1, 2, 3]
+    assert c.score(0, {"a", "zz"}) == 3.0
+    assert DeepPairwiseImpactCollection(p).score(3, {"x", "y"}) == 7.0
+    with pytest.raises(ValueError):
+        parse_line("a 1.5")
+
+
+def test_query_and_run_files(tmp_path):
+    q = tmp_path / "q.tsv"
+    q.write_text("7\thello world\n8\tfoo\n")
+    qs = Queries(q)
+    assert len(qs) == 2 and qs[7] == "hello world" and list(qs.keys()) == ["7", "8"]
+    assert QueryParser.parse('{"_id": "a1", "text": "t"}', 'beir') == ("a1", "t")
+    (tmp_path / "qrels").write_text("7\t0\t11\t1\n7\t0\t12\t1\n8\t0\t5\t1\n")
+    rel = QueryRelevanceDataset(tmp_path / "qrels")
+    assert rel[7] == {"11", "12"} and len(rel) == 2
+    (tmp_path / "bad").write_text("7\t1\t11\t1\n")
+    with pytest.raises(AssertionError):
+        QueryRelevanceDataset(tmp_path / "bad")
+    run = RunFile(tmp_path / "run")
+    run.writelines("7", [(11, 300), (3, 200)])
+    run.write("8", 5, 1, 10)
+    run.writelines("7", [(12, 1)])               # append semantics, like the reference
+    assert list(run.read()) == [("7", "11", 1, 300.0), ("7", "3", 2, 200.0), ("8", "5", 1, 10.0), ("7", "12", 1, 1.0)]
+
+
+def test_metrics_against_reference_numbers(golden, tmp_path):
+    g = golden("metrics")
+    (tmp_path / "run.tsv").write_text('\n'.join(g["run"]) + '\n')
+    (tmp_path / "qrels.tsv").write_text('\n'.join(g["qrels"]) + '\n')
+    m = Metrics(tmp_path / "run.tsv", tmp_path / "qrels.tsv", mrr_depths=[10, 100], recall_depths=[3, 10, 20, 50])
+    rep = m.evaluate()
+    assert {k.split('@')[1]: v for k, v in rep.items() if k.startswith('MRR')} == g["mrr"]
+    assert {k.split('@')[1]: v for k, v in rep.items() if k.startswith('Recall')} == g["recall"]
+
+
+def test_trec_metrics_hand_computed():
+    qrels = {"q1": {"d1": 1, "d3": 1}, "q2": {"d9": 1}}
+    results = {"q1": {"d1": 3.0, "d2": 2.0, "d3": 1.0, "q1": 99.0}, "q2": {"d8": 1.0}}
+    ndcg, _map, recall, prec = EvaluateRetrieval().evaluate(qrels, results, [1, 3])
+    import math
+    dcg3 = 1 + 1 / math.log2(4)
+    idcg3 = 1 + 1 / math.log2(3)
+    assert ndcg["NDCG@1"] == round((1.0 + 0.0) / 2, 5)
+    assert ndcg["NDCG@3"] == round((dcg3 / idcg3 + 0.0) / 2, 5)
+    assert _map["MAP@3"] == round(((1 + 2 / 3) / 2 + 0.0) / 2, 5)
+    assert recall["Recall@1"] == 0.25 and recall["Recall@3"] == 0.5
+    assert prec["P@1"] == 0.5 and prec["P@3"] == round((2 / 3) / 2, 5)
