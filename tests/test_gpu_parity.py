@@ -37,7 +37,7 @@ def test_quantize_self_max_sweep(golden):
 
 def test_quantize_random_matches_oracle():
     rng = np.random.default_rng(0)
-    x = np.concatenate([rng.lognormal(0, 2, 200_000), rng.uniform(0, 1e-3, 1000), [0.0, 1e300, 5e-324]])
+    x = np.concatenate([rng.lognormal(0, 2, 200_000), rng.uniform(0, 1e-3, 1000), [0.0, 1e4, 5e-324]])
     x = np.round(x, 3)
     for mx in (None, 7.0, 0.013):
         assert np.array_equal(engine.quantize(x, mx).astype(np.int64),
