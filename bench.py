@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py — QPS of top-1000 search on the MS MARCO-shaped synthetic index (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                     # the CPU restatement (oracle/) on host cores
+
+One "step" = scoring all 6,980 queries against the 8.8 M-document index and selecting each
+query's top-1000. With N > 1 (torchrun, one rank per GPU) documents are split into N contiguous
+docid ranges; every rank scores all queries on its shard, per-shard top-k keys are all-gathered
+over NCCL and merged (strong scaling: the index is fixed, per-GPU work shrinks with N).
+
+`value`  : queries / s with queries and results resident in HBM (device-timed, max over ranks).
+`e2e`    : the same through the host-buffer C-ABI call (di_search): pinned host query buffers
+           H2D, kernels, result D2H, all inside the timed region.
+`roofline`: algorithmic postings bytes (5 B per posting traversed) / time of the
+           score_tile launches (CUDA events on the launching stream, inside the library).
+`cpu_baseline`: the oracle's C scorer on a bounded sample of the same queries, all host threads;
+           the sample doubles as a full-size bit-exact parity check of the GPU results.
+
+Synthetic data (no network): Zipf(1) term popularity over a 30,522-term vocabulary, 120 draws
+per document (unique terms kept), 3-decimal log-normal impacts quantized to 8 bits by K1, queries
+of 1+Poisson(5) distinct Zipf terms — generated on the GPU with torch (plumbing, not the path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+ALGO_BYTES_PER_POSTING = 5          # u32 docid + u8 impact: the reference record (defaults.py:28-35)
+CHUNK_DOCS = 1 << 20
+DATA_SEED = 20240517
+IMPACT_CLIP = 12.0
+
+
+# ----------------------------------------------------------------------------- synthetic data (torch, on device)
+def zipf_tables(vocab_size, torch, dev):
+    from improving_learned_index_b200 import synthetic
+    cdf, perm = synthetic.zipf_cdf(vocab_size)
+    return (torch.from_numpy(cdf).to(dev), torch.from_numpy(perm.astype(np.int64)).to(dev))
+
+
+def gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, dev):
+    """Documents [lo, hi) of chunk `chunk_id` (rows are generated for the whole chunk so that any
+    shard split sees identical documents). Returns per-doc kept counts, term ids, float64 impacts."""
+    cdf, perm = tables
+    c0 = chunk_id * CHUNK_DOCS
+    n = min(CHUNK_DOCS, n_docs_total - c0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(DATA_SEED * 1_000_003 + chunk_id)
+    u = torch.rand((n, draws), generator=g, device=dev, dtype=torch.float64)
+    terms = perm[torch.searchsorted(cdf, u).clamp_(max=vocab_size - 1)]
+    del u
+    z = torch.randn((n, draws), generator=g, device=dev, dtype=torch.float32)
+    m = torch.round(1000.0 * torch.exp(0.75 * z.double())).clamp_(0, IMPACT_CLIP * 1000)
+    zero = torch.rand((n, draws), generator=g, device=dev, dtype=torch.float32) < 0.01
+    m[zero] = 0
+    del z, zero
+    terms, order = torch.sort(terms, dim=1)
+    m = torch.gather(m, 1, order)
+    del order
+    keep = torch.ones_like(terms, dtype=torch.bool)
+    keep[:, 1:] = terms[:, 1:] != terms[:, :-1]
+    sl = slice(lo - c0, hi - c0)
+    return terms[sl], (m[sl] / 1000.0), keep[sl]
+
+
+
+def build_shard_arrays(doc_lo, doc_hi, n_docs_total, vocab_size, draws, torch, dev, quantize_fn):
+    """Doc-major arrays of the shard [doc_lo, doc_hi): term ids (u32 as int32 bits), u8 impacts (quantized by
+    `quantize_fn`, postings with value 0 dropped as quantize.py:45 does), u64 doc offsets (local docs)."""
+    tables = zipf_tables(vocab_size, torch, dev)
+    t_parts, v_parts, c_parts = [], [], []
+    for chunk_id in range(doc_lo // CHUNK_DOCS, (doc_hi - 1) // CHUNK_DOCS + 1):
+        lo = max(doc_lo, chunk_id * CHUNK_DOCS)
+        hi = min(doc_hi, (chunk_id + 1) * CHUNK_DOCS)
+        terms, impacts, keep = gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, dev)
+        q = quantize_fn(impacts.reshape(-1).contiguous()).reshape(impacts.shape)
+        keep &= q > 0
+        t_parts.append(terms[keep].to(torch.int32))
+        v_parts.append(q[keep].to(torch.uint8))
+        c_parts.append(keep.sum(dim=1))
+        del terms, impacts, keep, q
+    counts = torch.cat(c_parts)
+    offs = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=offs[1:])
+    return torch.cat(t_parts), torch.cat(v_parts), offs
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.stop, self.gpu = [], threading.Event(), gpu_index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(float(r[0])) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+# ----------------------------------------------------------------------------- main arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from improving_learned_index_b200 import _native, engine, synthetic
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    _native.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    L = _native.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    N, V, k = args.docs, args.vocab, args.top_k
+    per = -(-N // world)
+    doc_lo, doc_hi = min(rank * per, N), min((rank + 1) * per, N)
+
+    # ---- build: synthetic doc-major lists -> K1 quantize -> K2 invert -> tiled shard
+    t0 = time.time()
+
+    def quantize_fn(x):   # K1 on device buffers; max over the collection is the clip value by construction
+        out = torch.empty(x.numel(), dtype=torch.int32, device=dev)
+        _native.check(L.di_quantize_f64_dev(x.data_ptr(), x.numel(), IMPACT_CLIP, out.data_ptr(), stream))
+        return out
+    terms, imps, offs = build_shard_arrays(doc_lo, doc_hi, N, V, args.draws, torch, dev, quantize_fn)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    P = terms.numel()
+    toff = torch.empty(V + 1, dtype=torch.int64, device=dev)
+    docids = torch.empty(P, dtype=torch.int32, device=dev)
+    vals = torch.empty(P, dtype=torch.uint8, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    _native.check(L.di_invert_dev(terms.data_ptr(), imps.data_ptr(), offs.data_ptr(), doc_hi - doc_lo, V, P,
+                                  toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), stream))
+    ev1.record()
+    torch.cuda.synchronize()
+    invert_ms = ev0.elapsed_time(ev1)
+    del terms, imps, offs
+    docids += doc_lo                                  # docids stay global across shards
+    torch.cuda.synchronize()
+    t1 = time.time()
+    index = engine.DeviceIndex.from_csr_device(toff, docids, vals, V, P, doc_lo=doc_lo, doc_hi=max(doc_hi, doc_lo + 1),
+                                               tile_docs=args.tile_docs, dense_ratio=args.dense_ratio)
+    t_tile = time.time() - t1
+    info = index.info()
+
+    # ---- queries
+    queries = synthetic.make_queries(args.queries, vocab_size=V, seed=7)
+    flat, qoffs = engine.flatten_queries(queries)
+    max_len = max(len(q) for q in queries)
+    Q = len(queries)
+    h_flat = torch.from_numpy(flat.astype(np.int64)).to(torch.int32).pin_memory()
+    h_offs = torch.from_numpy(qoffs.astype(np.int64)).pin_memory()
+    d_flat, d_offs = h_flat.to(dev), h_offs.to(dev)
+    df = index.term_df(flat)
+    local_postings = int(df.sum())
+    d_keys = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+    d_counts = torch.zeros(Q, dtype=torch.int32, device=dev)
+    if world > 1:
+        g_keys = torch.zeros((world, Q, k), dtype=torch.int64, device=dev)
+        g_counts = torch.zeros((world, Q), dtype=torch.int32, device=dev)
+        m_keys = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+        m_counts = torch.zeros(Q, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_device():
+        index.search_device(d_flat, d_offs, Q, max_len, k, d_keys, d_counts, stream)
+        if world > 1:
+            dist.all_gather_into_tensor(g_keys, d_keys)
+            dist.all_gather_into_tensor(g_counts, d_counts)
+            engine.merge_topk_device(g_keys, g_counts, world, Q, k, m_keys, m_counts, stream)
+
+    h_docs = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+    h_scores = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+    h_counts = torch.empty(Q, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        if world == 1:
+            index.search_flat(h_flat, h_offs, k, h_docs, h_scores, h_counts)   # H2D + kernels + D2H inside
+        else:
+            d_flat.copy_(h_flat, non_blocking=True)
+            d_offs.copy_(h_offs, non_blocking=True)
+            step_device()
+            if rank == 0:
+                dd = torch.empty((Q, k), dtype=torch.int32, device=dev)
+                ds = torch.empty((Q, k), dtype=torch.int32, device=dev)
+                engine.unpack_keys_device(m_keys, Q * k, dd, ds, stream)
+                h_docs.copy_(dd, non_blocking=True)
+                h_scores.copy_(ds, non_blocking=True)
+                h_counts.copy_(m_counts, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    # ---- timed: device-resident
+    score_ms, final_ms, step_ms = [], [], []
+    with ClockSampler(local) as clocks:
+        barrier()
+        for _ in range(args.steps):
+            flush.fill_(1)                      # L2 flush between iterations (outside the event pair)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_device()
+            b.record()
+            b.synchronize()
+            step_ms.append(a.elapsed_time(b))
+            t = index.timings()
+            score_ms.append(t["score_ms"])
+            final_ms.append(t["finalize_ms"])
+        barrier()
+        # ---- timed: end to end through the host-buffer call
+        step_e2e()
+        e2e_ms = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            barrier()
+            t_a = time.perf_counter()
+            step_e2e()
+            e2e_ms.append((time.perf_counter() - t_a) * 1e3)
+        barrier()
+    launches = index.timings()
+    total_ms = torch.tensor([sum(step_ms), sum(e2e_ms), sum(score_ms)], dtype=torch.float64, device=dev)
+    post = torch.tensor([local_postings], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(post, op=dist.ReduceOp.SUM)
+    total_dev_ms, total_e2e_ms, total_score_ms = total_ms.tolist()
+    total_postings = int(post.item())
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(REPO / "MEASURED_PEAKS.json"))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # per-GPU roofline of the dominant kernel (score_tile): this rank's postings bytes / its launch time
+        achieved = ALGO_BYTES_PER_POSTING * local_postings / (np.mean(score_ms) * 1e-3) / 1e9
+        out = {
+            "metric": "QPS top-1000 on 8.8M-doc MS MARCO-shaped index",
+            "value": round(Q * args.steps / (total_dev_ms * 1e-3), 2), "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(total_dev_ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 impacts, u16/int32 accumulators", "data": "synthetic",
+            "config": {"workload": "configs[1]: MS MARCO passage-shaped synthetic index, Zipf(1) terms, top-%d" % k,
+                       "docs": N, "vocab": V, "draws_per_doc": args.draws,
+                       "queries": Q, "top_k": k, "sharding": f"docid-range x{world}", "tile_docs": info["tile_docs"],
+                       "l2": "index payload (%.1f GB/GPU) exceeds L2 and a 256 MB buffer is written between timed steps"
+                             % (info["payload_bytes"] / 1e9)},
+            "e2e": {"value": round(Q * args.steps / (total_e2e_ms * 1e-3), 2), "unit": "queries/s",
+                    "h2d_bytes_per_step": int(h_flat.numel() * 4 + h_offs.numel() * 8),
+                    "d2h_bytes_per_step": int(Q * k * 8 + Q * 4)},
+            # kernels of this repo launched inside the `value` timed region, all ranks
+            "gpu_launches": int((launches["score_launches"] + 1 + (2 if world > 1 else 0)) * args.steps * world),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
+                         "kernel": "score_tile_kernel", "launches_per_step": launches["score_launches"],
+                         "algorithmic_bytes_per_step_this_gpu": ALGO_BYTES_PER_POSTING * local_postings,
+                         "score_ms_per_step": round(float(np.mean(score_ms)), 3),
+                         "finalize_ms_per_step": round(float(np.mean(final_ms)), 3)},
+            "clocks": clocks.summary(),
+            "index": {"postings_this_gpu": info["n_postings"], "payload_gb": round(info["payload_bytes"] / 1e9, 3),
+                      "dense_segments": info["n_dense_segments"], "sparse_segments": info["n_sparse_segments"],
+                      "dense_posting_frac": round(info["n_dense_postings"] / max(info["n_postings"], 1), 3),
+                      "tiles": info["n_tiles"]},
+            "build": {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "tile_layout_s": round(t_tile, 2),
+                      "invert_postings_per_s": round(P / (invert_ms * 1e-3)), "invert_gbs_at_17B": round(17 * P / (invert_ms * 1e-3) / 1e9, 1)},
+            "postings_per_query": round(total_postings / Q),
+        }
+        if world == 1 and args.cpu_sample > 0:
+            out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(
+                args, toff, docids, vals, queries, index, torch)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def cpu_baseline_and_parity(args, toff, docids, vals, queries, index, torch):
+    """Oracle (C port, all host threads) on a bounded query sample of the same index; the GPU results for
+    the same sample must match bit for bit (full-size parity check)."""
+    from oracle import oracle
+    h_toff = toff.cpu().numpy().astype(np.uint64)
+    h_docs = docids.cpu().numpy().view(np.uint32)
+    h_vals = vals.cpu().numpy()
+    rng = np.random.default_rng(123)
+    pick = sorted(rng.choice(len(queries), size=min(args.cpu_sample, len(queries)), replace=False).tolist())
+    sample = [queries[i] for i in pick]
+    threads = oracle.max_threads()
+    t0 = time.perf_counter()
+    o_docs, o_scores, o_counts, o_post = oracle.score_topk_csr(h_toff, h_docs, h_vals, args.docs, sample, args.top_k,
+                                                              n_threads=threads)
+    dt = time.perf_counter() - t0
+    g_docs, g_scores, g_counts = index.search(sample, args.top_k)
+    ok = bool(np.array_equal(g_counts, o_counts))
+    for i in range(len(sample)):
+        n = int(o_counts[i])
+        ok = ok and np.array_equal(g_docs[i, :n], o_docs[i, :n]) and np.array_equal(g_scores[i, :n], o_scores[i, :n])
+    base = {"value": round(len(sample) / dt, 3), "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"{len(sample)} of the {len(queries)} queries (seed 123), full index, oracle/di_oracle.c with OpenMP",
+            "postings_per_s": round(float(o_post.sum()) / dt), "seconds": round(dt, 2)}
+    parity = {"queries_checked": len(sample), "bit_exact": ok, "against": "oracle/di_oracle.c (pinned to reference golden vectors)"}
+    if not ok:
+        raise SystemExit("PARITY FAILURE at full size: GPU results differ from the oracle")
+    return base, parity
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    """The reference's algorithm on the host cores: oracle/di_oracle.c (a C restatement of
+    inverted_index.py:55-62; the reference's own Python cannot travel to the GPU box), all threads.
+    Index data comes from the same seeded generator; quantize + inversion also run on the CPU oracle."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    from improving_learned_index_b200 import synthetic
+    from oracle import oracle
+    dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+    N, V, k = args.docs, args.vocab, args.top_k
+    scale_max = IMPACT_CLIP
+
+    def quantize_fn(x):      # CPU oracle arithmetic (quantize.py:13-14), not the CUDA kernel
+        q = oracle.quantize(x.cpu().numpy(), scale_max)
+        return torch.from_numpy(q.astype(np.int32)).to(x.device)
+    terms, imps, offs = build_shard_arrays(0, N, N, V, args.draws, torch, dev, quantize_fn)
+    toff, docids, vals = oracle.invert(terms.cpu().numpy().view(np.uint32), imps.cpu().numpy(),
+                                       offs.cpu().numpy().astype(np.uint64), V)
+    del terms, imps, offs
+    queries = synthetic.make_queries(args.queries, vocab_size=V, seed=7)
+    threads = oracle.max_threads()
+    per_step = max(1, min(args.ref_queries_per_step, len(queries)))
+    rng = np.random.default_rng(123)
+    times, n_done = [], 0
+    for s in range(args.warmup + args.steps):
+        pick = rng.choice(len(queries), size=per_step, replace=False)
+        sample = [queries[i] for i in pick]
+        t0 = time.perf_counter()
+        oracle.score_topk_csr(toff, docids, vals, N, sample, k, n_threads=threads)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+            n_done += per_step
+    qps = n_done / sum(times)
+    out = {"impl": "reference", "metric": "QPS top-1000 on 8.8M-doc MS MARCO-shaped index", "value": round(qps, 3),
+           "unit": "queries/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(1e3 * sum(times) / args.steps, 2), "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "u8 impacts, int32 accumulators", "data": "synthetic",
+           "config": {"workload": "configs[1]: MS MARCO passage-shaped synthetic index, Zipf(1) terms, top-%d" % k,
+                      "docs": N, "vocab": V, "draws_per_doc": args.draws, "queries": len(queries), "top_k": k,
+                      "queries_per_step": per_step},
+           "cpu_baseline": {"value": round(qps, 3), "unit": "queries/s", "cores": threads, "kind": "port",
+                            "sample": f"{per_step} random queries of the {len(queries)} per step, full 8.8M-doc index"},
+           "e2e": {"value": round(qps, 3), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--docs", type=int, default=8_841_823)
+    ap.add_argument("--vocab", type=int, default=30522)
+    ap.add_argument("--draws", type=int, default=120)
+    ap.add_argument("--queries", type=int, default=6980)
+    ap.add_argument("--top-k", type=int, default=1000)
+    ap.add_argument("--tile-docs", type=int, default=0)
+    ap.add_argument("--dense-ratio", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
+    ap.add_argument("--ref-queries-per-step", type=int, default=32)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if int(os.environ.get("WORLD_SIZE", 1)) != args.gpus and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
