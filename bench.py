@@ -140,6 +140,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from improving_learned_index_b200 import _native, engine, synthetic
+    from improving_learned_index_b200.sharded import ShardedSearcher, shard_range
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -152,8 +153,7 @@ def run_b200(args):
     L = _native.lib()
     stream = torch.cuda.current_stream().cuda_stream
     N, V, k = args.docs, args.vocab, args.top_k
-    per = -(-N // world)
-    doc_lo, doc_hi = min(rank * per, N), min((rank + 1) * per, N)
+    doc_lo, doc_hi = shard_range(N, world, rank)
 
     # ---- build: synthetic doc-major lists -> K1 quantize -> K2 invert -> tiled shard
     t0 = time.time()
@@ -195,21 +195,11 @@ def run_b200(args):
     d_flat, d_offs = h_flat.to(dev), h_offs.to(dev)
     df = index.term_df(flat)
     local_postings = int(df.sum())
-    d_keys = torch.zeros((Q, k), dtype=torch.int64, device=dev)
-    d_counts = torch.zeros(Q, dtype=torch.int32, device=dev)
-    if world > 1:
-        g_keys = torch.zeros((world, Q, k), dtype=torch.int64, device=dev)
-        g_counts = torch.zeros((world, Q), dtype=torch.int32, device=dev)
-        m_keys = torch.zeros((Q, k), dtype=torch.int64, device=dev)
-        m_counts = torch.zeros(Q, dtype=torch.int32, device=dev)
+    searcher = ShardedSearcher.for_device_index(index, dev)      # local top-k -> NCCL all-gather -> K5 merge
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_device():
-        index.search_device(d_flat, d_offs, Q, max_len, k, d_keys, d_counts, stream)
-        if world > 1:
-            dist.all_gather_into_tensor(g_keys, d_keys)
-            dist.all_gather_into_tensor(g_counts, d_counts)
-            engine.merge_topk_device(g_keys, g_counts, world, Q, k, m_keys, m_counts, stream)
+        return searcher.search_tensors(d_flat, d_offs, Q, max_len, k)
 
     h_docs = torch.empty((Q, k), dtype=torch.int32).pin_memory()
     h_scores = torch.empty((Q, k), dtype=torch.int32).pin_memory()
@@ -221,7 +211,7 @@ def run_b200(args):
         else:
             d_flat.copy_(h_flat, non_blocking=True)
             d_offs.copy_(h_offs, non_blocking=True)
-            step_device()
+            m_keys, m_counts = step_device()
             if rank == 0:
                 dd = torch.empty((Q, k), dtype=torch.int32, device=dev)
                 ds = torch.empty((Q, k), dtype=torch.int32, device=dev)

@@ -602,16 +602,17 @@ extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_co
     if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t cap = pow2_ceil(n_shards * top_k);
-    DevBuf cand, cnt;  // freed after the stream is drained below
-    DI_TRY(cand.alloc((size_t)n_queries * cap * 8));
-    DI_TRY(cnt.alloc((size_t)n_queries * 4));
+    // scratch is cached per host thread (one process per GPU drives one merge stream) and only
+    // grows, so the steady state has no allocation and the call stays asynchronous
+    static thread_local DevBuf cand, cnt;
+    DI_TRY(ensure(cand, (size_t)n_queries * cap * 8));
+    DI_TRY(ensure(cnt, (size_t)n_queries * 4));
     merge_gather_kernel<<<n_queries, 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, top_k, cand.as<uint64_t>(),
                                                   cnt.as<uint32_t>(), cap);
     DI_KERNEL_CHECK();
     finalize_topk_kernel<<<n_queries, kScoreThreads, kSortSmemKeys * 8, st>>>(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k,
                                                                             48, d_keys_out, d_counts_out);
     DI_KERNEL_CHECK();
-    DI_CUDA(cudaStreamSynchronize(st));
     return DI_OK;
 }
 
