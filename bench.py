@@ -181,7 +181,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     t1 = time.time()
     index = engine.DeviceIndex.from_csr_device(toff, docids, vals, V, P, doc_lo=doc_lo, doc_hi=max(doc_hi, doc_lo + 1),
-                                               tile_docs=args.tile_docs, dense_ratio=args.dense_ratio)
+                                               tile_docs=args.tile_docs, dense_ratio=args.dense_ratio,
+                                               cand_slack=args.cand_slack)
     t_tile = time.time() - t1
     info = index.info()
 
@@ -409,6 +410,7 @@ def main():
     ap.add_argument("--top-k", type=int, default=1000)
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--dense-ratio", type=int, default=0)
+    ap.add_argument("--cand-slack", type=int, default=0, help="candidate slots kept per query between tiles (0 = default)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
     ap.add_argument("--ref-queries-per-step", type=int, default=32)
     args = ap.parse_args()

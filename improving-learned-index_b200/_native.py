@@ -14,9 +14,11 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_DIR = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "libdi_b200.so"
+import os
+# DI_B200_LIB lets a tuning run point at an alternative build of the SAME sources (e.g. other block size)
+LIB_PATH = Path(os.environ.get("DI_B200_LIB", PKG_DIR / "libdi_b200.so"))
 SOURCES = [PKG_DIR / "csrc" / n for n in
-           ("di_b200.cu", "common.cuh", "scan_sort.cuh", "build.cuh", "search.cuh")] + [REPO_DIR / "include" / "di_b200.h"]
+           ("di_b200.cu", "common.cuh", "scan_sort.cuh", "build.cuh", "select.cuh", "score_tile.cuh", "search.cuh")] + [REPO_DIR / "include" / "di_b200.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -135,14 +135,22 @@ inline int invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, cons
 }
 
 // ============================================================================ tiled shard layout
-// tile key = [tile:16 | term:24 | local docid:16 | impact:8]; hidden postings get ~0 and sort last.
+// tile key = [tile:16 | term:24 | parity:1 | local docid >> 1 : 15 | impact:8]; hidden postings get
+// ~0 and sort last. Sorting puts a segment's even documents first, then its odd documents, each
+// by ascending docid: the scorer adds a u8 impact into a u16 accumulator that shares a 32-bit
+// shared-memory word with its neighbour, and knowing the parity per 16-byte unit makes the
+// addend a single instruction (DESIGN.md "sparse segments").
 constexpr int kTkTermShift = 24, kTkTileShift = 48, kTkLocalShift = 8;
 constexpr uint32_t kDenseFlag = 0x80000000u;
+constexpr uint32_t kMaxTileDocs = 32768;
 
 struct SegDesc {        // one per (tile, term)
     uint32_t off16;     // payload offset in 16-byte units
-    uint32_t n_flag;    // postings in the segment | kDenseFlag
+    uint32_t n_flag;    // dense: kDenseFlag | postings.  sparse: even units << 16 | total units (16 B units)
 };
+
+__host__ __device__ __forceinline__ uint32_t local_to_field(uint32_t local) { return ((local & 1u) << 15) | (local >> 1); }
+__host__ __device__ __forceinline__ uint32_t field_to_local(uint32_t f) { return ((f & 0x7FFFu) << 1) | (f >> 15); }
 
 // inverted_index.py:50-51 — the reader stops at the FIRST zero impact of a term's list
 __global__ void first_zero_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
@@ -190,7 +198,8 @@ __global__ void tile_keys_kernel(const uint64_t *__restrict__ term_offsets, uint
                 stats->bad_docid = 1;
             } else {
                 const uint32_t local = rel & ((1u << tile_shift) - 1u);
-                key = (tile << kTkTileShift) | ((uint64_t)t << kTkTermShift) | ((uint64_t)local << kTkLocalShift) | impacts[i];
+                key = (tile << kTkTileShift) | ((uint64_t)t << kTkTermShift) | ((uint64_t)local_to_field(local) << kTkLocalShift) |
+                      impacts[i];
                 ++vis;
                 if (d + 1 > mx) mx = d + 1;  // d < doc_hi <= 2^32-1
             }
@@ -217,22 +226,27 @@ __device__ __forceinline__ uint64_t seg_index(uint64_t key, uint32_t n_terms)
 
 // `seg_dup[s]` is set when a segment holds the same document twice (possible in hand-made CSR or
 // a model that lists a term twice): such a segment cannot be stored densely (one byte per doc).
+// `seg_odd[s]` (pre-set to 0xFFFFFFFF) receives the index of the segment's first odd document.
 __global__ void seg_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t n_vis, uint32_t n_terms,
                                   uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ seg_end,
-                                  uint32_t *__restrict__ seg_dup)
+                                  uint32_t *__restrict__ seg_odd, uint32_t *__restrict__ seg_dup)
 {
+    constexpr int kParityBit = kTkLocalShift + 15;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t id = keys[i] >> kTkTermShift;
+        const bool starts = i == 0 || (keys[i - 1] >> kTkTermShift) != id;
         if (i && (keys[i - 1] >> kTkLocalShift) == (keys[i] >> kTkLocalShift)) seg_dup[seg_index(keys[i], n_terms)] = 1u;
-        if (i == 0 || (keys[i - 1] >> kTkTermShift) != id) seg_begin[seg_index(keys[i], n_terms)] = (uint32_t)i;
+        if (((keys[i] >> kParityBit) & 1u) && (starts || !((keys[i - 1] >> kParityBit) & 1u)))
+            seg_odd[seg_index(keys[i], n_terms)] = (uint32_t)i;
+        if (starts) seg_begin[seg_index(keys[i], n_terms)] = (uint32_t)i;
         if (i == n_vis - 1 || (keys[i + 1] >> kTkTermShift) != id) seg_end[seg_index(keys[i], n_terms)] = (uint32_t)(i + 1);
     }
 }
 
-// per (tile, term): choose dense (u8 per doc of the tile) or sparse (u32 per posting) storage.
+// per (tile, term): choose dense (u16 per doc of the tile) or sparse (u32 per posting) storage.
 // On entry size16[s] holds the duplicate flag written by seg_bounds_kernel.
 __global__ void seg_size_kernel(const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ seg_end,
-                                uint64_t n_segs, uint32_t n_terms, uint32_t tile_docs, uint32_t dense_ratio,
+                                const uint32_t *__restrict__ seg_odd, uint64_t n_segs, uint32_t n_terms, uint32_t tile_docs, uint32_t dense_ratio,
                                 uint32_t *__restrict__ size16, uint32_t *__restrict__ n_flag,
                                 unsigned long long *__restrict__ df, TileStats *__restrict__ stats)
 {
@@ -242,8 +256,15 @@ __global__ void seg_size_kernel(const uint32_t *__restrict__ seg_begin, const ui
         uint32_t sz = 0, nf = 0;
         if (n) {
             const bool dense = dense_ratio != 0xFFFFFFFFu && (uint64_t)n * dense_ratio >= tile_docs && size16[s] == 0;
-            sz = dense ? tile_docs / 16u : (n + 3u) / 4u;
-            nf = n | (dense ? kDenseFlag : 0u);
+            if (dense) {
+                sz = tile_docs / 8u;  // one u16 per document: the accumulator layout itself
+                nf = n | kDenseFlag;
+            } else {  // even documents first, then odd ones, each padded to whole 16-byte units
+                const uint32_t n_even = seg_odd[s] == 0xFFFFFFFFu ? n : seg_odd[s] - seg_begin[s];
+                const uint32_t ue = (n_even + 3u) / 4u, uo = (n - n_even + 3u) / 4u;
+                sz = ue + uo;
+                nf = (ue << 16) | sz;
+            }
             if (dense) { ++nd; ndp += n; } else ++ns;
             atomicAdd(&df[s % n_terms], (unsigned long long)n);
         }
@@ -270,20 +291,26 @@ __global__ void seg_desc_kernel(const uint32_t *__restrict__ off16, const uint32
         desc[s] = SegDesc{off16[s], n_flag[s]};
 }
 
+// dense segment: payload u16 [local docid] = impact.
+// sparse posting word = impact << 16 | byte offset of the accumulator word ((local >> 1) * 4); the
+// parity of the document is implied by the unit the word sits in.
 __global__ void fill_payload_kernel(const uint64_t *__restrict__ keys, uint64_t n_vis, uint32_t n_terms,
                                     const SegDesc *__restrict__ desc, const uint32_t *__restrict__ seg_begin,
-                                    uint8_t *__restrict__ payload)
+                                    const uint32_t *__restrict__ seg_odd, uint8_t *__restrict__ payload)
 {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i];
         const uint64_t s = seg_index(key, n_terms);
         const SegDesc d = desc[s];
-        const uint32_t local = (uint32_t)(key >> kTkLocalShift) & 0xFFFFu;
+        const uint32_t field = (uint32_t)(key >> kTkLocalShift) & 0xFFFFu;
         const uint32_t imp = (uint32_t)key & 0xFFu;
-        if (d.n_flag & kDenseFlag)
-            payload[(size_t)d.off16 * 16 + local] = (uint8_t)imp;
-        else
-            reinterpret_cast<uint32_t *>(payload)[(size_t)d.off16 * 4 + (i - seg_begin[s])] = (imp << 16) | local;
+        if (d.n_flag & kDenseFlag) {
+            reinterpret_cast<uint16_t *>(payload)[(size_t)d.off16 * 8 + field_to_local(field)] = (uint16_t)imp;
+        } else {
+            const uint32_t word = (imp << 16) | ((field & 0x7FFFu) << 2);
+            const size_t slot = (field >> 15) ? (size_t)(d.n_flag >> 16) * 4 + (i - seg_odd[s]) : (i - seg_begin[s]);
+            reinterpret_cast<uint32_t *>(payload)[(size_t)d.off16 * 4 + slot] = word;
+        }
     }
 }
 

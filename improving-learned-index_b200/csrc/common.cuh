@@ -101,6 +101,30 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *ptr)
     return r;
 }
 
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *ptr)
+{
+    uint32_t r;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r) : "l"(ptr));
+    return r;
+}
+
+// gpu-scope acquire / release on a 32-bit flag: the hand-off of a query's state between the CTAs
+// that process consecutive tiles of that query inside one persistent launch
+// The flag is polled with a RELAXED gpu-scope load (served by L2) on purpose: an acquire load makes
+// ptxas emit CCTL.IVALL, which would wipe the SM's L1 (segment descriptors) on every work item. The
+// consumer does not need L1 invalidation, because everything it then reads of the handed-off state
+// is read with ld.cg (L2) and only after a CTA barrier that follows the completed flag load.
+__device__ __forceinline__ uint32_t ld_flag_u32(const uint32_t *ptr)
+{
+    uint32_t r;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(ptr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *ptr, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+
 // ranked-result key: larger is better. score in the high word, bit-inverted docid in the low
 // word, so that equal scores order by ASCENDING docid under a descending key sort.
 __host__ __device__ __forceinline__ uint64_t make_key(uint32_t score, uint32_t docid)

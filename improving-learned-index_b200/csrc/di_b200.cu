@@ -1,6 +1,7 @@
 // di_b200.cu — the C ABI declared in include/di_b200.h. Host-side orchestration only; the
 // kernels live in build.cuh / search.cuh / scan_sort.cuh. Compiled for sm_100a.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -25,7 +26,7 @@ struct di_index {
 
     // search workspace (grown on demand)
     cudaStream_t stream = nullptr;
-    DevBuf ws_cand, ws_cnt, ws_theta;
+    DevBuf ws_cand, ws_cnt, ws_theta, ws_order, ws_done;
     DevBuf st_qterms, st_qoffs, st_keys, st_counts, st_docids, st_scores;
     int smem_opt_in = 0;
     bool attr_set16 = false, attr_set32 = false, attr_setfin = false;
@@ -256,9 +257,11 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
     if (n_segs * sizeof(SegDesc) > (48ull << 30))
         return set_error(DI_ERR_NOMEM, "segment table of %llu entries is too large; use larger tiles",
                          (unsigned long long)n_segs);
-    DevBuf d_begin, d_end, d_size, d_nflag, d_scan;
+    DevBuf d_begin, d_end, d_odd, d_size, d_nflag, d_scan;
     DI_TRY(d_begin.alloc(n_segs * 4));
     DI_TRY(d_end.alloc(n_segs * 4));
+    DI_TRY(d_odd.alloc(n_segs * 4));
+    DI_CUDA(cudaMemsetAsync(d_odd.p, 0xFF, n_segs * 4, st));
     DI_TRY(d_size.alloc((n_segs + 1) * 4));
     DI_TRY(d_nflag.alloc(n_segs * 4));
     DI_TRY(d_scan.alloc(scan_scratch_words(n_segs + 1) * 4));
@@ -268,9 +271,10 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
     DI_CUDA(cudaMemsetAsync(d_end.p, 0, n_segs * 4, st));
     DI_CUDA(cudaMemsetAsync(d_size.p, 0, (n_segs + 1) * 4, st));
     seg_bounds_kernel<<<grid_for(n_vis, 256), 256, 0, st>>>(sorted, n_vis, V, d_begin.as<uint32_t>(), d_end.as<uint32_t>(),
-                                                          d_size.as<uint32_t>());
+                                                          d_odd.as<uint32_t>(), d_size.as<uint32_t>());
     DI_KERNEL_CHECK();
-    seg_size_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_begin.as<uint32_t>(), d_end.as<uint32_t>(), n_segs, V,
+    seg_size_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_begin.as<uint32_t>(), d_end.as<uint32_t>(),
+                                                          d_odd.as<uint32_t>(), n_segs, V,
                                                           ix->tile_docs, ix->dense_ratio, d_size.as<uint32_t>(),
                                                           d_nflag.as<uint32_t>(), ix->d_df, d_stats.as<TileStats>());
     DI_KERNEL_CHECK();
@@ -291,7 +295,7 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
     seg_desc_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_size.as<uint32_t>(), d_nflag.as<uint32_t>(), n_segs, ix->d_desc);
     DI_KERNEL_CHECK();
     fill_payload_kernel<<<grid_for(n_vis, 256), 256, 0, st>>>(sorted, n_vis, V, ix->d_desc, d_begin.as<uint32_t>(),
-                                                              ix->d_payload);
+                                                              d_odd.as<uint32_t>(), ix->d_payload);
     DI_KERNEL_CHECK();
     DI_CUDA(cudaStreamSynchronize(st));
     return DI_OK;
@@ -304,8 +308,8 @@ static int new_index(uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const d
     DI_TRY(ensure_device());
     if (doc_hi <= doc_lo) return set_error(DI_ERR_ARG, "empty doc range [%u, %u)", doc_lo, doc_hi);
     uint32_t tile_docs = params && params->tile_docs ? params->tile_docs : 32768u;
-    if (tile_docs < 256 || tile_docs > 65536 || (tile_docs & (tile_docs - 1)))
-        return set_error(DI_ERR_ARG, "tile_docs must be a power of two in [256, 65536], got %u", tile_docs);
+    if (tile_docs < 256 || tile_docs > kMaxTileDocs || (tile_docs & (tile_docs - 1)))
+        return set_error(DI_ERR_ARG, "tile_docs must be a power of two in [256, %u], got %u", kMaxTileDocs, tile_docs);
     di_index *ix = new (std::nothrow) di_index();
     if (!ix) return set_error(DI_ERR_NOMEM, "host allocation failed");
     cudaGetDevice(&ix->device);
@@ -445,6 +449,24 @@ static uint32_t pow2_ceil(uint32_t x)
     return p;
 }
 
+// finalize_topk_kernel with a shared-memory key buffer sized for the longest list it can meet
+// (max_n), between 32 KB and 128 KB; longer lists take the kernel's global-memory path.
+static int launch_finalize(uint64_t *cand, const uint32_t *cnt, uint32_t cap, uint32_t top_k, int top_shift,
+                           uint32_t max_n, uint32_t n_queries, uint64_t *out_keys, uint32_t *out_counts, cudaStream_t st)
+{
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        DI_CUDA(cudaFuncSetAttribute(finalize_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        attr_set = true;
+    }
+    uint32_t smem_keys = kSortSmemKeys;
+    while (smem_keys < max_n && smem_keys < 16384) smem_keys <<= 1;
+    finalize_topk_kernel<<<n_queries, kScoreThreads, (size_t)smem_keys * 8, st>>>(cand, cnt, cap, top_k, top_shift,
+                                                                                 smem_keys, out_keys, out_counts);
+    DI_KERNEL_CHECK();
+    return DI_OK;
+}
+
 static int ensure(DevBuf &b, size_t bytes)
 {
     if (b.bytes >= bytes && b.p) return DI_OK;
@@ -470,21 +492,33 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         return set_error(DI_ERR_ARG, "tile of %u docs needs %zu B of shared memory for %d-bit accumulators (limit %d); "
                          "rebuild the index with smaller tiles for queries of %u terms",
                          ix->tile_docs, acc_bytes, acc32 ? 32 : 16, ix->smem_opt_in, max_query_len);
-    uint32_t c0 = ix->cand_slack ? ix->cand_slack : std::max(4u * top_k, 4096u);
+    uint32_t c0 = ix->cand_slack ? ix->cand_slack : std::max(2u * top_k, 2048u);
     c0 = std::max(c0, top_k);
     const uint32_t cap = std::max(c0 + ix->tile_docs, pow2_ceil(top_k));
     const int top_shift = acc32 ? 48 : 40;
 
     if (acc32 && !ix->attr_set32) {
         DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+        DI_CUDA(cudaFuncSetAttribute(score_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
         ix->attr_set32 = true;
     }
     if (!acc32 && !ix->attr_set16) {
         DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
         DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
+        DI_CUDA(cudaFuncSetAttribute(score_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+        DI_CUDA(cudaFuncSetAttribute(score_persistent_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         ix->attr_set16 = true;
     }
+    static const bool per_tile_launches = getenv("DI_B200_PER_TILE") != nullptr;
+    int ctas_per_sm = 0, n_sms = 0;
+    if (acc32)
+        DI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, score_persistent_kernel<true>, kScoreThreads, acc_bytes));
+    else
+        DI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, score_persistent_kernel<false>, kScoreThreads, acc_bytes));
+    DI_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ix->device));
+    const int resident_ctas = std::max(1, ctas_per_sm) * std::max(1, n_sms);
 
     // candidate workspace: at most ~6 GB, queries are processed in batches that fit
     const uint64_t per_query = (uint64_t)cap * 8;
@@ -494,6 +528,8 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     DI_TRY(ensure(ix->ws_cand, (size_t)batch * per_query));
     DI_TRY(ensure(ix->ws_cnt, (size_t)batch * 4));
     DI_TRY(ensure(ix->ws_theta, (size_t)batch * 8));
+    DI_TRY(ensure(ix->ws_order, (size_t)batch * sizeof(QueryRec)));
+    DI_TRY(ensure(ix->ws_done, 8 + (size_t)batch * 4));
 
     for (uint32_t q0 = 0; q0 < n_queries; q0 += batch) {
         const uint32_t nq = std::min(batch, n_queries - q0);
@@ -516,20 +552,41 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         a.c0 = c0;
         a.k = top_k;
         a.top_shift = top_shift;
+        a.recs = ix->ws_order.as<QueryRec>();
         DI_CUDA(cudaMemsetAsync(a.cnt, 0, (size_t)nq * 4, st));
         DI_CUDA(cudaMemsetAsync(a.theta, 0, (size_t)nq * 8, st));
         DI_CUDA(cudaEventRecord(ix->ev[b][0], st));
-        for (uint32_t tile = 0; tile < ix->n_tiles; ++tile) {
+        if (ix->n_tiles) {
+            query_order_kernel<<<1, 1024, 0, st>>>(d_q_terms, a.q_offsets, ix->d_df, ix->n_terms, nq,
+                                                   ix->ws_order.as<QueryRec>());
+            DI_KERNEL_CHECK();
+            ++ix->other_launches;
+        }
+        if (per_tile_launches) {  // DI_B200_PER_TILE=1: one launch per tile (to profile a single tile)
+            a.done = nullptr;
+            for (uint32_t tile = 0; tile < ix->n_tiles; ++tile) {
+                if (acc32)
+                    score_tile_kernel<true><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
+                else
+                    score_tile_kernel<false><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
+                ++ix->score_launches;
+            }
+        } else if (ix->n_tiles) {  // one persistent launch over all (tile, query) items of the batch
+            a.done = ix->ws_done.as<uint32_t>() + 2;  // [0..1] hold the 64-bit work counter
+            unsigned long long *counter = ix->ws_done.as<unsigned long long>();
+            DI_CUDA(cudaMemsetAsync(ix->ws_done.p, 0, 8 + (size_t)nq * 4, st));
+            const uint64_t n_items = (uint64_t)ix->n_tiles * nq;
+            const unsigned grid = (unsigned)std::min<uint64_t>(n_items, (uint64_t)resident_ctas);
             if (acc32)
-                score_tile_kernel<true><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
+                score_persistent_kernel<true><<<grid, kScoreThreads, acc_bytes, st>>>(a, ix->n_tiles, nq, counter);
             else
-                score_tile_kernel<false><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
+                score_persistent_kernel<false><<<grid, kScoreThreads, acc_bytes, st>>>(a, ix->n_tiles, nq, counter);
             ++ix->score_launches;
         }
         DI_KERNEL_CHECK();
         DI_CUDA(cudaEventRecord(ix->ev[b][1], st));
-        finalize_topk_kernel<<<nq, kScoreThreads, kSortSmemKeys * 8, st>>>(a.cand, a.cnt, cap, top_k, top_shift,
-                                                                          d_out_keys + (uint64_t)q0 * top_k, d_out_counts + q0);
+        DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, top_shift, /*max_n=*/c0, nq,
+                               d_out_keys + (uint64_t)q0 * top_k, d_out_counts + q0, st));
         DI_KERNEL_CHECK();
         ++ix->other_launches;
         DI_CUDA(cudaEventRecord(ix->ev[b][2], st));
@@ -610,10 +667,8 @@ extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_co
     merge_gather_kernel<<<n_queries, 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, top_k, cand.as<uint64_t>(),
                                                   cnt.as<uint32_t>(), cap);
     DI_KERNEL_CHECK();
-    finalize_topk_kernel<<<n_queries, kScoreThreads, kSortSmemKeys * 8, st>>>(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k,
-                                                                            48, d_keys_out, d_counts_out);
-    DI_KERNEL_CHECK();
-    return DI_OK;
+    return launch_finalize(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k, 48, /*max_n=*/n_shards * top_k, n_queries,
+                           d_keys_out, d_counts_out, st);
 }
 
 extern "C" int di_get_timings(di_index_t *ix, di_timings *out)

@@ -1,0 +1,471 @@
+// score_tile.cuh — K3: term-at-a-time scoring of every query of a batch against ONE document
+// tile, plus the tile-local half of K4 (candidate emission against the query's running threshold).
+//
+// Replaces the two hot loops of InvertedIndex.score (inverted_index.py:57-60: read the term's
+// postings, scores[doc] += impact) and of SparseSearch.search (nano_beir_evaluator.py:118-121).
+//
+// One CTA = one (query, tile) work item.
+//   phase 1  dense segments (u16 impact per document of the tile, 128-bit loads) are summed in
+//            registers and STORED into the shared-memory accumulators — this also zeroes them;
+//   phase 2  sparse segments (u32 postings) of all the query's terms are flattened into one index
+//            space, streamed with 128-bit loads and added with shared-memory atomics;
+//   phase 3  the accumulators are scanned once; documents whose key (score, ~docid) can still reach
+//            the query's top-k are appended to the query's candidate list in global memory.
+// Accumulators are u16 pairs packed in 32-bit words (ACC32 = false; queries of <= 257 terms cannot
+// overflow 16 bits) or u32 (ACC32 = true).
+#pragma once
+
+#include "build.cuh"
+#include "common.cuh"
+#include "select.cuh"
+
+namespace di {
+
+#ifndef DI_SCORE_THREADS
+#define DI_SCORE_THREADS 256
+#endif
+#ifndef DI_SCORE_MIN_BLOCKS
+#define DI_SCORE_MIN_BLOCKS 3
+#endif
+constexpr int kScoreThreads = DI_SCORE_THREADS;
+constexpr int kMaxSeg = 32;        // query terms handled per round inside a work item
+#ifndef DI_SPARSE_UNROLL
+#define DI_SPARSE_UNROLL 4
+#endif
+constexpr int kSparseUnroll = DI_SPARSE_UNROLL;  // independent 128-bit posting loads in flight per thread
+constexpr int kHistBins = 1024;    // score histogram of the tile-local pre-selection
+
+constexpr int kRecInlineTerms = 12;
+struct __align__(64) QueryRec {   // one cache-line-friendly record per query of the batch
+    uint32_t q;                   // query index inside the batch
+    uint32_t n;                   // number of term occurrences
+    uint64_t begin;               // first term in q_terms (for queries longer than the inline part)
+    uint32_t terms[kRecInlineTerms];
+};
+
+struct SearchArgs {
+    const SegDesc *desc;        // [n_tiles][n_terms]
+    const uint8_t *payload;
+    const uint32_t *q_terms;
+    const uint64_t *q_offsets;  // already offset to the first query of the batch
+    uint64_t *cand;             // [n_queries][cap] candidate keys (unsorted)
+    uint32_t *cnt;              // [n_queries] live candidates
+    uint64_t *theta;            // [n_queries] lower bound on the k-th best key (0 = none yet)
+    uint32_t n_terms, tile_docs, tile_shift, doc_lo;
+    uint32_t cap, c0, k;
+    int top_shift;              // highest radix-select digit that can be non-zero
+    const QueryRec *recs;       // [n_queries] work-item records in launch order
+    uint32_t *done;             // [n_queries] tiles completed per query (persistent launch), or nullptr
+};
+
+// Launch order of a batch: queries bucketed by log2 of their total posting count (sum of the document
+// frequencies of their terms), heaviest bucket first. One block; the order inside a bucket is arbitrary
+// (results do not depend on it).
+__global__ void __launch_bounds__(1024) query_order_kernel(const uint32_t *__restrict__ q_terms,
+                                                         const uint64_t *__restrict__ q_offsets,
+                                                         const unsigned long long *__restrict__ df, uint32_t n_terms,
+                                                         uint32_t n_queries, QueryRec *__restrict__ recs)
+{
+    __shared__ uint32_t s_cursor[64];
+    if (threadIdx.x < 64) s_cursor[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket_of = [&](uint32_t q) {
+        unsigned long long cost = 0;
+        for (uint64_t j = q_offsets[q]; j < q_offsets[q + 1]; ++j) {
+            const uint32_t t = q_terms[j];
+            if (t < n_terms) cost += df[t];
+        }
+        // two buckets per power of two, descending cost = ascending bucket
+        const int msb = cost ? 63 - __clzll((long long)cost) : 0;
+        const int half = msb ? (int)((cost >> (msb - 1)) & 1ull) : 0;
+        const int b = 2 * msb + half;
+        return (uint32_t)(63 - (b > 63 ? 63 : b));
+    };
+    for (uint32_t q = threadIdx.x; q < n_queries; q += blockDim.x) atomicAdd(&s_cursor[bucket_of(q)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < 64; ++b) {
+            const uint32_t c = s_cursor[b];
+            s_cursor[b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < n_queries; q += blockDim.x) {
+        QueryRec r;
+        r.q = q;
+        r.begin = q_offsets[q];
+        r.n = (uint32_t)(q_offsets[q + 1] - r.begin);
+        for (int i = 0; i < kRecInlineTerms; ++i) r.terms[i] = (uint32_t)i < r.n ? q_terms[r.begin + i] : DI_OOV_TERM;
+        recs[atomicAdd(&s_cursor[bucket_of(q)], 1u)] = r;
+    }
+}
+
+// ---- phase 1 helpers: NB dense segments, 8 documents per 128-bit load -----------------------
+template <int NB, bool INIT>
+__device__ __forceinline__ void dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
+                                             const uint4 *p3, uint32_t groups)
+{
+    const uint4 *ptr[4] = {p0, p1, p2, p3};
+    // U groups per step so that about 8 independent 128-bit loads are in flight per thread whatever
+    // the number of dense terms (a work item is latency-bound: few CTAs per SM, L2-resident postings)
+    constexpr int U = NB <= 1 ? 8 : (NB == 2 ? 4 : 2);
+    for (uint32_t g0 = threadIdx.x; g0 < groups; g0 += U * kScoreThreads) {
+        uint4 v[U][NB > 0 ? NB : 1];
+#pragma unroll
+        for (int s = 0; s < U; ++s) {
+            const uint32_t g = g0 + s * kScoreThreads;
+#pragma unroll
+            for (int u = 0; u < NB; ++u) v[s][u] = g < groups ? ldg_stream_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int s = 0; s < U; ++s) {
+            const uint32_t g = g0 + s * kScoreThreads;
+            if (g < groups) {
+                // a dense segment stores one u16 per document, i.e. exactly the accumulator layout: the
+                // update is four plain 32-bit adds per 8 documents (two u16 lanes per word, no carries)
+                uint4 a = INIT ? make_uint4(0, 0, 0, 0) : s_acc4[g];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    a.x += v[s][u].x; a.y += v[s][u].y; a.z += v[s][u].z; a.w += v[s][u].w;
+                }
+                s_acc4[g] = a;
+            }
+        }
+    }
+}
+
+template <bool INIT>
+__device__ __forceinline__ void dense_dispatch16(int nb, uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff,
+                                                 uint32_t groups)
+{
+    const uint4 *p0 = payload4 + doff[0], *p1 = payload4 + doff[1], *p2 = payload4 + doff[2], *p3 = payload4 + doff[3];
+    switch (nb) {  // nb is uniform across the CTA
+        case 4: dense_pass16<4, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
+        case 3: dense_pass16<3, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
+        case 2: dense_pass16<2, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
+        case 1: dense_pass16<1, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
+        default: if (INIT) dense_pass16<0, true>(s_acc4, p0, p1, p2, p3, groups); break;
+    }
+}
+
+// ACC32 twin (long queries only): plain loop, 8 documents = two 128-bit accumulator words
+template <bool INIT>
+__device__ __forceinline__ void dense_pass32(uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff, int nb,
+                                             uint32_t groups)
+{
+    for (uint32_t g = threadIdx.x; g < groups; g += kScoreThreads) {
+        uint32_t a[8];
+        if (INIT) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = 0;
+        } else {
+            const uint4 lo = s_acc4[2 * g], hi = s_acc4[2 * g + 1];
+            a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
+            a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+        }
+        for (int j = 0; j < nb; ++j) {
+            const uint4 v = ldg_stream_v4(payload4 + doff[j] + g);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[2 * i] += w[i] & 0xFFFFu;
+                a[2 * i + 1] += w[i] >> 16;
+            }
+        }
+        s_acc4[2 * g] = make_uint4(a[0], a[1], a[2], a[3]);
+        s_acc4[2 * g + 1] = make_uint4(a[4], a[5], a[6], a[7]);
+    }
+}
+
+// ---- phase 3 helper -------------------------------------------------------------------------
+__device__ __forceinline__ void emit_candidate(uint32_t score, uint32_t docid, uint64_t theta, uint64_t *cand,
+                                               uint32_t cnt0, uint32_t *s_emit)
+{
+    const uint64_t key = make_key(score, docid);
+    if (key >= theta) cand[cnt0 + atomicAdd(s_emit, 1u)] = key;
+}
+
+// One (query, tile) work item; `slot` indexes the batch's launch-ordered query records.
+template <bool ACC32>
+__device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, uint32_t slot)
+{
+    extern __shared__ uint4 s_acc4[];  // tile accumulators
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_acc4);
+    __shared__ uint32_t s_doff[kMaxSeg];       // dense segments of this round: payload offset (16 B units)
+    __shared__ uint32_t s_soff[kMaxSeg];       // sparse segments: payload offset
+    __shared__ uint32_t s_sunits[kMaxSeg];     // sparse segments: total 16 B units
+    __shared__ uint32_t s_seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
+    __shared__ uint32_t s_spref[kMaxSeg + 1];  // exclusive prefix of s_sunits
+    __shared__ uint32_t s_nd, s_ns, s_emit, s_npost, s_ready;
+    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tmp[2];
+
+    const uint32_t tid = threadIdx.x;
+    // One 64-byte record per work item (heaviest queries first, so the tail is made of light ones)
+    // holds everything needed to start: the dependent-load chain is record -> descriptor -> postings.
+    const QueryRec *__restrict__ rec = p.recs + slot;
+    const uint32_t q = rec->q;
+    const uint64_t qb = rec->begin, qe = rec->begin + rec->n;
+    const uint32_t T = p.tile_docs;
+    // The query's running state (threshold, candidate list) is handed from tile to tile through
+    // global memory; tile t may start once tile t-1 of the same query has published (done[q] >= t).
+    // Items are dispatched in tile-major order, so this is almost always already true: probe now,
+    // and only wait (before phase 3) in the rare case it is not.
+    if (tid == 0) s_ready = p.done == nullptr || tile == 0 || ld_flag_u32(p.done + q) >= tile;
+    const SegDesc *__restrict__ desc = p.desc + (uint64_t)tile * p.n_terms;
+    const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
+
+    if (tid == 0) s_npost = 0;
+    uint64_t theta = 0;
+    uint32_t cnt0 = 0;
+    bool first = true, touched = false, have_state = false;
+    for (uint64_t r0 = qb; first || r0 < qe; r0 += kMaxSeg) {
+        // ---- look up this round's (term, tile) segments
+        if (tid == 0) { s_nd = 0; s_ns = 0; }
+        __syncthreads();
+        if (tid < kMaxSeg && r0 + tid < qe) {
+            const uint32_t t = (first && tid < kRecInlineTerms) ? rec->terms[tid] : p.q_terms[r0 + tid];
+            if (t < p.n_terms) {  // DI_OOV_TERM and anything out of range: no postings
+                const SegDesc d = desc[t];
+                if (d.n_flag & kDenseFlag) {
+                    s_doff[atomicAdd(&s_nd, 1u)] = d.off16;
+                    atomicAdd(&s_npost, d.n_flag & ~kDenseFlag);
+                } else if (d.n_flag) {
+                    const uint32_t j = atomicAdd(&s_ns, 1u);
+                    s_soff[j] = d.off16;
+                    s_sunits[j] = d.n_flag & 0xFFFFu;
+                    s_seven[j] = d.n_flag >> 16;
+                    atomicAdd(&s_npost, (d.n_flag & 0xFFFFu) * 4u);  // upper bound on the postings
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nd = s_nd, ns = s_ns;
+        if (first && r0 + kMaxSeg >= qe && nd + ns == 0) return false;  // query has no posting in this tile
+        if (first && s_ready) {  // state already published: fetch it now (L2), it is needed only in phase 3
+            theta = ld_cg_u64(p.theta + q);
+            cnt0 = ld_cg_u32(p.cnt + q);
+            have_state = true;
+        }
+        touched = touched || (nd + ns) != 0;
+        if (tid == 0) {
+            uint32_t run = 0;
+            for (uint32_t j = 0; j < ns; ++j) { s_spref[j] = run; run += s_sunits[j]; }
+            s_spref[ns] = run;
+        }
+
+        // ---- phase 1: dense segments; the very first pass stores (and thereby zeroes) the accumulators
+        if (!ACC32) {
+            if (first) dense_dispatch16<true>(nd < 4 ? (int)nd : 4, s_acc4, payload4, s_doff, T >> 3);
+            // later batches read-modify-write the same words the same thread wrote: no barrier needed
+            for (uint32_t j0 = first ? 4 : 0; j0 < nd; j0 += 4) {
+                dense_dispatch16<false>(nd - j0 < 4 ? (int)(nd - j0) : 4, s_acc4, payload4, s_doff + j0, T >> 3);
+            }
+        } else {
+            if (first) dense_pass32<true>(s_acc4, payload4, s_doff, (int)nd, T >> 3);
+            else if (nd) dense_pass32<false>(s_acc4, payload4, s_doff, (int)nd, T >> 3);
+        }
+        __syncthreads();
+
+        // ---- phase 2: sparse segments. word = impact << 16 | byte offset of the accumulator word;
+        //      units [0, even) of a segment hold even documents, the rest odd ones.
+        const uint32_t total = s_spref[ns];
+        uint32_t seg = 0;
+        for (uint32_t u0 = tid; u0 < total; u0 += kSparseUnroll * kScoreThreads) {
+            uint4 v[kSparseUnroll];
+            bool odd[kSparseUnroll];
+#pragma unroll
+            for (int j = 0; j < kSparseUnroll; ++j) {
+                const uint32_t u = u0 + j * kScoreThreads;
+                odd[j] = false;
+                if (u < total) {
+                    while (u >= s_spref[seg + 1]) ++seg;
+                    const uint32_t lu = u - s_spref[seg];
+                    odd[j] = lu >= s_seven[seg];
+                    v[j] = ldg_stream_v4(payload4 + s_soff[seg] + lu);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kSparseUnroll; ++j) {
+                if (u0 + j * kScoreThreads < total) {
+                    const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    if (!ACC32) {
+                        char *base = reinterpret_cast<char *>(s_acc);
+                        if (!odd[j]) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] >> 16);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] & 0xFFFF0000u);
+                        }
+                    } else {
+                        const uint32_t par = odd[j] ? 1u : 0u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[((w[i] & 0xFFFFu) >> 1) | par], w[i] >> 16);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        first = false;
+    }
+    if (!touched) return false;
+
+    // ---- phase 3: candidates. Between done[q] == tile and the publish after this item, this CTA is
+    //      the only reader and writer of the query's list.
+    if (!have_state) {
+        if (tid == 0) {
+            uint32_t spins = 0;
+            while (ld_flag_u32(p.done + q) < tile) {
+                __nanosleep(128);
+                if (++spins > (1u << 23)) __trap();  // > 1 s: a protocol bug must fail loudly, never hang the GPU
+            }
+        }
+        __syncthreads();
+        theta = ld_cg_u64(p.theta + q);
+        cnt0 = ld_cg_u32(p.cnt + q);
+    }
+    uint32_t ths = (uint32_t)(theta >> 32);
+    if (ths == 0) ths = 1;  // score 0 = document not touched: never a result (inverted_index.py:58-62)
+    uint64_t *__restrict__ cand = p.cand + (uint64_t)q * p.cap;
+    const uint32_t doc_base = p.doc_lo + (tile << p.tile_shift);
+    // A document that only TIES the threshold score needs docid <= the threshold's docid. Tiles are
+    // visited in docid order, so the threshold's document lies in an earlier tile and every such tie in
+    // this tile loses: compare against score + 1 and keep the (many) ties out of the slow path.
+    if (theta != 0 && key_docid(theta) < doc_base) ++ths;
+    if (tid == 0) s_emit = 0;
+
+    if (theta == 0 && cnt0 + min(T, s_npost) > p.c0) {
+        // No threshold yet and this tile alone could flood the list (typically the first tile of a
+        // query with a frequent term): pre-select inside the tile with a score histogram. Keeping every
+        // document of the bins that hold the tile's k best is exact (at least k of them score >= the cut).
+        int shift = 0;
+        const uint32_t max_score = 255u * (uint32_t)min((uint64_t)(qe - qb), (uint64_t)65535);
+        while ((max_score >> shift) >= (uint32_t)kHistBins) ++shift;
+        for (uint32_t i = tid; i < (uint32_t)kHistBins; i += kScoreThreads) s_hist[i] = 0;
+        __syncthreads();
+        if (!ACC32) {
+            for (uint32_t g = tid; g < (T >> 1); g += kScoreThreads) {
+                const uint32_t w = s_acc[g];
+                if (w & 0xFFFFu) atomicAdd(&s_hist[(w & 0xFFFFu) >> shift], 1u);
+                if (w >> 16) atomicAdd(&s_hist[(w >> 16) >> shift], 1u);
+            }
+        } else {
+            for (uint32_t g = tid; g < T; g += kScoreThreads) {
+                const uint32_t w = s_acc[g];
+                if (w) atomicAdd(&s_hist[w >> shift], 1u);
+            }
+        }
+        __syncthreads();
+        const uint32_t bin = block_find_bin_from_top(s_hist, kHistBins, p.k, s_tmp);
+        ths = max(1u, bin << shift);
+    }
+    __syncthreads();
+
+    if (!ACC32) {
+        const uint32_t tm = ths - 1u, tm2 = tm | (tm << 16);  // half > tm  <=>  half >= ths
+        // 8 u16 accumulators per 128-bit load, two loads per step. Fast path per load: per-lane max of
+        // the four words (two 3-input SIMD max instructions), one more max against the threshold, one compare.
+        const uint32_t groups = T >> 3;
+        for (uint32_t g0 = tid; g0 < groups; g0 += 2 * kScoreThreads) {
+            uint4 x[2];
+            x[0] = s_acc4[g0];
+            x[1] = g0 + kScoreThreads < groups ? s_acc4[g0 + kScoreThreads] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t m = __vmaxu2(__vmaxu2(x[h].x, x[h].y), __vmaxu2(x[h].z, x[h].w));
+                if (__vmaxu2(m, tm2) != tm2) {  // rare: some document of the 8 is at or above the threshold
+                    const uint32_t g = g0 + h * kScoreThreads;
+                    const uint32_t w[4] = {x[h].x, x[h].y, x[h].z, x[h].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (__vmaxu2(w[i], tm2) != tm2) {
+                            const uint32_t lo = w[i] & 0xFFFFu, hi = w[i] >> 16;
+                            if (lo > tm) emit_candidate(lo, doc_base + 8 * g + 2 * i, theta, cand, cnt0, &s_emit);
+                            if (hi > tm) emit_candidate(hi, doc_base + 8 * g + 2 * i + 1, theta, cand, cnt0, &s_emit);
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        for (uint32_t g = tid; g < (T >> 2); g += kScoreThreads) {
+            const uint4 x = s_acc4[g];
+            if (max(max(x.x, x.y), max(x.z, x.w)) >= ths) {
+                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (w[i] >= ths) emit_candidate(w[i], doc_base + 4 * g + i, theta, cand, cnt0, &s_emit);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t n = cnt0 + s_emit;  // <= c0 + tile_docs <= cap
+    if (n > p.c0) {
+        // too many live candidates: keep exactly the k best and raise the threshold to the k-th
+        uint64_t kth;
+        if (n <= (T * (ACC32 ? 4u : 2u)) / 8u) {
+            // the accumulators are dead now: their shared memory stages the whole list (the usual case)
+            kth = block_cut_to_k_staged(cand, n, p.k, p.top_shift, reinterpret_cast<uint64_t *>(s_acc4), s_hist, s_tmp,
+                                        &s_emit);
+            n = p.k;
+        } else {
+            kth = block_select_kth<true>(cand, n, p.k, p.top_shift, s_hist, s_tmp);
+            n = block_compact_ge<true>(cand, n, kth, s_scan);
+        }
+        if (tid == 0) p.theta[q] = kth;
+    }
+    if (tid == 0) p.cnt[q] = n;
+    return true;  // the query's state was read after done[q] >= tile was observed
+}
+
+// ---- launch form A: one launch per tile, grid = queries (kept for profiling single tiles) -----
+template <bool ACC32>
+__global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS) score_tile_kernel(SearchArgs p, uint32_t tile)
+{
+    score_item<ACC32>(p, tile, blockIdx.x);  // p.done == nullptr: the launch boundary orders the tiles
+}
+
+// ---- launch form B: ONE persistent launch for all tiles of the batch ---------------------------
+// grid = resident CTAs; each CTA claims work items from a global counter in tile-major order
+// (item = tile * n_queries + slot), so at any moment the whole GPU works on one or two tiles (their
+// postings stay L2-resident) and there is no per-tile launch tail. After an item, done[q] = tile + 1
+// is published with release semantics; the next tile of the same query acquires it.
+template <bool ACC32>
+__global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS)
+score_persistent_kernel(SearchArgs p, uint32_t n_tiles, uint32_t n_queries, unsigned long long *counter)
+{
+    __shared__ unsigned long long s_item;
+    const unsigned long long n_items = (unsigned long long)n_tiles * n_queries;
+    for (;;) {
+        __syncthreads();  // everybody is done with the previous item's shared memory
+        if (threadIdx.x == 0) s_item = atomicAdd(counter, 1ull);
+        __syncthreads();
+        const unsigned long long item = s_item;
+        if (item >= n_items) break;
+        const uint32_t tile = (uint32_t)(item / n_queries), slot = (uint32_t)(item % n_queries);
+        const bool synced = score_item<ACC32>(p, tile, slot);
+        // Hand-off: CTA barrier, then ONE thread publishes with a release store (MEMBAR.GPU + store). The
+        // barrier orders every thread's candidate / threshold writes before the release (the pattern
+        // cooperative-groups grid sync relies on). done[q] must grow one tile at a time: an item that had
+        // nothing to do in this tile still waits for the previous tile before announcing the next.
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t *flag = p.done + p.recs[slot].q;
+            if (!synced && tile != 0) {
+                uint32_t spins = 0;
+                while (ld_flag_u32(flag) < tile) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 23)) __trap();
+                }
+            }
+            st_release_u32(flag, tile + 1);
+        }
+    }
+}
+
+}  // namespace di

@@ -1,0 +1,170 @@
+// select.cuh — block-wide exact selection primitives shared by K3/K4/K5: radix select of the k-th
+// largest 64-bit key, in-place compaction, bitonic sort, and a histogram cut finder.
+#pragma once
+
+#include "common.cuh"
+#include "scan_sort.cuh"
+
+namespace di {
+
+// ---------------------------------------------------------------------------- exact selection
+// k-th largest of n unique 64-bit keys (n >= k >= 1): MSB-first radix select, 8 bits per pass.
+// GLOBAL_CG: keys live in global memory written by other SMs during this launch -> read through L2.
+template <bool GLOBAL_CG = false>
+__device__ uint64_t block_select_kth(const uint64_t *keys, uint32_t n, uint32_t k, int top_shift,
+                                     uint32_t *s_hist /*256*/, uint32_t *s_tmp /*2*/)
+{
+    uint64_t prefix = 0, mask = 0;
+    uint32_t remaining = k;
+    for (int shift = top_shift; shift >= 0; shift -= 8) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t key = GLOBAL_CG ? ld_cg_u64(keys + i) : keys[i];
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const unsigned lane = threadIdx.x;
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // lane L owns bins 255-8L .. 248-8L, descending
+                c[j] = s_hist[255 - 8 * lane - j];
+                sum += c[j];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned)o) incl += t;
+            }
+            const uint32_t excl = incl - sum;
+            if (excl < remaining && remaining <= incl) {
+                uint32_t r = remaining - excl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (r <= c[j]) {
+                        s_tmp[0] = 255 - 8 * lane - j;
+                        s_tmp[1] = r;
+                        break;
+                    }
+                    r -= c[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (uint64_t)s_tmp[0] << shift;
+        mask |= 0xFFull << shift;
+        remaining = s_tmp[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// keeps keys >= theta, in place, order preserved; returns how many were kept
+template <bool GLOBAL_CG = false>
+__device__ uint32_t block_compact_ge(uint64_t *keys, uint32_t n, uint64_t theta, uint32_t *s_scan /*33*/)
+{
+    uint32_t out = 0;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t key = i < n ? (GLOBAL_CG ? ld_cg_u64(keys + i) : keys[i]) : 0ull;
+        const uint32_t flag = (i < n && key >= theta) ? 1u : 0u;
+        uint32_t total;
+        const uint32_t pos = block_exclusive_scan(flag, s_scan, total);  // barriers inside: loads are done
+        if (flag) keys[out + pos] = key;                                 // out + pos <= i
+        out += total;
+        __syncthreads();
+    }
+    return out;
+}
+
+// Cuts a candidate list (global memory, n unique keys, n >= k) to its k best through a shared-memory
+// staging buffer of at least n keys: one coalesced read, the radix-select passes run on shared memory,
+// one write of the k survivors to keys[0..k) (unordered). Returns the k-th largest key.
+__device__ __forceinline__ uint64_t block_cut_to_k_staged(uint64_t *keys, uint32_t n, uint32_t k, int top_shift,
+                                                          uint64_t *s_keys, uint32_t *s_hist /*256*/,
+                                                          uint32_t *s_tmp /*2*/, uint32_t *s_counter)
+{
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = ld_cg_u64(keys + i);  // other SMs wrote them
+    if (threadIdx.x == 0) *s_counter = 0;
+    __syncthreads();
+    const uint64_t kth = block_select_kth(s_keys, n, k, top_shift, s_hist, s_tmp);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = s_keys[i];
+        if (key >= kth) keys[atomicAdd(s_counter, 1u)] = key;
+    }
+    __syncthreads();
+    return kth;
+}
+
+template <typename Ptr>
+__device__ void bitonic_sort_desc(Ptr a, uint32_t n_pow2)
+{
+    for (uint32_t k2 = 2; k2 <= n_pow2; k2 <<= 1) {
+        for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t x = a[i], y = a[ixj];
+                    const bool desc_block = (i & k2) == 0;
+                    if (desc_block ? (x < y) : (x > y)) {
+                        a[i] = y;
+                        a[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// largest bin b such that hist[b] + hist[b+1] + ... >= k, or 0 when the whole histogram holds fewer
+// than k. n_bins is a multiple of 256. Result is returned to every thread of the block.
+__device__ uint32_t block_find_bin_from_top(const uint32_t *s_hist, int n_bins, uint32_t k, uint32_t *s_tmp /*2*/)
+{
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        uint32_t remaining = k;
+        bool done = false;
+        for (int base = n_bins - 256; base >= 0 && !done; base -= 256) {
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // lane L owns bins base+255-8L .. base+248-8L, descending
+                c[j] = s_hist[base + 255 - 8 * (int)lane - j];
+                sum += c[j];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (unsigned)o) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (remaining <= total) {
+                const uint32_t excl = incl - sum;
+                if (excl < remaining && remaining <= incl) {
+                    uint32_t r = remaining - excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (r <= c[j]) {
+                            s_tmp[0] = (uint32_t)(base + 255 - 8 * (int)lane - j);
+                            break;
+                        }
+                        r -= c[j];
+                    }
+                }
+                done = true;
+            } else {
+                remaining -= total;
+            }
+        }
+        if (!done && lane == 0) s_tmp[0] = 0;
+    }
+    __syncthreads();
+    const uint32_t bin = s_tmp[0];
+    __syncthreads();
+    return bin;
+}
+
+}  // namespace di

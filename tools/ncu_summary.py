@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep here (no GPU needed): key raw metrics per launch and the hottest source lines.
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [n_lines]"""
+import csv
+import io
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum',
+        'lts__t_sector_hit_rate.pct', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'sm__cycles_elapsed.avg', 'launch__grid_size', 'launch__waves_per_multiprocessor',
+        'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio', 'smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct',
+        'smsp__warp_issue_stalled_barrier_per_warp_active.pct', 'smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct',
+        'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_not_selected_per_warp_active.pct',
+        'smsp__warp_issue_stalled_wait_per_warp_active.pct', 'smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct']
+
+
+def run(args):
+    return subprocess.run(["ncu", "-i", *args], capture_output=True, text=True).stdout
+
+
+def main():
+    rep = sys.argv[1]
+    n_lines = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+    rows = list(csv.reader(io.StringIO(run([rep, "--page", "raw", "--csv"]))))
+    hdr, units = rows[0], rows[1]
+    print("== raw metrics (one column per captured launch)")
+    name_i = hdr.index("Kernel Name")
+    print("kernels:", [r[name_i][:40] for r in rows[2:]])
+    for w in WANT:
+        if w in hdr:
+            i = hdr.index(w)
+            print(f"{w:78s} {units[i]:10s}", [r[i] for r in rows[2:]])
+    rows = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
+    cur, kernel, agg = None, 0, []
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == 'File Path':
+            cur = r[1].split('/')[-1]
+            continue
+        if r[0] == 'Kernel Name':
+            kernel += 1
+            continue
+        if kernel > 1:
+            break
+        if r[0].isdigit() and len(r) > 8:
+            agg.append((cur, int(r[0]), r[1].strip()[:78], float(r[6] or 0), float(r[7] or 0)))
+    ti = sum(a[4] for a in agg) or 1
+    ts = sum(a[3] for a in agg) or 1
+    print(f"\n== hottest source lines of the first captured launch (warp instructions {ti:.0f}, stall samples {ts:.0f})")
+    for a in sorted(agg, key=lambda a: -a[4])[:n_lines]:
+        print(f"{a[0]:16s}:{a[1]:4d} inst={a[4] / ti * 100:5.1f}% samp={a[3] / ts * 100:5.1f}%  {a[2]}")
+
+
+if __name__ == "__main__":
+    main()
