@@ -135,6 +135,19 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
+def measured_traffic(n_docs, n_queries, top_k, world):
+    """dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json) — only when it was taken on this very configuration."""
+    try:
+        t = json.load(open(REPO / "profiles" / "r1_traffic.json"))
+        c = t["config"]
+        if (c["docs"], c["queries"], c["top_k"], c["n_gpus"]) == (n_docs, n_queries, top_k, world):
+            return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------- main arm
 def run_b200(args):
     import torch
@@ -293,9 +306,9 @@ def run_b200(args):
             # kernels of this repo launched inside the `value` timed region, all ranks
             "gpu_launches": int((launches["score_launches"] + 1 + (2 if world > 1 else 0)) * args.steps * world),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic(N, Q, k, world),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
-                         "kernel": "score_tile_kernel", "launches_per_step": launches["score_launches"],
+                         "kernel": "score_persistent_kernel", "launches_per_step": launches["score_launches"],
                          "algorithmic_bytes_per_step_this_gpu": ALGO_BYTES_PER_POSTING * local_postings,
                          "score_ms_per_step": round(float(np.mean(score_ms)), 3),
                          "finalize_ms_per_step": round(float(np.mean(final_ms)), 3)},
