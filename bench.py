@@ -142,7 +142,7 @@ def measured_traffic(n_docs, n_queries, top_k, world):
         t = json.load(open(REPO / "profiles" / "r1_traffic.json"))
         c = t["config"]
         if (c["docs"], c["queries"], c["top_k"], c["n_gpus"]) == (n_docs, n_queries, top_k, world):
-            return {"bytes_per_launch": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+            return t["dram_bytes_read"] + t["dram_bytes_write"]     # bytes per launch (one launch = one step)
     except Exception:
         pass
     return None
@@ -243,6 +243,7 @@ def run_b200(args):
     for _ in range(args.warmup):
         step_device()
     barrier()
+    index.timings()                          # the library accumulates until read: drop the warm-up records
     # ---- timed: device-resident
     score_ms, final_ms, step_ms = [], [], []
     with ClockSampler(local) as clocks:
@@ -258,6 +259,7 @@ def run_b200(args):
             t = index.timings()
             score_ms.append(t["score_ms"])
             final_ms.append(t["finalize_ms"])
+            launches = t                     # kernels this rank's library launched in this step
         barrier()
         # ---- timed: end to end through the host-buffer call
         step_e2e()
@@ -269,7 +271,7 @@ def run_b200(args):
             step_e2e()
             e2e_ms.append((time.perf_counter() - t_a) * 1e3)
         barrier()
-    launches = index.timings()
+    index.timings()                          # drop the e2e calls' records
     total_ms = torch.tensor([sum(step_ms), sum(e2e_ms), sum(score_ms)], dtype=torch.float64, device=dev)
     post = torch.tensor([local_postings], dtype=torch.int64, device=dev)
     if world > 1:
@@ -304,7 +306,8 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(h_flat.numel() * 4 + h_offs.numel() * 8),
                     "d2h_bytes_per_step": int(Q * k * 8 + Q * 4)},
             # kernels of this repo launched inside the `value` timed region, all ranks
-            "gpu_launches": int((launches["score_launches"] + 1 + (2 if world > 1 else 0)) * args.steps * world),
+            "gpu_launches": int((launches["score_launches"] + launches["other_launches"] + (3 if world > 1 else 0))
+                                * args.steps * world),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": measured_traffic(N, Q, k, world),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
@@ -320,6 +323,7 @@ def run_b200(args):
             "build": {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "tile_layout_s": round(t_tile, 2),
                       "invert_postings_per_s": round(P / (invert_ms * 1e-3)), "invert_gbs_at_17B": round(17 * P / (invert_ms * 1e-3) / 1e9, 1)},
             "postings_per_query": round(total_postings / Q),
+            "round2_queries_last_step": searcher.round2_queries,
         }
         if world == 1 and args.cpu_sample > 0:
             out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(

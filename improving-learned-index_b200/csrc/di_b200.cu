@@ -26,7 +26,7 @@ struct di_index {
 
     // search workspace (grown on demand)
     cudaStream_t stream = nullptr;
-    DevBuf ws_cand, ws_cnt, ws_theta, ws_order, ws_done;
+    DevBuf ws_cand, ws_cnt, ws_theta, ws_order, ws_done, ws_lane_keys, ws_lane_counts;
     DevBuf st_qterms, st_qoffs, st_keys, st_counts, st_docids, st_scores;
     int smem_opt_in = 0;
     bool attr_set16 = false, attr_set32 = false, attr_setfin = false;
@@ -482,8 +482,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     if (max_query_len > 65535) return set_error(DI_ERR_ARG, "queries longer than 65535 terms are not supported");
     cudaStream_t st = (cudaStream_t)stream;
     DI_CUDA(cudaSetDevice(ix->device));
-    ix->n_batches = 0;
-    ix->score_launches = ix->other_launches = 0;
+    // timings accumulate over calls until di_get_timings() reads (and clears) them
     if (n_queries == 0) return DI_OK;
 
     const bool acc32 = max_query_len > 257;  // 257 * 255 = 65535 still fits a u16 accumulator
@@ -525,14 +524,34 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     uint32_t batch = (uint32_t)std::min<uint64_t>(n_queries, std::max<uint64_t>(1, (6ull << 30) / per_query));
     if ((n_queries + batch - 1) / batch > (uint32_t)di_index::kMaxBatches)
         batch = (n_queries + di_index::kMaxBatches - 1) / di_index::kMaxBatches;
-    DI_TRY(ensure(ix->ws_cand, (size_t)batch * per_query));
-    DI_TRY(ensure(ix->ws_cnt, (size_t)batch * 4));
-    DI_TRY(ensure(ix->ws_theta, (size_t)batch * 8));
+    // A query is one chain of tiles; a batch smaller than the GPU (fewer queries than resident CTAs) is
+    // widened by cutting the tile range into `lanes` independent sub-ranges per query, merged at the end.
+    uint32_t lanes = 1;
+    if (!per_tile_launches && ix->n_tiles > 1 && batch < (uint32_t)resident_ctas) {
+        lanes = std::min<uint32_t>(ix->n_tiles, ((uint32_t)resident_ctas + batch - 1) / batch);
+        lanes = std::min<uint32_t>(lanes, std::max<uint32_t>(1, 16384 / top_k));  // the lane merge stays in shared memory
+        lanes = (uint32_t)std::min<uint64_t>(lanes, std::max<uint64_t>(1, (6ull << 30) / (per_query * batch)));
+    }
+    const uint32_t tiles_per_lane = ix->n_tiles ? (ix->n_tiles + lanes - 1) / lanes : 0;
+    if (tiles_per_lane) lanes = (ix->n_tiles + tiles_per_lane - 1) / tiles_per_lane;
+    const size_t n_virtual = (size_t)batch * lanes;
+    DI_TRY(ensure(ix->ws_cand, n_virtual * per_query));
+    DI_TRY(ensure(ix->ws_cnt, n_virtual * 4));
+    DI_TRY(ensure(ix->ws_theta, n_virtual * 8));
     DI_TRY(ensure(ix->ws_order, (size_t)batch * sizeof(QueryRec)));
-    DI_TRY(ensure(ix->ws_done, 8 + (size_t)batch * 4));
+    DI_TRY(ensure(ix->ws_done, 8 + n_virtual * 4));
+    if (lanes > 1) {
+        DI_TRY(ensure(ix->ws_lane_keys, n_virtual * top_k * 8));
+        DI_TRY(ensure(ix->ws_lane_counts, n_virtual * 4));
+    }
 
     for (uint32_t q0 = 0; q0 < n_queries; q0 += batch) {
         const uint32_t nq = std::min(batch, n_queries - q0);
+        const size_t nv = (size_t)nq * lanes;
+        if (ix->n_batches == di_index::kMaxBatches) {  // nobody is reading them: start over
+            ix->n_batches = 0;
+            ix->score_launches = ix->other_launches = 0;
+        }
         const int b = ix->n_batches++;
         for (int e = 0; e < 3; ++e)
             if (!ix->ev[b][e]) DI_CUDA(cudaEventCreate(&ix->ev[b][e]));
@@ -553,8 +572,12 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         a.k = top_k;
         a.top_shift = top_shift;
         a.recs = ix->ws_order.as<QueryRec>();
-        DI_CUDA(cudaMemsetAsync(a.cnt, 0, (size_t)nq * 4, st));
-        DI_CUDA(cudaMemsetAsync(a.theta, 0, (size_t)nq * 8, st));
+        a.n_queries = nq;
+        a.n_tiles = ix->n_tiles;
+        a.lanes = lanes;
+        a.tiles_per_lane = tiles_per_lane;
+        DI_CUDA(cudaMemsetAsync(a.cnt, 0, nv * 4, st));
+        DI_CUDA(cudaMemsetAsync(a.theta, 0, nv * 8, st));
         DI_CUDA(cudaEventRecord(ix->ev[b][0], st));
         if (ix->n_tiles) {
             query_order_kernel<<<1, 1024, 0, st>>>(d_q_terms, a.q_offsets, ix->d_df, ix->n_terms, nq,
@@ -571,24 +594,32 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
                     score_tile_kernel<false><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
                 ++ix->score_launches;
             }
-        } else if (ix->n_tiles) {  // one persistent launch over all (tile, query) items of the batch
+        } else if (ix->n_tiles) {  // one persistent launch over all (lane, query, tile) items of the batch
             a.done = ix->ws_done.as<uint32_t>() + 2;  // [0..1] hold the 64-bit work counter
             unsigned long long *counter = ix->ws_done.as<unsigned long long>();
-            DI_CUDA(cudaMemsetAsync(ix->ws_done.p, 0, 8 + (size_t)nq * 4, st));
-            const uint64_t n_items = (uint64_t)ix->n_tiles * nq;
+            DI_CUDA(cudaMemsetAsync(ix->ws_done.p, 0, 8 + nv * 4, st));
+            const uint64_t n_items = (uint64_t)tiles_per_lane * nv;
             const unsigned grid = (unsigned)std::min<uint64_t>(n_items, (uint64_t)resident_ctas);
             if (acc32)
-                score_persistent_kernel<true><<<grid, kScoreThreads, acc_bytes, st>>>(a, ix->n_tiles, nq, counter);
+                score_persistent_kernel<true><<<grid, kScoreThreads, acc_bytes, st>>>(a, counter);
             else
-                score_persistent_kernel<false><<<grid, kScoreThreads, acc_bytes, st>>>(a, ix->n_tiles, nq, counter);
+                score_persistent_kernel<false><<<grid, kScoreThreads, acc_bytes, st>>>(a, counter);
             ++ix->score_launches;
         }
         DI_KERNEL_CHECK();
         DI_CUDA(cudaEventRecord(ix->ev[b][1], st));
-        DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, top_shift, /*max_n=*/c0, nq,
-                               d_out_keys + (uint64_t)q0 * top_k, d_out_counts + q0, st));
-        DI_KERNEL_CHECK();
-        ++ix->other_launches;
+        uint64_t *out_keys = d_out_keys + (uint64_t)q0 * top_k;
+        uint32_t *out_counts = d_out_counts + q0;
+        if (lanes == 1) {
+            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, top_shift, /*max_n=*/c0, nq, out_keys, out_counts, st));
+            ++ix->other_launches;
+        } else {  // per-lane top-k rows [lanes][nq][k], then the same merge the multi-GPU path uses
+            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, top_shift, /*max_n=*/c0, (uint32_t)nv,
+                                   ix->ws_lane_keys.as<uint64_t>(), ix->ws_lane_counts.as<uint32_t>(), st));
+            DI_TRY(di_merge_topk_dev(ix->ws_lane_keys.as<uint64_t>(), ix->ws_lane_counts.as<uint32_t>(), lanes, nq, top_k, top_k,
+                                     out_keys, out_counts, nullptr, st));
+            ix->other_launches += 3;
+        }
         DI_CUDA(cudaEventRecord(ix->ev[b][2], st));
     }
     return DI_OK;
@@ -652,23 +683,30 @@ extern "C" int di_search(di_index_t *ix, const uint32_t *q_terms, const uint64_t
 }
 
 extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_counts_in, uint32_t n_shards,
-                                 uint32_t n_queries, uint32_t top_k, uint64_t *d_keys_out, uint32_t *d_counts_out,
-                                 void *stream)
+                                 uint32_t n_queries, uint32_t k_in, uint32_t top_k, uint64_t *d_keys_out,
+                                 uint32_t *d_counts_out, uint32_t *d_incomplete, void *stream)
 {
     if (n_queries == 0 || n_shards == 0) return DI_OK;
     if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
+    if (k_in == 0 || k_in > 65536) return set_error(DI_ERR_ARG, "k_in must be in [1, 65536], got %u", k_in);
     cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t cap = pow2_ceil(n_shards * top_k);
+    const uint32_t cap = pow2_ceil(std::max(n_shards * k_in, top_k));
     // scratch is cached per host thread (one process per GPU drives one merge stream) and only
     // grows, so the steady state has no allocation and the call stays asynchronous
     static thread_local DevBuf cand, cnt;
     DI_TRY(ensure(cand, (size_t)n_queries * cap * 8));
     DI_TRY(ensure(cnt, (size_t)n_queries * 4));
-    merge_gather_kernel<<<n_queries, 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, top_k, cand.as<uint64_t>(),
+    merge_gather_kernel<<<n_queries, 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, k_in, cand.as<uint64_t>(),
                                                   cnt.as<uint32_t>(), cap);
     DI_KERNEL_CHECK();
-    return launch_finalize(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k, 48, /*max_n=*/n_shards * top_k, n_queries,
-                           d_keys_out, d_counts_out, st);
+    DI_TRY(launch_finalize(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k, 48, /*max_n=*/n_shards * k_in, n_queries,
+                           d_keys_out, d_counts_out, st));
+    if (d_incomplete) {
+        merge_check_kernel<<<grid_for(n_queries, 256), 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, k_in, top_k,
+                                                                    d_keys_out, d_counts_out, d_incomplete);
+        DI_KERNEL_CHECK();
+    }
+    return DI_OK;
 }
 
 extern "C" int di_get_timings(di_index_t *ix, di_timings *out)
@@ -691,5 +729,7 @@ extern "C" int di_get_timings(di_index_t *ix, di_timings *out)
     }
     out->score_launches = ix->score_launches;
     out->other_launches = ix->other_launches;
+    ix->n_batches = 0;
+    ix->score_launches = ix->other_launches = 0;
     return DI_OK;
 }

@@ -55,7 +55,11 @@ struct SearchArgs {
     uint32_t cap, c0, k;
     int top_shift;              // highest radix-select digit that can be non-zero
     const QueryRec *recs;       // [n_queries] work-item records in launch order
-    uint32_t *done;             // [n_queries] tiles completed per query (persistent launch), or nullptr
+    uint32_t *done;             // [lanes * n_queries] tiles completed per (lane, query) (persistent launch), or nullptr
+    // Small batches cannot fill the GPU with one tile chain per query, so the tile range is cut into
+    // `lanes` contiguous sub-ranges that run independently (own candidate list and threshold per
+    // (lane, query), all per-query arrays are [lanes][n_queries]) and are merged like shards afterwards.
+    uint32_t n_queries, n_tiles, lanes, tiles_per_lane;
 };
 
 // Launch order of a batch: queries bucketed by log2 of their total posting count (sum of the document
@@ -189,7 +193,7 @@ __device__ __forceinline__ void emit_candidate(uint32_t score, uint32_t docid, u
 
 // One (query, tile) work item; `slot` indexes the batch's launch-ordered query records.
 template <bool ACC32>
-__device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, uint32_t slot)
+__device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, uint32_t slot, uint32_t lane, uint32_t step)
 {
     extern __shared__ uint4 s_acc4[];  // tile accumulators
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_acc4);
@@ -208,13 +212,14 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     // holds everything needed to start: the dependent-load chain is record -> descriptor -> postings.
     const QueryRec *__restrict__ rec = p.recs + slot;
     const uint32_t q = rec->q;
+    const uint32_t sq = lane * p.n_queries + q;  // this (lane, query)'s slot in the per-query state arrays
     const uint64_t qb = rec->begin, qe = rec->begin + rec->n;
     const uint32_t T = p.tile_docs;
     // The query's running state (threshold, candidate list) is handed from tile to tile through
     // global memory; tile t may start once tile t-1 of the same query has published (done[q] >= t).
     // Items are dispatched in tile-major order, so this is almost always already true: probe now,
     // and only wait (before phase 3) in the rare case it is not.
-    if (tid == 0) s_ready = p.done == nullptr || tile == 0 || ld_flag_u32(p.done + q) >= tile;
+    if (tid == 0) s_ready = p.done == nullptr || step == 0 || ld_flag_u32(p.done + sq) >= step;
     const SegDesc *__restrict__ desc = p.desc + (uint64_t)tile * p.n_terms;
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
 
@@ -246,8 +251,8 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
         const uint32_t nd = s_nd, ns = s_ns;
         if (first && r0 + kMaxSeg >= qe && nd + ns == 0) return false;  // query has no posting in this tile
         if (first && s_ready) {  // state already published: fetch it now (L2), it is needed only in phase 3
-            theta = ld_cg_u64(p.theta + q);
-            cnt0 = ld_cg_u32(p.cnt + q);
+            theta = ld_cg_u64(p.theta + sq);
+            cnt0 = ld_cg_u32(p.cnt + sq);
             have_state = true;
         }
         touched = touched || (nd + ns) != 0;
@@ -320,18 +325,18 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     if (!have_state) {
         if (tid == 0) {
             uint32_t spins = 0;
-            while (ld_flag_u32(p.done + q) < tile) {
+            while (ld_flag_u32(p.done + sq) < step) {
                 __nanosleep(128);
                 if (++spins > (1u << 23)) __trap();  // > 1 s: a protocol bug must fail loudly, never hang the GPU
             }
         }
         __syncthreads();
-        theta = ld_cg_u64(p.theta + q);
-        cnt0 = ld_cg_u32(p.cnt + q);
+        theta = ld_cg_u64(p.theta + sq);
+        cnt0 = ld_cg_u32(p.cnt + sq);
     }
     uint32_t ths = (uint32_t)(theta >> 32);
     if (ths == 0) ths = 1;  // score 0 = document not touched: never a result (inverted_index.py:58-62)
-    uint64_t *__restrict__ cand = p.cand + (uint64_t)q * p.cap;
+    uint64_t *__restrict__ cand = p.cand + (uint64_t)sq * p.cap;
     const uint32_t doc_base = p.doc_lo + (tile << p.tile_shift);
     // A document that only TIES the threshold score needs docid <= the threshold's docid. Tiles are
     // visited in docid order, so the threshold's document lies in an earlier tile and every such tie in
@@ -417,9 +422,9 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
             kth = block_select_kth<true>(cand, n, p.k, p.top_shift, s_hist, s_tmp);
             n = block_compact_ge<true>(cand, n, kth, s_scan);
         }
-        if (tid == 0) p.theta[q] = kth;
+        if (tid == 0) p.theta[sq] = kth;
     }
-    if (tid == 0) p.cnt[q] = n;
+    if (tid == 0) p.cnt[sq] = n;
     return true;  // the query's state was read after done[q] >= tile was observed
 }
 
@@ -427,7 +432,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
 template <bool ACC32>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS) score_tile_kernel(SearchArgs p, uint32_t tile)
 {
-    score_item<ACC32>(p, tile, blockIdx.x);  // p.done == nullptr: the launch boundary orders the tiles
+    score_item<ACC32>(p, tile, blockIdx.x, 0, tile);  // p.done == nullptr: the launch boundary orders the tiles
 }
 
 // ---- launch form B: ONE persistent launch for all tiles of the batch ---------------------------
@@ -437,33 +442,38 @@ __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS
 // is published with release semantics; the next tile of the same query acquires it.
 template <bool ACC32>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS)
-score_persistent_kernel(SearchArgs p, uint32_t n_tiles, uint32_t n_queries, unsigned long long *counter)
+score_persistent_kernel(SearchArgs p, unsigned long long *counter)
 {
     __shared__ unsigned long long s_item;
-    const unsigned long long n_items = (unsigned long long)n_tiles * n_queries;
+    const uint32_t n_virtual = p.lanes * p.n_queries;  // (lane, query) chains
+    const unsigned long long n_items = (unsigned long long)p.tiles_per_lane * n_virtual;
     for (;;) {
         __syncthreads();  // everybody is done with the previous item's shared memory
         if (threadIdx.x == 0) s_item = atomicAdd(counter, 1ull);
         __syncthreads();
         const unsigned long long item = s_item;
         if (item >= n_items) break;
-        const uint32_t tile = (uint32_t)(item / n_queries), slot = (uint32_t)(item % n_queries);
-        const bool synced = score_item<ACC32>(p, tile, slot);
+        // step-major: all chains advance together, so the GPU works on `lanes` tiles at a time
+        const uint32_t step = (uint32_t)(item / n_virtual), v = (uint32_t)(item % n_virtual);
+        const uint32_t lane = v / p.n_queries, slot = v % p.n_queries;
+        const uint32_t tile = lane * p.tiles_per_lane + step;
+        if (tile >= p.n_tiles) continue;  // the last lane may be shorter; nobody waits on these steps
+        const bool synced = score_item<ACC32>(p, tile, slot, lane, step);
         // Hand-off: CTA barrier, then ONE thread publishes with a release store (MEMBAR.GPU + store). The
         // barrier orders every thread's candidate / threshold writes before the release (the pattern
         // cooperative-groups grid sync relies on). done[q] must grow one tile at a time: an item that had
         // nothing to do in this tile still waits for the previous tile before announcing the next.
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint32_t *flag = p.done + p.recs[slot].q;
-            if (!synced && tile != 0) {
+            uint32_t *flag = p.done + lane * p.n_queries + p.recs[slot].q;
+            if (!synced && step != 0) {
                 uint32_t spins = 0;
-                while (ld_flag_u32(flag) < tile) {
+                while (ld_flag_u32(flag) < step) {
                     __nanosleep(64);
                     if (++spins > (1u << 23)) __trap();
                 }
             }
-            st_release_u32(flag, tile + 1);
+            st_release_u32(flag, step + 1);
         }
     }
 }

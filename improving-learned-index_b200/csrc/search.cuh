@@ -96,4 +96,26 @@ __global__ void merge_gather_kernel(const uint64_t *__restrict__ keys_in, const 
     if (threadIdx.x == 0) cnt[q] = run;
 }
 
+// When shards return only their k_in < k best keys, the merged top-k is exact unless some shard that
+// filled its row could still hold a better key than the merged k-th: every key it did NOT return is
+// below its last returned key, so the merge is proven complete iff last_returned <= merged k-th for all
+// full shards (and the merge itself holds k keys). incomplete[q] = 1 marks the queries to re-run with
+// full rows.
+__global__ void merge_check_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ counts_in,
+                                   uint32_t n_shards, uint32_t n_queries, uint32_t k_in, uint32_t k_out,
+                                   const uint64_t *__restrict__ keys_out, const uint32_t *__restrict__ counts_out,
+                                   uint32_t *__restrict__ incomplete)
+{
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_queries; q += gridDim.x * blockDim.x) {
+        const uint32_t n = counts_out[q];
+        const uint64_t kth = n == k_out ? keys_out[(uint64_t)q * k_out + k_out - 1] : 0ull;  // 0: fewer than k found
+        uint32_t bad = 0;
+        for (uint32_t s = 0; s < n_shards; ++s) {
+            const uint64_t row = (uint64_t)s * n_queries + q;
+            if (counts_in[row] == k_in && keys_in[row * k_in + k_in - 1] > kth) bad = 1;
+        }
+        incomplete[q] = bad;
+    }
+}
+
 }  // namespace di

@@ -187,7 +187,8 @@ def unpack_keys_device(d_keys, n: int, d_docids, d_scores, stream: int = 0):
 
 
 def merge_topk_device(d_keys_in, d_counts_in, n_shards: int, n_queries: int, top_k: int, d_keys_out, d_counts_out,
-                      stream: int = 0):
-    """K5: [n_shards][n_queries][k] gathered keys -> global top-k per query."""
-    N.check(N.lib().di_merge_topk_dev(N.ptr(d_keys_in), N.ptr(d_counts_in), n_shards, n_queries, top_k,
-                                      N.ptr(d_keys_out), N.ptr(d_counts_out), stream))
+                      stream: int = 0, k_in: int = 0, d_incomplete=None):
+    """K5: [n_shards][n_queries][k_in] gathered keys -> global top-k per query. With k_in < top_k,
+    d_incomplete[q] = 1 marks queries whose merge could not be proven exact (re-run them with full rows)."""
+    N.check(N.lib().di_merge_topk_dev(N.ptr(d_keys_in), N.ptr(d_counts_in), n_shards, n_queries, k_in or top_k, top_k,
+                                      N.ptr(d_keys_out), N.ptr(d_counts_out), N.ptr(d_incomplete), stream))

@@ -4,17 +4,24 @@ New functionality: the reference searches on one host only (its parallelism is a
 process pool, ranker.py:44-46). Documents are split into `world_size` contiguous docid ranges;
 rank r holds a full-vocabulary shard of range r with GLOBAL docids. Every rank scores every
 query on its shard (no data-path collective: a document's score depends only on its own
-postings), then the per-shard top-k keys — (score << 32 | ~docid), sorted — are all-gathered
+postings), then the per-shard best keys — (score << 32 | ~docid), sorted — are all-gathered
 (NCCL over NVLink on GPUs; gloo in the CPU tests) and merged by K5 into the global top-k, which
 is identical to the single-GPU result because the key order is total.
 
+Two rounds keep it exact AND cheap. Round 1 asks every shard for only k_in < k keys (about
+1.25 k / G + 64: with G shards each holds ~k/G of the global top-k), which cuts the per-shard selection
+work and the gathered bytes by ~G/1.25. The merge proves the result complete per query: a shard that
+filled its row could only hide keys below its last returned key, so the merged top-k is exact iff that
+key is <= the merged k-th (merge_check_kernel). The (rare, e.g. docid-clustered relevance) queries that
+fail the proof are re-run in round 2 with full rows of k keys.
+
 The collective and the two compute steps are injected, so the plumbing (ranges, tensor layout of
-the gather, count handling) is testable on CPU with world_size 2 while the CUDA path plugs in
-DeviceIndex.search_device and engine.merge_topk_device.
+the gather, count handling, the two-round protocol) is testable on CPU with world_size 2 while the
+CUDA path plugs in DeviceIndex.search_device and engine.merge_topk_device.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Sequence, Tuple
+from typing import Callable, Sequence, Tuple
 
 import numpy as np
 
@@ -25,6 +32,13 @@ def shard_range(n_docs: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Contiguous docid range [lo, hi) of `rank`: ceil(n_docs / world_size) docs per shard."""
     per = -(-n_docs // world_size)
     return min(rank * per, n_docs), min((rank + 1) * per, n_docs)
+
+
+def shard_k(k: int, world_size: int) -> int:
+    """Keys each shard returns in round 1."""
+    if world_size <= 2:   # with two shards the rows would shrink by < 1/3: not worth a possible second round
+        return k
+    return min(k, -(-5 * k // (4 * world_size)) + 64)
 
 
 def pack_keys(scores: np.ndarray, docids: np.ndarray) -> np.ndarray:
@@ -38,15 +52,16 @@ def unpack_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 
 
 class ShardedSearcher:
-    """search(): local top-k on this rank's shard -> all_gather -> merge. Call on every rank with the
-    same queries; every rank gets the global result.
+    """search(): local best keys on this rank's shard -> all_gather -> merge (+ proof, + round 2).
+    Call on every rank with the same queries; every rank gets the global result.
 
     local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, out_keys, out_counts) fills this shard's
     sorted keys [Q, k] (int64 bit patterns) and counts [Q] (int32) — torch tensors on `device`.
-    merge(gathered_keys [G,Q,k], gathered_counts [G,Q], G, Q, k, out_keys, out_counts) writes the global top-k.
+    merge(gathered_keys [G,Q,k_in], gathered_counts [G,Q], G, Q, k_in, k, out_keys [Q,k], out_counts [Q],
+    incomplete [Q] int32) writes the global top-k and flags the queries whose merge is not proven exact.
     """
 
-    def __init__(self, local_search: Callable, merge: Callable, device, group=None):
+    def __init__(self, local_search: Callable, merge: Callable, device, group=None, rows_per_shard=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -55,7 +70,9 @@ class ShardedSearcher:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self._buffers = None
+        self._buffers = {}
+        self.rows_per_shard = rows_per_shard   # optional override of shard_k: k -> keys per shard in round 1
+        self.round2_queries = 0          # how many queries the last search had to re-run
 
     @classmethod
     def for_device_index(cls, index: "engine.DeviceIndex", device, group=None) -> "ShardedSearcher":
@@ -64,29 +81,61 @@ class ShardedSearcher:
         def local_search(qt, qo, n_q, max_len, k, out_keys, out_counts):
             index.search_device(qt, qo, n_q, max_len, k, out_keys, out_counts, torch.cuda.current_stream().cuda_stream)
 
-        def merge(g_keys, g_counts, n_shards, n_q, k, out_keys, out_counts):
+        def merge(g_keys, g_counts, n_shards, n_q, k_in, k, out_keys, out_counts, incomplete):
             engine.merge_topk_device(g_keys, g_counts, n_shards, n_q, k, out_keys, out_counts,
-                                     torch.cuda.current_stream().cuda_stream)
+                                     torch.cuda.current_stream().cuda_stream, k_in=k_in, d_incomplete=incomplete)
         return cls(local_search, merge, device, group)
+
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape))
+        if key not in self._buffers:
+            self._buffers[key] = self.torch.zeros(shape, dtype=dtype, device=self.device)
+        return self._buffers[key]
+
+    def _round(self, d_q_terms, d_q_offsets, n_queries, max_len, k_in, k, tag):
+        """One gather + merge with rows of k_in keys. Returns (keys [Q,k], counts [Q], incomplete [Q])."""
+        torch, dist = self.torch, self.dist
+        keys = self._buf(tag + "keys", (n_queries, k_in), torch.int64)
+        counts = self._buf(tag + "counts", (n_queries,), torch.int32)
+        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k_in, keys, counts)
+        g_keys = self._buf(tag + "g_keys", (self.world, n_queries, k_in), torch.int64)
+        g_counts = self._buf(tag + "g_counts", (self.world, n_queries), torch.int32)
+        # concatenated-along-dim-0 form: accepted by both the NCCL and the gloo backend
+        dist.all_gather_into_tensor(g_keys.view(self.world * n_queries, k_in), keys, group=self.group)
+        dist.all_gather_into_tensor(g_counts.view(self.world * n_queries), counts, group=self.group)
+        out_keys = self._buf(tag + "out_keys", (n_queries, k), torch.int64)
+        out_counts = self._buf(tag + "out_counts", (n_queries,), torch.int32)
+        incomplete = self._buf(tag + "incomplete", (n_queries,), torch.int32)
+        self.merge(g_keys, g_counts, self.world, n_queries, k_in, k, out_keys, out_counts, incomplete)
+        return out_keys, out_counts, incomplete
 
     def search_tensors(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
         """Device-level entry: returns (keys [Q,k] int64, counts [Q] int32) tensors holding the GLOBAL top-k.
         The returned tensors are owned by the searcher and overwritten by the next call."""
-        torch, dist = self.torch, self.dist
-        if self._buffers is None or self._buffers[0] != (n_queries, k):      # reused across calls of one shape
-            def buf(*shape, dtype):
-                return torch.zeros(shape, dtype=dtype, device=self.device)
-            self._buffers = ((n_queries, k), buf(n_queries, k, dtype=torch.int64), buf(n_queries, dtype=torch.int32),
-                             buf(self.world, n_queries, k, dtype=torch.int64), buf(self.world, n_queries, dtype=torch.int32),
-                             buf(n_queries, k, dtype=torch.int64), buf(n_queries, dtype=torch.int32))
-        _, keys, counts, g_keys, g_counts, out_keys, out_counts = self._buffers
-        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)
+        torch = self.torch
+        self.round2_queries = 0
         if self.world == 1:
+            keys = self._buf("keys", (n_queries, k), torch.int64)
+            counts = self._buf("counts", (n_queries,), torch.int32)
+            self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)
             return keys, counts
-        # concatenated-along-dim-0 form: accepted by both the NCCL and the gloo backend
-        dist.all_gather_into_tensor(g_keys.view(self.world * n_queries, k), keys, group=self.group)
-        dist.all_gather_into_tensor(g_counts.view(self.world * n_queries), counts, group=self.group)
-        self.merge(g_keys, g_counts, self.world, n_queries, k, out_keys, out_counts)
+        k_in = min(k, self.rows_per_shard(k)) if self.rows_per_shard else shard_k(k, self.world)
+        out_keys, out_counts, incomplete = self._round(d_q_terms, d_q_offsets, n_queries, max_len, k_in, k, "r1_")
+        if k_in < k:
+            # the flags derive from gathered data, identical on every rank: all ranks take the same branch
+            redo = torch.nonzero(incomplete).flatten()
+            if redo.numel():
+                self.round2_queries = int(redo.numel())
+                offs = d_q_offsets.to(torch.int64)
+                lens = (offs[1:] - offs[:-1])[redo]
+                new_offs = torch.zeros(redo.numel() + 1, dtype=torch.int64, device=self.device)
+                torch.cumsum(lens, 0, out=new_offs[1:])
+                idx = torch.repeat_interleave(offs[:-1][redo] - new_offs[:-1], lens) + torch.arange(
+                    int(new_offs[-1]), device=self.device)
+                sub_terms = d_q_terms[idx] if idx.numel() else d_q_terms[:1]
+                k2, c2, _ = self._round(sub_terms.contiguous(), new_offs, int(redo.numel()), max_len, k, k, "r2_")
+                out_keys[redo] = k2
+                out_counts[redo] = c2
         return out_keys, out_counts
 
     def search(self, queries: Sequence[Sequence[int]], k: int):

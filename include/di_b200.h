@@ -148,17 +148,23 @@ int di_unpack_keys_dev(const uint64_t *d_keys, uint64_t n, uint32_t *d_docids, i
 
 /* ------------------------------------------------------------------ K5: cross-shard top-k merge
  * New functionality (the reference is single-host): d_keys_in holds n_shards blocks of
- * [n_queries][top_k] sorted keys (as gathered over NCCL), d_counts_in n_shards x [n_queries].
- * Output: the global top_k per query in the same deterministic order.
+ * [n_queries][k_in] sorted keys (as gathered over NCCL), d_counts_in n_shards x [n_queries].
+ * Output: the global top_k per query in the same deterministic order, rows of top_k keys.
+ * Shards may return fewer keys than top_k (k_in < top_k, less traffic and less per-shard selection
+ * work). The merge is then exact unless a shard that filled its row could still hold a better key; if
+ * d_incomplete is not NULL it receives 1 for exactly those queries (0 otherwise) and the caller re-runs
+ * them with k_in = top_k (improving-learned-index_b200/sharded.py does). With k_in == top_k no query is
+ * ever flagged.
  */
 int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_counts_in,
-                      uint32_t n_shards, uint32_t n_queries, uint32_t top_k,
-                      uint64_t *d_keys_out, uint32_t *d_counts_out, void *stream);
+                      uint32_t n_shards, uint32_t n_queries, uint32_t k_in, uint32_t top_k,
+                      uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_incomplete, void *stream);
 
 /* ------------------------------------------------------------------ measurement hooks
- * Device time (CUDA events on the launching stream) of the last di_search / di_search_dev call. */
+ * Device time (CUDA events on the launching stream) of the di_search / di_search_dev calls made since the
+ * previous di_get_timings() (reading clears the record). */
 typedef struct di_timings {
-    float score_ms;      /* all score_tile launches */
+    float score_ms;      /* score kernel launches */
     float finalize_ms;   /* final select + sort */
     float total_ms;      /* first kernel to last kernel */
     uint32_t score_launches;

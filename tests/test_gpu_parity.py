@@ -269,6 +269,52 @@ def test_shards_and_merge_equal_single_index():
     assert sum(s.info()["n_postings"] for s in shards) == full.info()["n_postings"]
 
 
+def test_short_rows_merge_proves_or_flags():
+    """K5 with k_in < k: unflagged queries must equal the single-index result; a query whose top-k sits in
+    one shard must be flagged (and is exact again once re-run with full rows)."""
+    torch = pytest.importorskip("torch")
+    x = quantized_csr(6000, 900, 60, 41)
+    # term 900 lives only in documents 0..599 (first shard)
+    toff = np.concatenate([x["toff"], [x["toff"][-1] + 600]]).astype(np.uint64)
+    docs = np.concatenate([x["docs"], np.arange(600, dtype=np.uint32)])
+    vals = np.concatenate([x["vals"], (255 - np.arange(600) % 100).astype(np.uint8)])
+    full = engine.DeviceIndex.from_csr(toff, docs, vals, tile_docs=1024)
+    queries = syn.make_queries(30, vocab_size=900, seed=6)
+    queries[7] = [900]
+    k, k_in = 300, 120
+    want = full.search(queries, k)
+    bounds = [(0, 2000), (2000, 4000), (4000, 6000)]
+    flat, offs = engine.flatten_queries(queries)
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    d_flat = torch.from_numpy(flat.astype(np.int64)).to(dev).to(torch.int32)
+    d_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    shards = [engine.DeviceIndex.from_csr(toff, docs, vals, doc_lo=lo, doc_hi=hi, tile_docs=1024) for lo, hi in bounds]
+
+    def run(rows):
+        keys = torch.zeros((3, len(queries), rows), dtype=torch.int64, device=dev)
+        counts = torch.zeros((3, len(queries)), dtype=torch.int32, device=dev)
+        for s, shard in enumerate(shards):
+            shard.search_device(d_flat, d_offs, len(queries), max(len(q) for q in queries), rows, keys[s], counts[s], st)
+        out_keys = torch.zeros((len(queries), k), dtype=torch.int64, device=dev)
+        out_counts = torch.zeros(len(queries), dtype=torch.int32, device=dev)
+        flags = torch.full((len(queries),), 7, dtype=torch.int32, device=dev)
+        engine.merge_topk_device(keys, counts, 3, len(queries), k, out_keys, out_counts, st, k_in=rows, d_incomplete=flags)
+        torch.cuda.synchronize()
+        keys_np = out_keys.cpu().numpy().view(np.uint64)
+        return ((~(keys_np & np.uint64(0xFFFFFFFF)).astype(np.uint32)), (keys_np >> np.uint64(32)).astype(np.int32),
+                out_counts.cpu().numpy().view(np.uint32), flags.cpu().numpy())
+
+    d, s, c, flags = run(k_in)
+    assert flags[7] == 1 and set(flags.tolist()) <= {0, 1}
+    for i in np.flatnonzero(flags == 0):
+        n = int(want[2][i])
+        assert c[i] == n and np.array_equal(d[i, :n], want[0][i, :n]) and np.array_equal(s[i, :n], want[1][i, :n]), i
+    d, s, c, flags = run(k)
+    assert not flags.any()
+    assert_same_results((d, s, c), want, "full rows")
+
+
 # ------------------------------------------------------------------ in-memory twin, ranker, metrics
 def test_sparse_search_golden(golden):
     g = golden("sparse")

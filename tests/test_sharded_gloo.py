@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from improving_learned_index_b200 import synthetic as syn
-from improving_learned_index_b200.sharded import ShardedSearcher, pack_keys, shard_range, unpack_keys
+from improving_learned_index_b200.sharded import ShardedSearcher, pack_keys, shard_k, shard_range, unpack_keys
 from oracle import oracle
 from helpers import quantized_csr
 
@@ -38,38 +38,60 @@ def _worker(rank, world, port, out_dict):
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     x = quantized_csr(4000, 600, 50, 77)
+    # term 600: only documents 0..699 (all inside shard 0) carry it, with their best impacts -> a query on it has
+    # its whole top-k in one shard, which round 1 (k_in < k keys per shard) cannot prove complete
+    extra_docs = np.arange(700, dtype=np.uint32)
+    extra_vals = (255 - (extra_docs % 200)).astype(np.uint8)
+    toff_full = np.concatenate([x["toff"], [x["toff"][-1] + extra_docs.size]]).astype(np.uint64)
+    docs_full = np.concatenate([x["docs"], extra_docs])
+    vals_full = np.concatenate([x["vals"], extra_vals])
+    n_terms = 601
     lo, hi = shard_range(x["n_docs"], world, rank)
-    term_of = np.repeat(np.arange(600), np.diff(x["toff"].astype(np.int64)))
-    sel = (x["docs"] >= lo) & (x["docs"] < hi)
-    toff = np.zeros(601, dtype=np.uint64)
-    toff[1:] = np.cumsum(np.bincount(term_of[sel], minlength=600))
-    docs, vals = x["docs"][sel], x["vals"][sel]
+    term_of = np.repeat(np.arange(n_terms), np.diff(toff_full.astype(np.int64)))
+    sel = (docs_full >= lo) & (docs_full < hi)
+    toff = np.zeros(n_terms + 1, dtype=np.uint64)
+    toff[1:] = np.cumsum(np.bincount(term_of[sel], minlength=n_terms))
+    docs, vals = docs_full[sel], vals_full[sel]
     queries = syn.make_queries(25, vocab_size=600, seed=4)
     queries[3] = []
+    queries[5] = [600]
+    queries[6] = [600, queries[6][0]]
+    calls = []
 
     def local_search(qt, qo, n_q, max_len, k, out_keys, out_counts):
-        d, s, c, _ = oracle.score_topk_csr(toff, docs, vals, x["n_docs"], queries, k)
+        offs = qo.numpy().astype(np.int64)
+        flat = qt.numpy().view(np.uint32)
+        qs = [flat[offs[i]:offs[i + 1]].tolist() for i in range(n_q)]
+        calls.append((n_q, k))
+        d, s, c, _ = oracle.score_topk_csr(toff, docs, vals, x["n_docs"], qs, k)
         keys = np.zeros((n_q, k), dtype=np.uint64)
         for i in range(n_q):
             keys[i, :c[i]] = pack_keys(s[i, :c[i]], d[i, :c[i]])
         out_keys.copy_(torch.from_numpy(keys.view(np.int64)))
         out_counts.copy_(torch.from_numpy(c.astype(np.int32)))
 
-    def merge(g_keys, g_counts, n_shards, n_q, k, out_keys, out_counts):
+    def merge(g_keys, g_counts, n_shards, n_q, k_in, k, out_keys, out_counts, incomplete):
         gk, gc = g_keys.numpy().view(np.uint64), g_counts.numpy()
-        assert gk.shape == (n_shards, n_q, k) and gc.shape == (n_shards, n_q)
+        assert gk.shape == (n_shards, n_q, k_in) and gc.shape == (n_shards, n_q)
         for q in range(n_q):
             allk = np.concatenate([gk[s, q, :gc[s, q]] for s in range(n_shards)])
             top = np.sort(allk)[::-1][:k]
             out_keys[q, :top.size] = torch.from_numpy(top.copy().view(np.int64))
             out_counts[q] = top.size
+            kth = top[-1] if top.size == k else np.uint64(0)
+            incomplete[q] = int(any(gc[s, q] == k_in and gk[s, q, k_in - 1] > kth for s in range(n_shards)))
 
-    searcher = ShardedSearcher(local_search, merge, torch.device("cpu"))
-    d, s, c = searcher.search(queries, 50)
-    want = oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], x["n_docs"], queries, 50)
-    ok = np.array_equal(c, want[2])
-    for i in range(len(queries)):
-        ok = ok and np.array_equal(d[i, :c[i]], want[0][i, :c[i]]) and np.array_equal(s[i, :c[i]], want[1][i, :c[i]])
+    searcher = ShardedSearcher(local_search, merge, torch.device("cpu"), rows_per_shard=lambda k: 5 * k // 8 + 64)
+    ok = True
+    for k in (50, 400):
+        d, s, c = searcher.search(queries, k)
+        want = oracle.score_topk_csr(toff_full, docs_full, vals_full, x["n_docs"], queries, k)
+        ok = ok and np.array_equal(c, want[2])
+        for i in range(len(queries)):
+            ok = ok and np.array_equal(d[i, :c[i]], want[0][i, :c[i]]) and np.array_equal(s[i, :c[i]], want[1][i, :c[i]])
+    # k = 50: rows are already full-size (no round 2); k = 400: 314-key rows, the two clustered queries are re-run
+    ok = ok and shard_k(400, 2) == 400 and shard_k(1000, 8) == 221 and shard_k(10, 8) == 10 and searcher.round2_queries == 2
+    ok = ok and calls == [(25, 50), (25, 314), (2, 400)]
     out_dict[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
