@@ -189,6 +189,21 @@ def run_b200(args):
     ev1.record()
     torch.cuda.synchronize()
     invert_ms = ev0.elapsed_time(ev1)
+    build_parity = None
+    if args.verify_build and world == 1:              # configs[4]: the whole K2 output vs the CPU oracle, bit for bit
+        from oracle import oracle
+        t_cpu = time.time()
+        o_toff, o_docs, o_vals = oracle.invert(terms.cpu().numpy().view(np.uint32), imps.cpu().numpy(),
+                                               offs.cpu().numpy().astype(np.uint64), V)
+        t_cpu = time.time() - t_cpu
+        same = (np.array_equal(o_toff, toff.cpu().numpy().astype(np.uint64))
+                and np.array_equal(o_docs, docids.cpu().numpy().view(np.uint32))
+                and np.array_equal(o_vals, vals.cpu().numpy()))
+        build_parity = {"postings": int(P), "bit_exact": bool(same), "oracle_invert_s": round(t_cpu, 2),
+                        "against": "oracle/di_oracle.c dio_invert (create.py:31-46)"}
+        del o_toff, o_docs, o_vals
+        if not same:
+            raise SystemExit("PARITY FAILURE: GPU inversion differs from the oracle at full size")
     del terms, imps, offs
     docids += doc_lo                                  # docids stay global across shards
     torch.cuda.synchronize()
@@ -212,28 +227,37 @@ def run_b200(args):
     searcher = ShardedSearcher.for_device_index(index, dev)      # local top-k -> NCCL all-gather -> K5 merge
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    B = args.batch or Q                       # queries per search call (configs[3] uses batches of 4096)
+    batches = [(q0, min(q0 + B, Q)) for q0 in range(0, Q, B)]
+
     def step_device():
-        return searcher.search_tensors(d_flat, d_offs, Q, max_len, k)
+        out = None
+        for q0, q1 in batches:
+            out = searcher.search_tensors(d_flat, d_offs[q0:q1 + 1], q1 - q0, max_len, k)
+        return out
 
     h_docs = torch.empty((Q, k), dtype=torch.int32).pin_memory()
     h_scores = torch.empty((Q, k), dtype=torch.int32).pin_memory()
     h_counts = torch.empty(Q, dtype=torch.int32).pin_memory()
+    if world > 1:
+        dd = torch.empty((B, k), dtype=torch.int32, device=dev)
+        ds = torch.empty((B, k), dtype=torch.int32, device=dev)
 
     def step_e2e():
-        if world == 1:
-            index.search_flat(h_flat, h_offs, k, h_docs, h_scores, h_counts)   # H2D + kernels + D2H inside
-        else:
-            d_flat.copy_(h_flat, non_blocking=True)
-            d_offs.copy_(h_offs, non_blocking=True)
-            m_keys, m_counts = step_device()
-            if rank == 0:
-                dd = torch.empty((Q, k), dtype=torch.int32, device=dev)
-                ds = torch.empty((Q, k), dtype=torch.int32, device=dev)
-                engine.unpack_keys_device(m_keys, Q * k, dd, ds, stream)
-                h_docs.copy_(dd, non_blocking=True)
-                h_scores.copy_(ds, non_blocking=True)
-                h_counts.copy_(m_counts, non_blocking=True)
-            torch.cuda.synchronize()
+        for q0, q1 in batches:
+            if world == 1:      # H2D + kernels + D2H inside the C-ABI call
+                index.search_flat(h_flat, h_offs[q0:q1 + 1], k, h_docs[q0:q1], h_scores[q0:q1], h_counts[q0:q1])
+            else:
+                d_flat.copy_(h_flat, non_blocking=True)
+                d_offs.copy_(h_offs, non_blocking=True)
+                m_keys, m_counts = searcher.search_tensors(d_flat, d_offs[q0:q1 + 1], q1 - q0, max_len, k)
+                if rank == 0:
+                    n = q1 - q0
+                    engine.unpack_keys_device(m_keys, n * k, dd, ds, stream)
+                    h_docs[q0:q1].copy_(dd[:n], non_blocking=True)
+                    h_scores[q0:q1].copy_(ds[:n], non_blocking=True)
+                    h_counts[q0:q1].copy_(m_counts, non_blocking=True)
+                torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -299,7 +323,7 @@ def run_b200(args):
             "dtype": "u8 impacts, u16/int32 accumulators", "data": "synthetic",
             "config": {"workload": "configs[1]: MS MARCO passage-shaped synthetic index, Zipf(1) terms, top-%d" % k,
                        "docs": N, "vocab": V, "draws_per_doc": args.draws,
-                       "queries": Q, "top_k": k, "sharding": f"docid-range x{world}", "tile_docs": info["tile_docs"],
+                       "queries": Q, "top_k": k, "batch": B, "sharding": f"docid-range x{world}", "tile_docs": info["tile_docs"],
                        "l2": "index payload (%.1f GB/GPU) exceeds L2 and a 256 MB buffer is written between timed steps"
                              % (info["payload_bytes"] / 1e9)},
             "e2e": {"value": round(Q * args.steps / (total_e2e_ms * 1e-3), 2), "unit": "queries/s",
@@ -323,6 +347,7 @@ def run_b200(args):
             "build": {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "tile_layout_s": round(t_tile, 2),
                       "invert_postings_per_s": round(P / (invert_ms * 1e-3)), "invert_gbs_at_17B": round(17 * P / (invert_ms * 1e-3) / 1e9, 1)},
             "postings_per_query": round(total_postings / Q),
+            "build_parity": build_parity,
             "round2_queries_last_step": searcher.round2_queries,
         }
         if world == 1 and args.cpu_sample > 0:
@@ -427,7 +452,9 @@ def main():
     ap.add_argument("--top-k", type=int, default=1000)
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--dense-ratio", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0, help="queries per search call (0 = all queries at once)")
     ap.add_argument("--cand-slack", type=int, default=0, help="candidate slots kept per query between tiles (0 = default)")
+    ap.add_argument("--verify-build", action="store_true", help="compare the full GPU inversion with the CPU oracle (~1 min)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
     ap.add_argument("--ref-queries-per-step", type=int, default=32)
     args = ap.parse_args()
