@@ -77,7 +77,7 @@ SIGNATURES = {
     "di_index_get_info": (ctypes.c_int, [_vp, ctypes.POINTER(IndexInfo)]),
     "di_index_term_df": (ctypes.c_int, [_vp, _vp, ctypes.c_uint64, _vp]),
     "di_search": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp]),
-    "di_search_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp]),
+    "di_search_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp, _vp]),
     "di_unpack_keys_dev": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "di_merge_topk_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                          _vp, _vp, _vp, _vp]),

@@ -474,8 +474,8 @@ static int ensure(DevBuf &b, size_t bytes)
 }
 
 extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const uint64_t *d_q_offsets, uint32_t n_queries,
-                             uint32_t max_query_len, uint32_t top_k, uint64_t *d_out_keys, uint32_t *d_out_counts,
-                             void *stream)
+                             uint32_t max_query_len, uint32_t top_k, const uint64_t *d_theta_init, uint64_t *d_out_keys,
+                             uint32_t *d_out_counts, void *stream)
 {
     if (!ix) return set_error(DI_ERR_ARG, "index is NULL");
     if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
@@ -491,7 +491,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         return set_error(DI_ERR_ARG, "tile of %u docs needs %zu B of shared memory for %d-bit accumulators (limit %d); "
                          "rebuild the index with smaller tiles for queries of %u terms",
                          ix->tile_docs, acc_bytes, acc32 ? 32 : 16, ix->smem_opt_in, max_query_len);
-    uint32_t c0 = ix->cand_slack ? ix->cand_slack : std::max(2u * top_k, 2048u);
+    uint32_t c0 = ix->cand_slack ? ix->cand_slack : std::max(2u * top_k, 256u);
     c0 = std::max(c0, top_k);
     const uint32_t cap = std::max(c0 + ix->tile_docs, pow2_ceil(top_k));
     const int top_shift = acc32 ? 48 : 40;
@@ -577,7 +577,13 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         a.lanes = lanes;
         a.tiles_per_lane = tiles_per_lane;
         DI_CUDA(cudaMemsetAsync(a.cnt, 0, nv * 4, st));
-        DI_CUDA(cudaMemsetAsync(a.theta, 0, nv * 8, st));
+        if (d_theta_init) {  // caller-proven lower bounds, one copy per lane
+            for (uint32_t l = 0; l < lanes; ++l)
+                DI_CUDA(cudaMemcpyAsync(a.theta + (size_t)l * nq, d_theta_init + q0, (size_t)nq * 8,
+                                        cudaMemcpyDeviceToDevice, st));
+        } else {
+            DI_CUDA(cudaMemsetAsync(a.theta, 0, nv * 8, st));
+        }
         DI_CUDA(cudaEventRecord(ix->ev[b][0], st));
         if (ix->n_tiles) {
             query_order_kernel<<<1, 1024, 0, st>>>(d_q_terms, a.q_offsets, ix->d_df, ix->n_terms, nq,
@@ -672,7 +678,7 @@ extern "C" int di_search(di_index_t *ix, const uint32_t *q_terms, const uint64_t
         return DI_OK;
     }
     DI_TRY(di_search_dev(ix, ix->st_qterms.as<uint32_t>(), ix->st_qoffs.as<uint64_t>(), n_queries, (uint32_t)max_len, top_k,
-                         ix->st_keys.as<uint64_t>(), ix->st_counts.as<uint32_t>(), st));
+                         nullptr, ix->st_keys.as<uint64_t>(), ix->st_counts.as<uint32_t>(), st));
     DI_TRY(di_unpack_keys_dev(ix->st_keys.as<uint64_t>(), n_out, ix->st_docids.as<uint32_t>(), ix->st_scores.as<int32_t>(), st));
     ++ix->other_launches;
     DI_CUDA(cudaMemcpyAsync(out_docids, ix->st_docids.p, n_out * 4, cudaMemcpyDeviceToHost, st));

@@ -343,6 +343,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     // this tile loses: compare against score + 1 and keep the (many) ties out of the slow path.
     if (theta != 0 && key_docid(theta) < doc_base) ++ths;
     if (tid == 0) s_emit = 0;
+    uint64_t theta_pre = 0;
 
     if (theta == 0 && cnt0 + min(T, s_npost) > p.c0) {
         // No threshold yet and this tile alone could flood the list (typically the first tile of a
@@ -368,6 +369,9 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
         __syncthreads();
         const uint32_t bin = block_find_bin_from_top(s_hist, kHistBins, p.k, s_tmp);
         ths = max(1u, bin << shift);
+        // at least k documents of this tile score >= ths, so (ths, any docid) is already a valid lower
+        // bound of the final k-th key: publish it, the next tiles then skip this pre-selection
+        if (bin) theta_pre = (uint64_t)ths << 32;
     }
     __syncthreads();
 
@@ -422,7 +426,9 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
             kth = block_select_kth<true>(cand, n, p.k, p.top_shift, s_hist, s_tmp);
             n = block_compact_ge<true>(cand, n, kth, s_scan);
         }
-        if (tid == 0) p.theta[sq] = kth;
+        if (tid == 0) p.theta[sq] = kth;  // >= theta_pre: k of the emitted keys are at or above that bound
+    } else if (theta_pre > theta) {
+        if (tid == 0) p.theta[sq] = theta_pre;
     }
     if (tid == 0) p.cnt[sq] = n;
     return true;  // the query's state was read after done[q] >= tile was observed

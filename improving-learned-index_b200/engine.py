@@ -170,11 +170,12 @@ class DeviceIndex:
         return self.search_flat(flat, offs, top_k)
 
     def search_device(self, d_q_terms, d_q_offsets, n_queries: int, max_query_len: int, top_k: int,
-                      d_out_keys, d_out_counts, stream: int = 0):
+                      d_out_keys, d_out_counts, stream: int = 0, d_theta_init=None):
         """Device-buffer entry point, asynchronous on `stream`; outputs are packed keys
-        (score << 32 | ~docid) sorted descending — the form the cross-shard merge consumes."""
+        (score << 32 | ~docid) sorted descending — the form the cross-shard merge consumes.
+        d_theta_init: optional per-query keys known to be lower bounds of the final k-th best key."""
         N.check(N.lib().di_search_dev(self._h, N.ptr(d_q_terms), N.ptr(d_q_offsets), n_queries, max_query_len, top_k,
-                                      N.ptr(d_out_keys), N.ptr(d_out_counts), stream))
+                                      N.ptr(d_theta_init), N.ptr(d_out_keys), N.ptr(d_out_counts), stream))
 
     def timings(self) -> dict:
         t = N.Timings()

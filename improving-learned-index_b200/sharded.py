@@ -55,8 +55,10 @@ class ShardedSearcher:
     """search(): local best keys on this rank's shard -> all_gather -> merge (+ proof, + round 2).
     Call on every rank with the same queries; every rank gets the global result.
 
-    local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, out_keys, out_counts) fills this shard's
-    sorted keys [Q, k] (int64 bit patterns) and counts [Q] (int32) — torch tensors on `device`.
+    local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, out_keys, out_counts[, theta_init=]) fills this
+    shard's sorted keys [Q, k] (int64 bit patterns) and counts [Q] (int32) — torch tensors on `device`;
+    theta_init [Q] (int64 keys), when given, are proven lower bounds of the final k-th keys: the shard may
+    leave out anything below them.
     merge(gathered_keys [G,Q,k_in], gathered_counts [G,Q], G, Q, k_in, k, out_keys [Q,k], out_counts [Q],
     incomplete [Q] int32) writes the global top-k and flags the queries whose merge is not proven exact.
     """
@@ -78,8 +80,9 @@ class ShardedSearcher:
     def for_device_index(cls, index: "engine.DeviceIndex", device, group=None) -> "ShardedSearcher":
         import torch
 
-        def local_search(qt, qo, n_q, max_len, k, out_keys, out_counts):
-            index.search_device(qt, qo, n_q, max_len, k, out_keys, out_counts, torch.cuda.current_stream().cuda_stream)
+        def local_search(qt, qo, n_q, max_len, k, out_keys, out_counts, theta_init=None):
+            index.search_device(qt, qo, n_q, max_len, k, out_keys, out_counts, torch.cuda.current_stream().cuda_stream,
+                                d_theta_init=theta_init)
 
         def merge(g_keys, g_counts, n_shards, n_q, k_in, k, out_keys, out_counts, incomplete):
             engine.merge_topk_device(g_keys, g_counts, n_shards, n_q, k, out_keys, out_counts,
@@ -92,12 +95,15 @@ class ShardedSearcher:
             self._buffers[key] = self.torch.zeros(shape, dtype=dtype, device=self.device)
         return self._buffers[key]
 
-    def _round(self, d_q_terms, d_q_offsets, n_queries, max_len, k_in, k, tag):
+    def _round(self, d_q_terms, d_q_offsets, n_queries, max_len, k_in, k, tag, theta_init=None):
         """One gather + merge with rows of k_in keys. Returns (keys [Q,k], counts [Q], incomplete [Q])."""
         torch, dist = self.torch, self.dist
         keys = self._buf(tag + "keys", (n_queries, k_in), torch.int64)
         counts = self._buf(tag + "counts", (n_queries,), torch.int32)
-        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k_in, keys, counts)
+        if theta_init is None:
+            self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k_in, keys, counts)
+        else:
+            self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k_in, keys, counts, theta_init=theta_init)
         g_keys = self._buf(tag + "g_keys", (self.world, n_queries, k_in), torch.int64)
         g_counts = self._buf(tag + "g_counts", (self.world, n_queries), torch.int32)
         # concatenated-along-dim-0 form: accepted by both the NCCL and the gloo backend
@@ -133,7 +139,12 @@ class ShardedSearcher:
                 idx = torch.repeat_interleave(offs[:-1][redo] - new_offs[:-1], lens) + torch.arange(
                     int(new_offs[-1]), device=self.device)
                 sub_terms = d_q_terms[idx] if idx.numel() else d_q_terms[:1]
-                k2, c2, _ = self._round(sub_terms.contiguous(), new_offs, int(redo.numel()), max_len, k, k, "r2_")
+                # round 1 already proves a lower bound of each flagged query's final k-th key: the k-th key of
+                # its (incomplete) merge, all of whose keys exist. Round 2 only has to surface documents above it.
+                full = out_counts[redo] == k
+                theta = torch.where(full, out_keys[redo, k - 1], torch.zeros_like(out_keys[redo, k - 1])).contiguous()
+                k2, c2, _ = self._round(sub_terms.contiguous(), new_offs, int(redo.numel()), max_len, k, k, "r2_",
+                                        theta_init=theta)
                 out_keys[redo] = k2
                 out_counts[redo] = c2
         return out_keys, out_counts

@@ -91,7 +91,7 @@ typedef struct di_index_params {
     uint32_t tile_docs;      /* documents per tile: power of two in [256, 32768]; 0 = default (32768) */
     uint32_t dense_ratio;    /* a (term, tile) segment with n postings is stored as a dense u16 array
                                 when n * dense_ratio >= tile_docs; 0 = default (4); 0xFFFFFFFF = never */
-    uint32_t cand_slack;     /* per-query candidate slots kept between tiles; 0 = default (max(2k, 2048)) */
+    uint32_t cand_slack;     /* per-query candidate slots kept between tiles; 0 = default (max(2k, 256)) */
     uint32_t reserved;
 } di_index_params;
 
@@ -140,9 +140,12 @@ int di_search(di_index_t *index, const uint32_t *q_terms, const uint64_t *q_offs
               uint32_t n_queries, uint32_t top_k,
               uint32_t *out_docids, int32_t *out_scores, uint32_t *out_counts);
 /* device variant: packed keys (score << 32 | ~docid), sorted descending, for the multi-GPU merge.
- * max_query_len = longest query in the batch (chooses 16- or 32-bit accumulators). */
+ * max_query_len = longest query in the batch (chooses 16- or 32-bit accumulators).
+ * d_theta_init (optional, may be NULL): per query a key that the caller KNOWS to be a lower bound of the
+ * query's final k-th best key over the whole collection (e.g. the k-th key of a previous, partial merge);
+ * documents below it are not returned, which makes a second search round cheap. */
 int di_search_dev(di_index_t *index, const uint32_t *d_q_terms, const uint64_t *d_q_offsets,
-                  uint32_t n_queries, uint32_t max_query_len, uint32_t top_k,
+                  uint32_t n_queries, uint32_t max_query_len, uint32_t top_k, const uint64_t *d_theta_init,
                   uint64_t *d_out_keys, uint32_t *d_out_counts, void *stream);
 int di_unpack_keys_dev(const uint64_t *d_keys, uint64_t n, uint32_t *d_docids, int32_t *d_scores, void *stream);
 

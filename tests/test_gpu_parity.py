@@ -269,6 +269,34 @@ def test_shards_and_merge_equal_single_index():
     assert sum(s.info()["n_postings"] for s in shards) == full.info()["n_postings"]
 
 
+def test_initial_thresholds_cut_the_result_exactly():
+    """di_search_dev with caller-proven lower bounds returns exactly the keys at or above them."""
+    torch = pytest.importorskip("torch")
+    x = quantized_csr(9000, 1200, 60, 51)
+    index = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], tile_docs=1024)
+    queries = syn.make_queries(40, vocab_size=1200, seed=8)
+    flat, offs = engine.flatten_queries(queries)
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    d_flat = torch.from_numpy(flat.astype(np.int64)).to(dev).to(torch.int32)
+    d_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    k, max_len = 200, max(len(q) for q in queries)
+    keys = torch.zeros((len(queries), k), dtype=torch.int64, device=dev)
+    counts = torch.zeros(len(queries), dtype=torch.int32, device=dev)
+    index.search_device(d_flat, d_offs, len(queries), max_len, k, keys, counts, st)
+    torch.cuda.synchronize()
+    cut = torch.clamp(counts.to(torch.int64) // 3, min=0)                      # keep about a third of every row
+    theta = torch.where(counts > 0, keys[torch.arange(len(queries), device=dev), cut], torch.zeros_like(cut))
+    keys2 = torch.zeros_like(keys)
+    counts2 = torch.zeros_like(counts)
+    index.search_device(d_flat, d_offs, len(queries), max_len, k, keys2, counts2, st, d_theta_init=theta.contiguous())
+    torch.cuda.synchronize()
+    for i in range(len(queries)):
+        n = int(cut[i]) + 1 if int(counts[i]) else 0
+        assert int(counts2[i]) == n, i
+        assert torch.equal(keys2[i, :n], keys[i, :n]), i
+
+
 def test_short_rows_merge_proves_or_flags():
     """K5 with k_in < k: unflagged queries must equal the single-index result; a query whose top-k sits in
     one shard must be flagged (and is exact again once re-run with full rows)."""

@@ -58,7 +58,7 @@ def _worker(rank, world, port, out_dict):
     queries[6] = [600, queries[6][0]]
     calls = []
 
-    def local_search(qt, qo, n_q, max_len, k, out_keys, out_counts):
+    def local_search(qt, qo, n_q, max_len, k, out_keys, out_counts, theta_init=None):
         offs = qo.numpy().astype(np.int64)
         flat = qt.numpy().view(np.uint32)
         qs = [flat[offs[i]:offs[i + 1]].tolist() for i in range(n_q)]
@@ -67,6 +67,12 @@ def _worker(rank, world, port, out_dict):
         keys = np.zeros((n_q, k), dtype=np.uint64)
         for i in range(n_q):
             keys[i, :c[i]] = pack_keys(s[i, :c[i]], d[i, :c[i]])
+        if theta_init is not None:        # like the CUDA path: nothing below the proven bound is returned
+            th = theta_init.numpy().view(np.uint64)
+            for i in range(n_q):
+                keep = keys[i, :c[i]] >= th[i]
+                c[i] = int(keep.sum())
+                keys[i, c[i]:] = 0
         out_keys.copy_(torch.from_numpy(keys.view(np.int64)))
         out_counts.copy_(torch.from_numpy(c.astype(np.int32)))
 
