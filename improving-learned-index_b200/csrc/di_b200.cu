@@ -307,7 +307,7 @@ static int new_index(uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const d
     *out = nullptr;
     DI_TRY(ensure_device());
     if (doc_hi <= doc_lo) return set_error(DI_ERR_ARG, "empty doc range [%u, %u)", doc_lo, doc_hi);
-    uint32_t tile_docs = params && params->tile_docs ? params->tile_docs : 32768u;
+    uint32_t tile_docs = params && params->tile_docs ? params->tile_docs : 16384u;
     if (tile_docs < 256 || tile_docs > kMaxTileDocs || (tile_docs & (tile_docs - 1)))
         return set_error(DI_ERR_ARG, "tile_docs must be a power of two in [256, %u], got %u", kMaxTileDocs, tile_docs);
     di_index *ix = new (std::nothrow) di_index();

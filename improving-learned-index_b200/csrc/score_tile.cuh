@@ -22,10 +22,10 @@
 namespace di {
 
 #ifndef DI_SCORE_THREADS
-#define DI_SCORE_THREADS 256
+#define DI_SCORE_THREADS 128
 #endif
 #ifndef DI_SCORE_MIN_BLOCKS
-#define DI_SCORE_MIN_BLOCKS 3
+#define DI_SCORE_MIN_BLOCKS 6
 #endif
 constexpr int kScoreThreads = DI_SCORE_THREADS;
 constexpr int kMaxSeg = 32;        // query terms handled per round inside a work item
