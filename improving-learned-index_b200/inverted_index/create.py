@@ -15,14 +15,15 @@ from typing import Union
 
 import numpy as np
 
-from .. import engine
+from .. import collection_io, engine
 from ..indexing.deep_impact_collection import DeepImpactCollection
 from ..utils.defaults import (INVERTED_INDEX_DATA, INVERTED_INDEX_INDEX, INVERTED_INDEX_VOCAB, MAX_IMPACT)
 
 
 class InvertedIndexCreator:
     def __init__(self, deep_impact_collection_path: Union[str, Path], output_path: Union[str, Path]):
-        self.deep_impact_collection = DeepImpactCollection(Path(deep_impact_collection_path))
+        self._collection_path = Path(deep_impact_collection_path)
+        self.deep_impact_collection = DeepImpactCollection(self._collection_path)
         self.output_path = Path(output_path)
         self.output_path.mkdir(parents=True, exist_ok=True)
         self.vocab = dict()
@@ -30,31 +31,28 @@ class InvertedIndexCreator:
 
     def _parsed(self):
         if self._docs is None:
-            self._docs = [item for _, item in self.deep_impact_collection]
+            self._docs = collection_io.parse_file(self._collection_path, collection_io.DICT)
         return self._docs
 
     def _vocab_file(self):
         """create.py:19-29 — term id = rank of the term in sorted() (code-point) order."""
-        terms = set()
-        for item in self._parsed():
-            terms.update(item.keys())
-        self.vocab = {term: i for i, term in enumerate(sorted(terms))}
-        with open(self.output_path / INVERTED_INDEX_VOCAB, 'w', encoding='utf-8') as f:
-            f.writelines(f'{term}\n' for term in self.vocab)
+        parsed = self._parsed()
+        self.vocab = {term: i for i, term in enumerate(parsed.vocab())}
+        (self.output_path / INVERTED_INDEX_VOCAB).write_bytes(parsed.vocab_file_bytes())
 
     def _inverted_index(self):
-        docs = self._parsed()
-        offsets = np.zeros(len(docs) + 1, dtype=np.uint64)
-        np.cumsum([len(d) for d in docs], out=offsets[1:])
-        n_post = int(offsets[-1])
-        term_ids = np.fromiter((self.vocab[t] for d in docs for t in d), dtype=np.uint32, count=n_post)
-        # create.py:35 stores int(val): truncation toward zero of the parsed float
-        values = np.fromiter((int(v) for d in docs for v in d.values()), dtype=np.int64, count=n_post)
-        if n_post and (values.min() < 0 or values.max() > MAX_IMPACT):
+        parsed = self._parsed()
+        scores = parsed.scores
+        if scores.size and not np.isfinite(scores).all():       # int(nan) / int(inf) in create.py:35
+            raise (ValueError('cannot convert float NaN to integer') if np.isnan(scores).any()
+                   else OverflowError('cannot convert float infinity to integer'))
+        values = np.trunc(scores)                               # create.py:35 stores int(val): truncation toward zero
+        if values.size and (values.min() < 0 or values.max() > MAX_IMPACT):
             raise struct.error('ubyte format requires 0 <= number <= 255')     # what pack('B', val) raises
-        if len(docs) >= 2 ** 32:
+        if parsed.n_docs >= 2 ** 32:
             raise struct.error("'I' format requires 0 <= number <= 4294967295")
-        toff, docids, impacts = engine.invert(term_ids, values.astype(np.uint8), offsets, len(self.vocab))
+        toff, docids, impacts = engine.invert(parsed.term_ids, values.astype(np.uint8), parsed.doc_offsets,
+                                              max(parsed.n_terms, 0))
         dat, idx = engine.serialize(toff, docids, impacts)
         dat.tofile(self.output_path / INVERTED_INDEX_DATA)
         idx.tofile(self.output_path / INVERTED_INDEX_INDEX)
@@ -62,6 +60,9 @@ class InvertedIndexCreator:
     def run(self):
         self._vocab_file()
         self._inverted_index()
+        if self._docs is not None:
+            self._docs.close()
+            self._docs = None
 
 
 if __name__ == '__main__':

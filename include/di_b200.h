@@ -34,7 +34,8 @@ extern "C" {
 #define DI_ERR_RANGE 3     /* a value does not fit the index format (impact > 255, docid out of range, ...) */
 #define DI_ERR_NOMEM 4     /* device or host allocation failed */
 #define DI_ERR_NODEVICE 5  /* no CUDA device present */
-#define DI_ERR_FORMAT 6    /* malformed index file image (short read) */
+#define DI_ERR_FORMAT 6    /* malformed index file image (short read) or collection line (a ValueError in the reference) */
+#define DI_ERR_UNSUPPORTED 7 /* valid input outside the fast host parser's grammar: use the Python parser */
 
 #define DI_OOV_TERM 0xFFFFFFFFu /* query term id meaning "not in vocabulary" (inverted_index.py:43-44) */
 
@@ -56,6 +57,27 @@ int di_find_max_f64(const double *scores, int64_t n, double *max_out);
 int di_quantize_f64(const double *scores, int64_t n, double max_val, int32_t *out);
 int di_find_max_f64_dev(const double *d_scores, int64_t n, double *d_max_out, void *stream);
 int di_quantize_f64_dev(const double *d_scores, int64_t n, double max_val, int32_t *d_out, void *stream);
+
+/* ------------------------------------------------------------------ collection text parser (host only, no GPU)
+ * Replaces the Python string loops around K1/K2: DeepImpactCollection (deep_impact_collection.py:11-25),
+ * the vocabulary of create.py:19-29 (term id = rank in sorted() order) and the parse/format halves of
+ * quantize_file (quantize.py:17-24, 39-47). Text is the doc-major format "term: score, term: score",
+ * one document per line. DI_PARSE_DICT = InvertedIndexCreator semantics (blank line = empty document, a
+ * repeated term keeps its last score); DI_PARSE_SEQUENCE = quantize_file semantics (all pairs in order,
+ * blank line = DI_ERR_FORMAT). The arrays returned by di_collection_arrays stay owned by the collection:
+ * doc_offsets[n_docs+1], term_ids[n_postings] (ids = sorted rank), scores[n_postings] (float64), the
+ * sorted vocabulary as one byte blob + vocab_offsets[n_terms+1].
+ */
+#define DI_PARSE_DICT 0
+#define DI_PARSE_SEQUENCE 1
+typedef struct di_collection di_collection_t;
+int di_collection_parse(const char *text, uint64_t n_bytes, int mode, di_collection_t **out);
+void di_collection_free(di_collection_t *collection);
+int di_collection_info(const di_collection_t *collection, uint64_t *n_docs, uint64_t *n_postings, uint32_t *n_terms);
+int di_collection_arrays(const di_collection_t *collection, const uint64_t **doc_offsets, const uint32_t **term_ids,
+                         const double **scores, const char **vocab_blob, const uint64_t **vocab_offsets);
+/* quantize.py:40-47: one line per document, "term: value" for every value > 0 joined by ", " */
+int di_collection_write_quantized(const di_collection_t *collection, const int32_t *values, const char *path);
 
 /* ------------------------------------------------------------------ K2: term -> document inversion
  * Replaces src/deep_impact/inverted_index/create.py:31-51 (InvertedIndexCreator._inverted_index).

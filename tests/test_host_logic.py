@@ -104,3 +104,76 @@ def test_trec_metrics_hand_computed():
     assert _map["MAP@3"] == round(((1 + 2 / 3) / 2 + 0.0) / 2, 5)
     assert recall["Recall@1"] == 0.25 and recall["Recall@3"] == 0.5
     assert prec["P@1"] == 0.5 and prec["P@3"] == round((2 / 3) / 2, 5)
+
+
+# ------------------------------------------------------------------ host-side collection parser (no GPU involved)
+def _same(a, b):
+    return (a.vocab() == b.vocab() and np.array_equal(a.doc_offsets, b.doc_offsets)
+            and np.array_equal(a.term_ids, b.term_ids) and np.array_equal(a.scores, b.scores))
+
+
+def test_fast_parser_equals_reference_shaped_parser_on_golden(golden):
+    from improving_learned_index_b200 import collection_io as C
+    for name in ("kat", "small", "zeros"):
+        g = golden(name)
+        for lines in (g["lines"], g.get("quantized_lines", g["lines"])):
+            text = ''.join(l + '\n' for l in lines)
+            a, b = C.parse_bytes(text.encode(), C.DICT), C.parse_python(text, C.DICT)
+            assert _same(a, b)
+            if "quantized_lines" in g and lines is g["quantized_lines"]:
+                assert a.vocab() == g["vocab"]
+            if '' not in [l.strip() for l in lines]:
+                assert _same(C.parse_bytes(text.encode(), C.SEQUENCE), C.parse_python(text, C.SEQUENCE))
+
+
+def test_fast_parser_fuzz_against_python():
+    from improving_learned_index_b200 import collection_io as C
+    rng = np.random.default_rng(3)
+    terms = ["a", "b c", "đá", "x|y", "t:1", "q,r", "naïve", "end ", "　lead", "tab\tin", "colon:", " sp"]
+    nums = ["1", "0.5", "2.50", "1e3", "-3.25", "+7", ".5", "5.", "1E-2", "0", "inf", "-Infinity", "nan", "12.0", " 3 ", "4\t"]
+    for trial in range(300):
+        lines = []
+        for _ in range(rng.integers(1, 6)):
+            n = rng.integers(0, 5)
+            pairs = [f"{terms[rng.integers(len(terms))]}: {nums[rng.integers(len(nums))]}" for _ in range(n)]
+            pad = [" ", "", "\t", " ", "  "][rng.integers(5)]
+            lines.append(pad + ', '.join(pairs) + pad)
+        eol = ["\n", "\r\n", "\r"][rng.integers(3)]
+        text = eol.join(lines) + (eol if rng.integers(2) else "")
+        for mode in (C.DICT, C.SEQUENCE):
+            try:
+                want = C.parse_python(text, mode)
+            except ValueError:
+                with pytest.raises(ValueError):
+                    C.parse_bytes(text.encode(), mode)
+                continue
+            got = C.parse_bytes(text.encode(), mode)
+            assert got.vocab() == want.vocab() and np.array_equal(got.doc_offsets, want.doc_offsets), (trial, text)
+            assert np.array_equal(got.term_ids, want.term_ids), (trial, text)
+            assert np.array_equal(got.scores, want.scores, equal_nan=True), (trial, text)
+
+
+def test_fast_parser_errors_and_fallback(tmp_path):
+    from improving_learned_index_b200 import collection_io as C
+    for bad in (b"a 1.5\n", b"a: 1: 2\n", b"a: x\n", b"a: 1,b: 2\n", b"a: \n"):
+        with pytest.raises(ValueError):
+            C.parse_bytes(bad, C.DICT)
+        with pytest.raises(ValueError):
+            C.parse_python(bad.decode(), C.DICT)
+    with pytest.raises(ValueError):
+        C.parse_bytes(b"a: 1\n\nb: 2\n", C.SEQUENCE)           # quantize.py:43 on a blank line
+    assert C.parse_bytes(b"a: 1\n\nb: 2\n", C.DICT).doc_offsets.tolist() == [0, 1, 1, 2]
+    with pytest.raises(_native.NativeError) as e:               # CPython accepts 1_0; the fast parser defers
+        C.parse_bytes(b"a: 1_0\n", C.DICT)
+    assert e.value.code == _native.ERR_UNSUPPORTED
+    p = tmp_path / "c"
+    p.write_bytes("a: 1_0, b: ٣\n".encode())                   # underscore literal, Arabic-Indic digit
+    got = C.parse_file(p, C.DICT)
+    assert got.scores.tolist() == [10.0, 3.0] and got.vocab() == ["a", "b"]
+    (tmp_path / "bad").write_bytes(b"a: 1\n\xff\xfe: 2\n")
+    with pytest.raises(UnicodeDecodeError):
+        C.parse_file(tmp_path / "bad", C.DICT)
+    # writer: quantize.py:40-47
+    c = C.parse_bytes("x: 1, đ: 2\ny: 3\nz: 4\n".encode(), C.SEQUENCE)
+    c.write_quantized(np.array([5, 0, -1, 9], dtype=np.int32), tmp_path / "out")
+    assert (tmp_path / "out").read_text(encoding="utf-8") == "x: 5\n\nz: 9\n"
