@@ -182,13 +182,16 @@ def run_b200(args):
     toff = torch.empty(V + 1, dtype=torch.int64, device=dev)
     docids = torch.empty(P, dtype=torch.int32, device=dev)
     vals = torch.empty(P, dtype=torch.uint8, device=dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    _native.check(L.di_invert_dev(terms.data_ptr(), imps.data_ptr(), offs.data_ptr(), doc_hi - doc_lo, V, P,
-                                  toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), stream))
-    ev1.record()
-    torch.cuda.synchronize()
-    invert_ms = ev0.elapsed_time(ev1)
+    invert_runs = []
+    for _ in range(2):      # the first call also pays for mapping ~13 GB of fresh sort scratch (cudaMalloc)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _native.check(L.di_invert_dev(terms.data_ptr(), imps.data_ptr(), offs.data_ptr(), doc_hi - doc_lo, V, P,
+                                      toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), stream))
+        ev1.record()
+        torch.cuda.synchronize()
+        invert_runs.append(ev0.elapsed_time(ev1))
+    invert_ms = invert_runs[-1]
     build_parity = None
     if args.verify_build and world == 1:              # configs[4]: the whole K2 output vs the CPU oracle, bit for bit
         from oracle import oracle
@@ -344,7 +347,7 @@ def run_b200(args):
                       "dense_segments": info["n_dense_segments"], "sparse_segments": info["n_sparse_segments"],
                       "dense_posting_frac": round(info["n_dense_postings"] / max(info["n_postings"], 1), 3),
                       "tiles": info["n_tiles"]},
-            "build": {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "tile_layout_s": round(t_tile, 2),
+            "build": {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "invert_ms_first_call": round(invert_runs[0], 1), "tile_layout_s": round(t_tile, 2),
                       "invert_postings_per_s": round(P / (invert_ms * 1e-3)), "invert_gbs_at_17B": round(17 * P / (invert_ms * 1e-3) / 1e9, 1)},
             "postings_per_query": round(total_postings / Q),
             "build_parity": build_parity,

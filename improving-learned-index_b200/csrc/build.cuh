@@ -56,12 +56,19 @@ __global__ void invert_keys_kernel(const uint32_t *__restrict__ term_ids, const 
                                    const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, uint64_t n_post,
                                    uint32_t n_terms, uint64_t *__restrict__ keys, int *__restrict__ err)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t doc = upper_bound_u64(doc_offsets, n_docs + 1, i) - 1;  // doc_offsets[doc] <= i < [doc+1]
-        const uint32_t t = term_ids[i];
-        if (t >= n_terms) *err = 1;
-        keys[i] = ((uint64_t)t << kInvTermShift) | ((uint64_t)(255u - impacts[i]) << 32) | (uint64_t)(uint32_t)doc;
+    // one warp per document (lists are ~100 postings): the docid comes for free and the accesses stay
+    // coalesced, instead of a 23-step binary search over doc_offsets per posting
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t doc = warp; doc < n_docs; doc += n_warps) {
+        const uint64_t lo = doc_offsets[doc], hi = doc_offsets[doc + 1];
+        for (uint64_t i = lo + lane_id(); i < hi; i += 32) {
+            const uint32_t t = term_ids[i];
+            if (t >= n_terms) *err = 1;
+            keys[i] = ((uint64_t)t << kInvTermShift) | ((uint64_t)(255u - impacts[i]) << 32) | (uint64_t)(uint32_t)doc;
+        }
     }
+    (void)n_post;
 }
 
 __global__ void invert_extract_kernel(const uint64_t *__restrict__ keys, uint64_t n_post, uint32_t n_terms,

@@ -175,10 +175,20 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ k
         __syncwarp();
     }
     __syncthreads();
-    // digit d: exclusive scan over the warps, seeded with this block's global start for d
+    // Block-local sort first: keys are placed in shared memory grouped by digit (stable), so that the
+    // global scatter below writes each digit's run with consecutive threads -> consecutive addresses.
+    // A direct scatter from registers would touch up to 32 different 32-byte sectors per warp store.
+    __shared__ uint64_t s_keys[kRsTile];
+    __shared__ uint32_t s_global[256];       // global start of digit d for this block, minus s_digit_start[d]
+    __shared__ uint32_t s_warp[33];
     {
-        const unsigned d = threadIdx.x;
-        uint32_t run = block_offsets[(uint64_t)d * nblocks + blockIdx.x];
+        const unsigned d = threadIdx.x;      // blockDim.x == 256 == number of digits
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kRsWarps; ++w) total += warp_cnt[w][d];
+        uint32_t block_total;
+        uint32_t run = block_exclusive_scan(total, s_warp, block_total);
+        s_global[d] = block_offsets[(uint64_t)d * nblocks + blockIdx.x] - run;
 #pragma unroll
         for (int w = 0; w < kRsWarps; ++w) {
             uint32_t c = warp_cnt[w][d];
@@ -192,8 +202,15 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, uint64_t *__restrict__ k
         const uint64_t idx = wbase + (uint64_t)s * 32 + lane;
         if (idx < n) {
             const unsigned digit = (unsigned)(key[s] >> shift) & dmask;
-            keys_out[warp_cnt[warp][digit] + rank[s]] = key[s];
+            s_keys[warp_cnt[warp][digit] + rank[s]] = key[s];
         }
+    }
+    __syncthreads();
+    const uint64_t block_base = (uint64_t)blockIdx.x * kRsTile;
+    const uint32_t n_here = (uint32_t)(n - block_base < (uint64_t)kRsTile ? n - block_base : (uint64_t)kRsTile);
+    for (uint32_t i = threadIdx.x; i < n_here; i += kRsThreads) {
+        const uint64_t k = s_keys[i];
+        keys_out[s_global[(unsigned)(k >> shift) & dmask] + i] = k;  // = global start + (i - local start)
     }
 }
 
