@@ -29,7 +29,7 @@ struct di_index {
     DevBuf ws_cand, ws_cnt, ws_theta, ws_order, ws_done, ws_lane_keys, ws_lane_counts;
     DevBuf st_qterms, st_qoffs, st_keys, st_counts, st_docids, st_scores;
     int smem_opt_in = 0;
-    bool attr_set16 = false, attr_set32 = false, attr_setfin = false;
+    bool attr_set16 = false, attr_set32 = false;
 
     // timing of the last search
     static constexpr int kMaxBatches = 64;

@@ -136,15 +136,14 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, unsigne
 }
 
 // totals[d] = number of keys with digit d (used on the host to skip passes whose digit is uniform)
-__global__ void rs_digit_totals_kernel(const uint32_t *block_hist_scanned, const uint32_t *block_hist_last,
-                                       uint32_t nblocks, uint64_t n, uint32_t *totals)
+__global__ void rs_digit_totals_kernel(const uint32_t *block_hist_scanned, uint32_t nblocks, uint64_t n,
+                                       uint32_t *totals)
 {
     // exclusive-scanned digit-major table: start of digit d = scanned[d*nblocks]; end = start of d+1 (or n)
     unsigned d = threadIdx.x;
     uint64_t start = block_hist_scanned[(uint64_t)d * nblocks];
     uint64_t end = d == 255 ? n : block_hist_scanned[(uint64_t)(d + 1) * nblocks];
     totals[d] = (uint32_t)(end - start);
-    (void)block_hist_last;
 }
 
 __global__ void __launch_bounds__(kRsThreads)
@@ -249,7 +248,7 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, int bit_lo, int 
         rs_hist_kernel<<<nb, kRsThreads, 0, st>>>(src, n, shift, dmask, hist, nb);
         DI_KERNEL_CHECK();
         DI_TRY(exclusive_scan_u32(hist, hist, (uint64_t)256 * nb, ws.scan.as<uint32_t>(), st));
-        rs_digit_totals_kernel<<<1, 256, 0, st>>>(hist, nullptr, nb, n, ws.totals.as<uint32_t>());
+        rs_digit_totals_kernel<<<1, 256, 0, st>>>(hist, nb, n, ws.totals.as<uint32_t>());
         DI_KERNEL_CHECK();
         uint32_t totals[256];
         DI_CUDA(cudaMemcpyAsync(totals, ws.totals.p, sizeof totals, cudaMemcpyDeviceToHost, st));
