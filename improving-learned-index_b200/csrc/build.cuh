@@ -184,7 +184,113 @@ struct TileStats {
     unsigned long long n_dense_segments, n_sparse_segments, n_dense_postings;
     unsigned int max_docid_plus1;
     unsigned int bad_docid;
+    unsigned int n_dup_segments;  // segments listing one document twice (hand-made CSR): no threshold seeding then
 };
+
+// ---------------------------------------------------------------------------- threshold seeds
+// A query's k-th best score is at least the k-th highest impact of any single one of its terms: k
+// different documents hold that term with at least that impact, and the other terms only add.
+// So a per-term table cum[v] = #visible postings with impact >= v gives every (query, k) a proven lower
+// bound on its k-th best score before a single posting is scored: the first tiles of a search (and
+// of every shard and lane of it) then start with a threshold instead of flooding their candidate
+// lists. Exhaustive scoring (inverted_index.py:57-62) is unchanged: documents below a proven bound
+// can never be in the top k. Terms with fewer than kSeedMinDf postings get no table (bound 0): they
+// cannot flood anything.
+constexpr uint32_t kSeedMinDf = 4096;
+constexpr uint32_t kSeedChunk = 16384;   // postings per CTA of impact_hist_kernel
+constexpr uint32_t kNoSeedSlot = 0xFFFFFFFFu;
+
+__global__ void seed_slots_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
+                                  uint32_t *__restrict__ slot_of_term, uint32_t *__restrict__ counter)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_terms; t += gridDim.x * blockDim.x)
+        slot_of_term[t] = term_offsets[t + 1] - term_offsets[t] >= kSeedMinDf ? atomicAdd(counter, 1u) : kNoSeedSlot;
+}
+
+// hist[slot][v] += #visible postings of the slot's term with impact v, for the chunk of the term-major
+// posting arrays this CTA owns. Visible = what tile_keys_kernel keeps: before the term's first zero
+// impact and inside the shard's docid range.
+__global__ void __launch_bounds__(256) impact_hist_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
+                                                          const uint32_t *__restrict__ docids,
+                                                          const uint8_t *__restrict__ impacts, uint64_t n_post,
+                                                          const unsigned long long *__restrict__ first_zero, uint32_t doc_lo,
+                                                          uint32_t doc_hi, const uint32_t *__restrict__ slot_of_term,
+                                                          uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t s_h[256];
+    const uint64_t i0 = (uint64_t)blockIdx.x * kSeedChunk, i1 = min(i0 + (uint64_t)kSeedChunk, n_post);
+    if (i0 >= i1) return;
+    const uint64_t t_first = upper_bound_u64(term_offsets, (uint64_t)n_terms + 1, i0) - 1;
+    const uint64_t t_last = upper_bound_u64(term_offsets, (uint64_t)n_terms + 1, i1 - 1) - 1;
+    for (uint64_t t = t_first; t <= t_last; ++t) {  // uniform across the CTA
+        const uint32_t slot = slot_of_term[t];
+        if (slot == kNoSeedSlot) continue;
+        const uint64_t lo = max(term_offsets[t], i0), hi = min(min(term_offsets[t + 1], i1), (uint64_t)first_zero[t]);
+        s_h[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += 256) {
+            const uint32_t d = docids[i];
+            if (d >= doc_lo && d < doc_hi) atomicAdd(&s_h[impacts[i]], 1u);
+        }
+        __syncthreads();
+        if (s_h[threadIdx.x]) atomicAdd(&hist[(size_t)slot * 256 + threadIdx.x], s_h[threadIdx.x]);
+        __syncthreads();
+    }
+}
+
+// in place: hist[slot][v] -> #postings with impact >= v
+__global__ void seed_cum_kernel(uint32_t *__restrict__ hist, uint32_t n_slots)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (warp >= n_slots) return;
+    uint32_t *h = hist + (size_t)warp * 256;
+    uint32_t c[8], sum = 0;  // lane L owns bins 255-8L .. 248-8L, descending
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sum += h[255 - 8 * lane - j];
+        c[j] = sum;
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += up;
+    }
+    const uint32_t before = incl - sum;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[255 - 8 * lane - j] = before + c[j];
+}
+
+// theta[lane][q] = max(theta[lane][q], bound(q) << 32) with bound(q) = max over the query's terms of the largest
+// v with cum[term][v] >= k (0 when no term has k postings). One thread per query.
+__global__ void seed_theta_kernel(const uint32_t *__restrict__ q_terms, const uint64_t *__restrict__ q_offsets,
+                                  uint32_t n_queries, uint32_t lanes, const uint32_t *__restrict__ slot_of_term,
+                                  const uint32_t *__restrict__ cum, uint32_t n_terms, uint32_t k, uint64_t *__restrict__ theta)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    uint32_t best = 0;
+    for (uint64_t j = q_offsets[q]; j < q_offsets[q + 1]; ++j) {
+        const uint32_t t = q_terms[j];
+        if (t >= n_terms) continue;
+        const uint32_t slot = slot_of_term[t];
+        if (slot == kNoSeedSlot) continue;
+        const uint32_t *c = cum + (size_t)slot * 256;
+        if (c[best + 1 > 255 ? 255 : best + 1] < k) continue;  // cannot improve on the current bound
+        uint32_t lo = best, hi = 255;                          // invariant: cum[lo] >= k (or lo == best), cum[hi + 1] < k
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (c[mid] >= k) lo = mid; else hi = mid - 1;
+        }
+        best = lo;
+    }
+    if (best == 0) return;
+    const uint64_t bound = (uint64_t)best << 32;  // (score, worst possible docid): below every key of that score
+    for (uint32_t l = 0; l < lanes; ++l) {
+        uint64_t *p = theta + (size_t)l * n_queries + q;
+        if (*p < bound) *p = bound;
+    }
+}
 
 __global__ void tile_keys_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
                                  const uint32_t *__restrict__ docids, const uint8_t *__restrict__ impacts,
@@ -262,6 +368,7 @@ __global__ void seg_size_kernel(const uint32_t *__restrict__ seg_begin, const ui
         const uint32_t n = seg_end[s] - seg_begin[s];
         uint32_t sz = 0, nf = 0;
         if (n) {
+            if (size16[s]) stats->n_dup_segments = 1;  // benign race: everybody writes 1
             const bool dense = dense_ratio != 0xFFFFFFFFu && (uint64_t)n * dense_ratio >= tile_docs && size16[s] == 0;
             if (dense) {
                 sz = tile_docs / 8u;  // one u16 per document: the accumulator layout itself

@@ -1,6 +1,7 @@
 // di_b200.cu — the C ABI declared in include/di_b200.h. Host-side orchestration only; the
 // kernels live in build.cuh / search.cuh / scan_sort.cuh. Compiled for sm_100a.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -576,6 +577,16 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         a.n_tiles = ix->n_tiles;
         a.lanes = lanes;
         a.tiles_per_lane = tiles_per_lane;
+#ifdef DI_PROFILE_PHASES
+        static DevBuf prof_buf;  // diagnostic build: per-tile phase cycles, dumped to $DI_B200_PROF after the launch
+        const char *prof_path = getenv("DI_B200_PROF");
+        a.prof = nullptr;
+        if (prof_path) {
+            DI_TRY(ensure(prof_buf, (size_t)ix->n_tiles * 64 + 64));
+            DI_CUDA(cudaMemsetAsync(prof_buf.p, 0, (size_t)ix->n_tiles * 64, st));
+            a.prof = prof_buf.as<unsigned long long>();
+        }
+#endif
         DI_CUDA(cudaMemsetAsync(a.cnt, 0, nv * 4, st));
         if (d_theta_init) {  // caller-proven lower bounds, one copy per lane
             for (uint32_t l = 0; l < lanes; ++l)
@@ -614,6 +625,22 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         }
         DI_KERNEL_CHECK();
         DI_CUDA(cudaEventRecord(ix->ev[b][1], st));
+#ifdef DI_PROFILE_PHASES
+        if (a.prof) {  // overwrite: the file holds the last launch
+            std::vector<unsigned long long> h((size_t)ix->n_tiles * 8);
+            DI_CUDA(cudaMemcpyAsync(h.data(), a.prof, h.size() * 8, cudaMemcpyDeviceToHost, st));
+            DI_CUDA(cudaStreamSynchronize(st));
+            if (FILE *f = fopen(prof_path, "w")) {
+                fprintf(f, "tile,lookup,dense,sparse,wait_presel,scan_emit,cut,unused,items\n");
+                for (uint32_t t = 0; t < ix->n_tiles; ++t) {
+                    fprintf(f, "%u", t);
+                    for (int c = 0; c < 8; ++c) fprintf(f, ",%llu", h[(size_t)t * 8 + c]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
+#endif
         uint64_t *out_keys = d_out_keys + (uint64_t)q0 * top_k;
         uint32_t *out_counts = d_out_counts + q0;
         if (lanes == 1) {

@@ -34,6 +34,9 @@ constexpr int kMaxSeg = 32;        // query terms handled per round inside a wor
 #endif
 constexpr int kSparseUnroll = DI_SPARSE_UNROLL;  // independent 128-bit posting loads in flight per thread
 constexpr int kHistBins = 1024;    // score histogram of the tile-local pre-selection
+#ifndef DI_DEFER_EMIT
+#define DI_DEFER_EMIT 1            // phase 3 remembers hit groups and expands them with all lanes busy
+#endif
 
 constexpr int kRecInlineTerms = 12;
 struct __align__(64) QueryRec {   // one cache-line-friendly record per query of the batch
@@ -60,7 +63,27 @@ struct SearchArgs {
     // `lanes` contiguous sub-ranges that run independently (own candidate list and threshold per
     // (lane, query), all per-query arrays are [lanes][n_queries]) and are merged like shards afterwards.
     uint32_t n_queries, n_tiles, lanes, tiles_per_lane;
+#ifdef DI_PROFILE_PHASES
+    unsigned long long *prof;   // [n_tiles][8] cycles per phase, summed over the tile's work items (diagnostic build)
+#endif
 };
+
+// Diagnostic build only (-DDI_PROFILE_PHASES, tools/phase_profile.sh): thread 0 adds the cycles since the
+// previous mark to prof[tile][phase]. Compiles to nothing in the product build.
+#ifdef DI_PROFILE_PHASES
+#define DI_PROF_DECL long long prof_t = clock64()
+#define DI_PROF_MARK(phase)                                                              \
+    do {                                                                                 \
+        if (threadIdx.x == 0 && p.prof) {                                                \
+            const long long now = clock64();                                             \
+            atomicAdd(p.prof + (size_t)tile * 8 + (phase), (unsigned long long)(now - prof_t)); \
+            prof_t = now;                                                                \
+        }                                                                                \
+    } while (0)
+#else
+#define DI_PROF_DECL
+#define DI_PROF_MARK(phase)
+#endif
 
 // Launch order of a batch: queries bucketed by log2 of their total posting count (sum of the document
 // frequencies of their terms), heaviest bucket first. One block; the order inside a bucket is arbitrary
@@ -191,6 +214,19 @@ __device__ __forceinline__ void emit_candidate(uint32_t score, uint32_t docid, u
     if (key >= theta) cand[cnt0 + atomicAdd(s_emit, 1u)] = key;
 }
 
+// the 8 packed u16 accumulators of group g: append those above tm
+__device__ __forceinline__ void emit_group16(const uint4 x, uint32_t g, uint32_t tm, uint32_t doc_base, uint64_t theta,
+                                             uint64_t *cand, uint32_t cnt0, uint32_t *s_emit)
+{
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = w[i] & 0xFFFFu, hi = w[i] >> 16;
+        if (lo > tm) emit_candidate(lo, doc_base + 8 * g + 2 * i, theta, cand, cnt0, s_emit);
+        if (hi > tm) emit_candidate(hi, doc_base + 8 * g + 2 * i + 1, theta, cand, cnt0, s_emit);
+    }
+}
+
 // One (query, tile) work item; `slot` indexes the batch's launch-ordered query records.
 template <bool ACC32>
 __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, uint32_t slot, uint32_t lane, uint32_t step)
@@ -202,7 +238,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     __shared__ uint32_t s_sunits[kMaxSeg];     // sparse segments: total 16 B units
     __shared__ uint32_t s_seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
     __shared__ uint32_t s_spref[kMaxSeg + 1];  // exclusive prefix of s_sunits
-    __shared__ uint32_t s_nd, s_ns, s_emit, s_npost, s_ready;
+    __shared__ uint32_t s_nd, s_ns, s_emit, s_npost, s_ready, s_nhits;
     __shared__ uint32_t s_hist[kHistBins];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tmp[2];
@@ -223,6 +259,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     const SegDesc *__restrict__ desc = p.desc + (uint64_t)tile * p.n_terms;
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
 
+    DI_PROF_DECL;
     if (tid == 0) s_npost = 0;
     uint64_t theta = 0;
     uint32_t cnt0 = 0;
@@ -256,6 +293,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
             have_state = true;
         }
         touched = touched || (nd + ns) != 0;
+        DI_PROF_MARK(0);  // segment lookup
         if (tid == 0) {
             uint32_t run = 0;
             for (uint32_t j = 0; j < ns; ++j) { s_spref[j] = run; run += s_sunits[j]; }
@@ -274,11 +312,14 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
             else if (nd) dense_pass32<false>(s_acc4, payload4, s_doff, (int)nd, T >> 3);
         }
         __syncthreads();
+        DI_PROF_MARK(1);  // dense
 
         // ---- phase 2: sparse segments. word = impact << 16 | byte offset of the accumulator word;
         //      units [0, even) of a segment hold even documents, the rest odd ones.
         const uint32_t total = s_spref[ns];
-        uint32_t seg = 0;
+        // the current segment's bounds live in registers and are re-read only when a unit crosses into the
+        // next segment (segments are hundreds of units long for the terms queries actually use)
+        uint32_t seg = 0, seg_lo = 0, seg_hi = s_spref[1], seg_even = s_seven[0], seg_off = s_soff[0];
         for (uint32_t u0 = tid; u0 < total; u0 += kSparseUnroll * kScoreThreads) {
             uint4 v[kSparseUnroll];
             bool odd[kSparseUnroll];
@@ -287,10 +328,15 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
                 const uint32_t u = u0 + j * kScoreThreads;
                 odd[j] = false;
                 if (u < total) {
-                    while (u >= s_spref[seg + 1]) ++seg;
-                    const uint32_t lu = u - s_spref[seg];
-                    odd[j] = lu >= s_seven[seg];
-                    v[j] = ldg_stream_v4(payload4 + s_soff[seg] + lu);
+                    if (u >= seg_hi) {
+                        do { ++seg; seg_hi = s_spref[seg + 1]; } while (u >= seg_hi);
+                        seg_lo = s_spref[seg];
+                        seg_even = s_seven[seg];
+                        seg_off = s_soff[seg];
+                    }
+                    const uint32_t lu = u - seg_lo;
+                    odd[j] = lu >= seg_even;
+                    v[j] = ldg_stream_v4(payload4 + seg_off + lu);
                 }
             }
 #pragma unroll
@@ -316,6 +362,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
             }
         }
         __syncthreads();
+        DI_PROF_MARK(2);  // sparse
         first = false;
     }
     if (!touched) return false;
@@ -342,7 +389,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     // visited in docid order, so the threshold's document lies in an earlier tile and every such tie in
     // this tile loses: compare against score + 1 and keep the (many) ties out of the slow path.
     if (theta != 0 && key_docid(theta) < doc_base) ++ths;
-    if (tid == 0) s_emit = 0;
+    if (tid == 0) { s_emit = 0; s_nhits = 0; }
     uint64_t theta_pre = 0;
 
     if (theta == 0 && cnt0 + min(T, s_npost) > p.c0) {
@@ -374,6 +421,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
         if (bin) theta_pre = (uint64_t)ths << 32;
     }
     __syncthreads();
+    DI_PROF_MARK(3);  // state wait + tile-local pre-selection
 
     if (!ACC32) {
         const uint32_t tm = ths - 1u, tm2 = tm | (tm << 16);  // half > tm  <=>  half >= ths
@@ -389,18 +437,29 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
                 const uint32_t m = __vmaxu2(__vmaxu2(x[h].x, x[h].y), __vmaxu2(x[h].z, x[h].w));
                 if (__vmaxu2(m, tm2) != tm2) {  // rare: some document of the 8 is at or above the threshold
                     const uint32_t g = g0 + h * kScoreThreads;
-                    const uint32_t w[4] = {x[h].x, x[h].y, x[h].z, x[h].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (__vmaxu2(w[i], tm2) != tm2) {
-                            const uint32_t lo = w[i] & 0xFFFFu, hi = w[i] >> 16;
-                            if (lo > tm) emit_candidate(lo, doc_base + 8 * g + 2 * i, theta, cand, cnt0, &s_emit);
-                            if (hi > tm) emit_candidate(hi, doc_base + 8 * g + 2 * i + 1, theta, cand, cnt0, &s_emit);
-                        }
+#if DI_DEFER_EMIT
+                    // Only REMEMBER the group here. Emitting inside this divergent branch would run the whole
+                    // key/compare/append sequence with one or two lanes active; the groups are expanded below
+                    // with every lane busy. s_hist is free between the pre-selection and the radix select.
+                    const uint32_t hit = atomicAdd(&s_nhits, 1u);
+                    if (hit < (uint32_t)kHistBins) {
+                        s_hist[hit] = g;
+                        continue;
                     }
+                    // more hit groups than slots (first tiles of a frequent-term query): emit in place
+#endif
+                    emit_group16(x[h], g, tm, doc_base, theta, cand, cnt0, &s_emit);
                 }
             }
         }
+#if DI_DEFER_EMIT
+        __syncthreads();
+        const uint32_t n_hits = min(s_nhits, (uint32_t)kHistBins);
+        for (uint32_t j = tid; j < n_hits; j += kScoreThreads) {  // one remembered group per lane
+            const uint32_t g = s_hist[j];
+            emit_group16(s_acc4[g], g, tm, doc_base, theta, cand, cnt0, &s_emit);
+        }
+#endif
     } else {
         for (uint32_t g = tid; g < (T >> 2); g += kScoreThreads) {
             const uint4 x = s_acc4[g];
@@ -413,6 +472,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
         }
     }
     __syncthreads();
+    DI_PROF_MARK(4);  // accumulator scan + emission
     uint32_t n = cnt0 + s_emit;  // <= c0 + tile_docs <= cap
     if (n > p.c0) {
         // too many live candidates: keep exactly the k best and raise the threshold to the k-th
@@ -431,6 +491,10 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
         if (tid == 0) p.theta[sq] = theta_pre;
     }
     if (tid == 0) p.cnt[sq] = n;
+    DI_PROF_MARK(5);  // cut to k
+#ifdef DI_PROFILE_PHASES
+    if (tid == 0 && p.prof) atomicAdd(p.prof + (size_t)tile * 8 + 7, 1ull);  // items that reached phase 3
+#endif
     return true;  // the query's state was read after done[q] >= tile was observed
 }
 
