@@ -149,6 +149,7 @@ inline int invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, cons
 // addend a single instruction (DESIGN.md "sparse segments").
 constexpr int kTkTermShift = 24, kTkTileShift = 48, kTkLocalShift = 8;
 constexpr uint32_t kDenseFlag = 0x80000000u;
+constexpr int kDenseUnitShift = 4;  // a dense segment holds one byte per document: 16 documents per 16-byte unit
 constexpr uint32_t kMaxTileDocs = 32768;
 
 struct SegDesc {        // one per (tile, term)
@@ -228,9 +229,23 @@ __global__ void __launch_bounds__(256) impact_hist_kernel(const uint64_t *__rest
         const uint64_t lo = max(term_offsets[t], i0), hi = min(min(term_offsets[t + 1], i1), (uint64_t)first_zero[t]);
         s_h[threadIdx.x] = 0;
         __syncthreads();
-        for (uint64_t i = lo + threadIdx.x; i < hi; i += 256) {
-            const uint32_t d = docids[i];
-            if (d >= doc_lo && d < doc_hi) atomicAdd(&s_h[impacts[i]], 1u);
+        // Lists written by the inversion are sorted by impact (create.py:41), so the 32 postings of a warp mostly
+        // share one value: count RUNS (one atomic per run) instead of 32 atomics on the same bin.
+        const uint32_t lane = lane_id();
+        for (uint64_t base = lo + (threadIdx.x - lane); base < hi; base += 256) {  // warp-uniform
+            const uint64_t i = base + lane;
+            uint32_t v = 0x100u + lane;  // not counted, and never equal to a neighbour
+            if (i < hi) {
+                const uint32_t d = docids[i];
+                if (d >= doc_lo && d < doc_hi) v = impacts[i];
+            }
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, v, 1);
+            const bool head = lane == 0 || v != prev;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (head && v < 0x100u) {
+                const uint32_t next = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+                atomicAdd(&s_h[v], (next ? (uint32_t)__ffs(next) - 1u : 32u) - lane);
+            }
         }
         __syncthreads();
         if (s_h[threadIdx.x]) atomicAdd(&hist[(size_t)slot * 256 + threadIdx.x], s_h[threadIdx.x]);
@@ -356,7 +371,7 @@ __global__ void seg_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t n_
     }
 }
 
-// per (tile, term): choose dense (u16 per doc of the tile) or sparse (u32 per posting) storage.
+// per (tile, term): choose dense (one byte per doc of the tile) or sparse (u32 per posting) storage.
 // On entry size16[s] holds the duplicate flag written by seg_bounds_kernel.
 __global__ void seg_size_kernel(const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ seg_end,
                                 const uint32_t *__restrict__ seg_odd, uint64_t n_segs, uint32_t n_terms, uint32_t tile_docs, uint32_t dense_ratio,
@@ -371,7 +386,7 @@ __global__ void seg_size_kernel(const uint32_t *__restrict__ seg_begin, const ui
             if (size16[s]) stats->n_dup_segments = 1;  // benign race: everybody writes 1
             const bool dense = dense_ratio != 0xFFFFFFFFu && (uint64_t)n * dense_ratio >= tile_docs && size16[s] == 0;
             if (dense) {
-                sz = tile_docs / 8u;  // one u16 per document: the accumulator layout itself
+                sz = tile_docs >> kDenseUnitShift;  // one byte per document of the tile
                 nf = n | kDenseFlag;
             } else {  // even documents first, then odd ones, each padded to whole 16-byte units
                 const uint32_t n_even = seg_odd[s] == 0xFFFFFFFFu ? n : seg_odd[s] - seg_begin[s];
@@ -405,12 +420,12 @@ __global__ void seg_desc_kernel(const uint32_t *__restrict__ off16, const uint32
         desc[s] = SegDesc{off16[s], n_flag[s]};
 }
 
-// dense segment: payload u16 [local docid] = impact.
+// dense segment: one impact byte per document of the tile, in the unit order dense_pass16 reads.
 // sparse posting word = impact << 16 | byte offset of the accumulator word ((local >> 1) * 4); the
 // parity of the document is implied by the unit the word sits in.
 __global__ void fill_payload_kernel(const uint64_t *__restrict__ keys, uint64_t n_vis, uint32_t n_terms,
                                     const SegDesc *__restrict__ desc, const uint32_t *__restrict__ seg_begin,
-                                    const uint32_t *__restrict__ seg_odd, uint8_t *__restrict__ payload)
+                                    const uint32_t *__restrict__ seg_odd, uint32_t tile_docs, uint8_t *__restrict__ payload)
 {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i];
@@ -419,7 +434,9 @@ __global__ void fill_payload_kernel(const uint64_t *__restrict__ keys, uint64_t 
         const uint32_t field = (uint32_t)(key >> kTkLocalShift) & 0xFFFFu;
         const uint32_t imp = (uint32_t)key & 0xFFu;
         if (d.n_flag & kDenseFlag) {
-            reinterpret_cast<uint16_t *>(payload)[(size_t)d.off16 * 8 + field_to_local(field)] = (uint16_t)imp;
+            // unit u = documents 8u..8u+7 then 8(u+H)..8(u+H)+7, H = tile_docs / 16 (see dense_pass16)
+            const uint32_t local = field_to_local(field), g = local >> 3, H = tile_docs >> 4;
+            payload[(size_t)d.off16 * 16 + (size_t)(g < H ? g : g - H) * 16 + (g < H ? 0u : 8u) + (local & 7u)] = (uint8_t)imp;
         } else {
             const uint32_t word = (imp << 16) | ((field & 0x7FFFu) << 2);
             const size_t slot = (field >> 15) ? (size_t)(d.n_flag >> 16) * 4 + (i - seg_odd[s]) : (i - seg_begin[s]);

@@ -18,12 +18,14 @@ struct di_index {
     int device = 0;
     uint32_t n_terms = 0, doc_lo = 0, doc_hi = 0;
     uint32_t n_tiles = 0, tile_docs = 0, tile_shift = 0, max_docid_plus1 = 0;
-    uint32_t dense_ratio = 4, cand_slack = 0;
+    uint32_t dense_ratio = 8, cand_slack = 0;
     uint64_t n_postings = 0, payload_bytes = 0, table_bytes = 0;
     uint64_t n_dense_segments = 0, n_sparse_segments = 0, n_dense_postings = 0;
     SegDesc *d_desc = nullptr;
     uint8_t *d_payload = nullptr;
     unsigned long long *d_df = nullptr;
+    // threshold seeds (build.cuh): per-term tables cum[v] = #postings with impact >= v for the frequent terms
+    uint32_t *d_seed_slot = nullptr, *d_seed_cum = nullptr;
 
     // search workspace (grown on demand)
     cudaStream_t stream = nullptr;
@@ -43,6 +45,8 @@ struct di_index {
         if (d_desc) cudaFree(d_desc);
         if (d_payload) cudaFree(d_payload);
         if (d_df) cudaFree(d_df);
+        if (d_seed_slot) cudaFree(d_seed_slot);
+        if (d_seed_cum) cudaFree(d_seed_cum);
         for (auto &b : ev)
             for (auto &e : b)
                 if (e) cudaEventDestroy(e);
@@ -244,6 +248,26 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
         if (stats.bad_docid)
             return set_error(DI_ERR_RANGE, "shard spans more than 65535 tiles of %u docs; raise tile_docs or shard further",
                              ix->tile_docs);
+        // threshold seeds: impact histograms of the frequent terms over the same visible postings
+        static const bool no_seeds = getenv("DI_B200_NO_SEEDS") != nullptr;  // tuning switch only
+        const uint64_t max_slots = std::min<uint64_t>(V, n_post / kSeedMinDf);
+        if (max_slots && !no_seeds) {
+            DevBuf d_cnt;
+            DI_TRY(d_cnt.alloc(4));
+            DI_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4, st));
+            DI_CUDA(cudaMalloc(&ix->d_seed_slot, (size_t)V * 4));
+            DI_CUDA(cudaMalloc(&ix->d_seed_cum, max_slots * 256 * 4));
+            DI_CUDA(cudaMemsetAsync(ix->d_seed_cum, 0, max_slots * 256 * 4, st));
+            seed_slots_kernel<<<grid_for(V, 256), 256, 0, st>>>(d_term_offsets, V, ix->d_seed_slot, d_cnt.as<uint32_t>());
+            DI_KERNEL_CHECK();
+            impact_hist_kernel<<<(unsigned)((n_post + kSeedChunk - 1) / kSeedChunk), 256, 0, st>>>(
+                d_term_offsets, V, d_docids, d_impacts, n_post, d_fz.as<unsigned long long>(), ix->doc_lo, ix->doc_hi,
+                ix->d_seed_slot, ix->d_seed_cum);
+            DI_KERNEL_CHECK();
+            seed_cum_kernel<<<(unsigned)((max_slots * 32 + 255) / 256), 256, 0, st>>>(ix->d_seed_cum, (uint32_t)max_slots);
+            DI_KERNEL_CHECK();
+            DI_CUDA(cudaStreamSynchronize(st));  // d_cnt goes out of scope
+        }
         d_fz.release();
         // hidden postings carry ~0 and sort to the end; the (tile, term, local) order is total
         DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, kTkLocalShift, 64, ws, st, &sorted));
@@ -285,6 +309,11 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
     DI_CUDA(cudaMemcpyAsync(&total16, d_size.as<uint32_t>() + n_segs, 4, cudaMemcpyDeviceToHost, st));
     DI_CUDA(cudaMemcpyAsync(&stats, d_stats.p, sizeof stats, cudaMemcpyDeviceToHost, st));
     DI_CUDA(cudaStreamSynchronize(st));
+    if (stats.n_dup_segments && ix->d_seed_cum) {  // a posting list that names a document twice: k postings != k documents
+        cudaFree(ix->d_seed_cum);
+        cudaFree(ix->d_seed_slot);
+        ix->d_seed_cum = ix->d_seed_slot = nullptr;
+    }
     ix->n_dense_segments = stats.n_dense_segments;
     ix->n_sparse_segments = stats.n_sparse_segments;
     ix->n_dense_postings = stats.n_dense_postings;
@@ -296,7 +325,7 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
     seg_desc_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_size.as<uint32_t>(), d_nflag.as<uint32_t>(), n_segs, ix->d_desc);
     DI_KERNEL_CHECK();
     fill_payload_kernel<<<grid_for(n_vis, 256), 256, 0, st>>>(sorted, n_vis, V, ix->d_desc, d_begin.as<uint32_t>(),
-                                                              d_odd.as<uint32_t>(), ix->d_payload);
+                                                              d_odd.as<uint32_t>(), ix->tile_docs, ix->d_payload);
     DI_KERNEL_CHECK();
     DI_CUDA(cudaStreamSynchronize(st));
     return DI_OK;
@@ -319,7 +348,7 @@ static int new_index(uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const d
     ix->doc_hi = doc_hi;
     ix->tile_docs = tile_docs;
     while ((1u << ix->tile_shift) < tile_docs) ++ix->tile_shift;
-    ix->dense_ratio = params && params->dense_ratio ? params->dense_ratio : 4u;
+    ix->dense_ratio = params && params->dense_ratio ? params->dense_ratio : 8u;
     ix->cand_slack = params ? params->cand_slack : 0u;
     cudaDeviceGetAttribute(&ix->smem_opt_in, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device);
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
@@ -452,7 +481,7 @@ static uint32_t pow2_ceil(uint32_t x)
 
 // finalize_topk_kernel with a shared-memory key buffer sized for the longest list it can meet
 // (max_n), between 32 KB and 128 KB; longer lists take the kernel's global-memory path.
-static int launch_finalize(uint64_t *cand, const uint32_t *cnt, uint32_t cap, uint32_t top_k, int top_shift,
+static int launch_finalize(uint64_t *cand, const uint32_t *cnt, uint32_t cap, uint32_t top_k,
                            uint32_t max_n, uint32_t n_queries, uint64_t *out_keys, uint32_t *out_counts, cudaStream_t st)
 {
     static thread_local bool attr_set = false;
@@ -462,7 +491,7 @@ static int launch_finalize(uint64_t *cand, const uint32_t *cnt, uint32_t cap, ui
     }
     uint32_t smem_keys = kSortSmemKeys;
     while (smem_keys < max_n && smem_keys < 16384) smem_keys <<= 1;
-    finalize_topk_kernel<<<n_queries, kScoreThreads, (size_t)smem_keys * 8, st>>>(cand, cnt, cap, top_k, top_shift,
+    finalize_topk_kernel<<<n_queries, kScoreThreads, (size_t)smem_keys * 8, st>>>(cand, cnt, cap, top_k,
                                                                                  smem_keys, out_keys, out_counts);
     DI_KERNEL_CHECK();
     return DI_OK;
@@ -495,7 +524,6 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     uint32_t c0 = ix->cand_slack ? ix->cand_slack : std::max(2u * top_k, 256u);
     c0 = std::max(c0, top_k);
     const uint32_t cap = std::max(c0 + ix->tile_docs, pow2_ceil(top_k));
-    const int top_shift = acc32 ? 48 : 40;
 
     if (acc32 && !ix->attr_set32) {
         DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
@@ -571,7 +599,6 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         a.cap = cap;
         a.c0 = c0;
         a.k = top_k;
-        a.top_shift = top_shift;
         a.recs = ix->ws_order.as<QueryRec>();
         a.n_queries = nq;
         a.n_tiles = ix->n_tiles;
@@ -596,6 +623,12 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
             DI_CUDA(cudaMemsetAsync(a.theta, 0, nv * 8, st));
         }
         DI_CUDA(cudaEventRecord(ix->ev[b][0], st));
+        if (ix->n_tiles && ix->d_seed_cum) {
+            seed_theta_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_q_terms, a.q_offsets, nq, lanes, ix->d_seed_slot,
+                                                                ix->d_seed_cum, ix->n_terms, top_k, a.theta);
+            DI_KERNEL_CHECK();
+            ++ix->other_launches;
+        }
         if (ix->n_tiles) {
             query_order_kernel<<<1, 1024, 0, st>>>(d_q_terms, a.q_offsets, ix->d_df, ix->n_terms, nq,
                                                    ix->ws_order.as<QueryRec>());
@@ -644,10 +677,10 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         uint64_t *out_keys = d_out_keys + (uint64_t)q0 * top_k;
         uint32_t *out_counts = d_out_counts + q0;
         if (lanes == 1) {
-            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, top_shift, /*max_n=*/c0, nq, out_keys, out_counts, st));
+            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, /*max_n=*/c0, nq, out_keys, out_counts, st));
             ++ix->other_launches;
         } else {  // per-lane top-k rows [lanes][nq][k], then the same merge the multi-GPU path uses
-            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, top_shift, /*max_n=*/c0, (uint32_t)nv,
+            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, /*max_n=*/c0, (uint32_t)nv,
                                    ix->ws_lane_keys.as<uint64_t>(), ix->ws_lane_counts.as<uint32_t>(), st));
             DI_TRY(di_merge_topk_dev(ix->ws_lane_keys.as<uint64_t>(), ix->ws_lane_counts.as<uint32_t>(), lanes, nq, top_k, top_k,
                                      out_keys, out_counts, nullptr, st));
@@ -732,7 +765,7 @@ extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_co
     merge_gather_kernel<<<n_queries, 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, k_in, cand.as<uint64_t>(),
                                                   cnt.as<uint32_t>(), cap);
     DI_KERNEL_CHECK();
-    DI_TRY(launch_finalize(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k, 48, /*max_n=*/n_shards * k_in, n_queries,
+    DI_TRY(launch_finalize(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k, /*max_n=*/n_shards * k_in, n_queries,
                            d_keys_out, d_counts_out, st));
     if (d_incomplete) {
         merge_check_kernel<<<grid_for(n_queries, 256), 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, k_in, top_k,

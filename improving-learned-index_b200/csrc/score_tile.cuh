@@ -5,12 +5,14 @@
 // postings, scores[doc] += impact) and of SparseSearch.search (nano_beir_evaluator.py:118-121).
 //
 // One CTA = one (query, tile) work item.
-//   phase 1  dense segments (u16 impact per document of the tile, 128-bit loads) are summed in
-//            registers and STORED into the shared-memory accumulators — this also zeroes them;
+//   phase 1  dense segments (one impact byte per document of the tile, 128-bit loads) are widened and
+//            summed in registers and STORED into the shared-memory accumulators — this also zeroes them;
 //   phase 2  sparse segments (u32 postings) of all the query's terms are flattened into one index
 //            space, streamed with 128-bit loads and added with shared-memory atomics;
-//   phase 3  the accumulators are scanned once; documents whose key (score, ~docid) can still reach
-//            the query's top-k are appended to the query's candidate list in global memory.
+//   phase 3  the accumulators are scanned once (a register bit mask per thread marks the groups that hold
+//            a document at or above the query's threshold); those groups are then expanded with every lane
+//            busy and the surviving keys (score, ~docid) appended to the query's candidate list in global
+//            memory. Every query starts from a PROVEN threshold (build.cuh, threshold seeds).
 // Accumulators are u16 pairs packed in 32-bit words (ACC32 = false; queries of <= 257 terms cannot
 // overflow 16 bits) or u32 (ACC32 = true).
 #pragma once
@@ -34,9 +36,6 @@ constexpr int kMaxSeg = 32;        // query terms handled per round inside a wor
 #endif
 constexpr int kSparseUnroll = DI_SPARSE_UNROLL;  // independent 128-bit posting loads in flight per thread
 constexpr int kHistBins = 1024;    // score histogram of the tile-local pre-selection
-#ifndef DI_DEFER_EMIT
-#define DI_DEFER_EMIT 1            // phase 3 remembers hit groups and expands them with all lanes busy
-#endif
 
 constexpr int kRecInlineTerms = 12;
 struct __align__(64) QueryRec {   // one cache-line-friendly record per query of the batch
@@ -56,7 +55,6 @@ struct SearchArgs {
     uint64_t *theta;            // [n_queries] lower bound on the k-th best key (0 = none yet)
     uint32_t n_terms, tile_docs, tile_shift, doc_lo;
     uint32_t cap, c0, k;
-    int top_shift;              // highest radix-select digit that can be non-zero
     const QueryRec *recs;       // [n_queries] work-item records in launch order
     uint32_t *done;             // [lanes * n_queries] tiles completed per (lane, query) (persistent launch), or nullptr
     // Small batches cannot fill the GPU with one tile chain per query, so the tile range is cut into
@@ -129,35 +127,48 @@ __global__ void __launch_bounds__(1024) query_order_kernel(const uint32_t *__res
     }
 }
 
-// ---- phase 1 helpers: NB dense segments, 8 documents per 128-bit load -----------------------
+// ---- phase 1 helpers: NB dense segments, 16 documents per 128-bit load -----------------------
+// A dense segment stores one BYTE per document of the tile. 16-byte unit u holds documents 8u .. 8u+7 and
+// 8(u+H) .. 8(u+H)+7 (H = tile_docs / 16 units), i.e. the accumulator words s_acc4[u] and s_acc4[u + H]: a
+// warp's stores stay contiguous (no bank conflicts) and a byte pair widens to a packed u16 accumulator word
+// with one PRMT.
+__device__ __forceinline__ void add_bytes8(uint4 &a, uint32_t lo, uint32_t hi)
+{
+    a.x += __byte_perm(lo, 0, 0x4140);
+    a.y += __byte_perm(lo, 0, 0x4342);
+    a.z += __byte_perm(hi, 0, 0x4140);
+    a.w += __byte_perm(hi, 0, 0x4342);
+}
+
 template <int NB, bool INIT>
 __device__ __forceinline__ void dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
-                                             const uint4 *p3, uint32_t groups)
+                                             const uint4 *p3, uint32_t units)
 {
     const uint4 *ptr[4] = {p0, p1, p2, p3};
-    // U groups per step so that about 8 independent 128-bit loads are in flight per thread whatever
+    // U units per step so that about 8 independent 128-bit loads are in flight per thread whatever
     // the number of dense terms (a work item is latency-bound: few CTAs per SM, L2-resident postings)
     constexpr int U = NB <= 1 ? 8 : (NB == 2 ? 4 : 2);
-    for (uint32_t g0 = threadIdx.x; g0 < groups; g0 += U * kScoreThreads) {
+    for (uint32_t g0 = threadIdx.x; g0 < units; g0 += U * kScoreThreads) {
         uint4 v[U][NB > 0 ? NB : 1];
 #pragma unroll
         for (int s = 0; s < U; ++s) {
             const uint32_t g = g0 + s * kScoreThreads;
 #pragma unroll
-            for (int u = 0; u < NB; ++u) v[s][u] = g < groups ? ldg_stream_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < NB; ++u) v[s][u] = g < units ? ldg_stream_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int s = 0; s < U; ++s) {
             const uint32_t g = g0 + s * kScoreThreads;
-            if (g < groups) {
-                // a dense segment stores one u16 per document, i.e. exactly the accumulator layout: the
-                // update is four plain 32-bit adds per 8 documents (two u16 lanes per word, no carries)
+            if (g < units) {
                 uint4 a = INIT ? make_uint4(0, 0, 0, 0) : s_acc4[g];
+                uint4 b = INIT ? make_uint4(0, 0, 0, 0) : s_acc4[g + units];
 #pragma unroll
                 for (int u = 0; u < NB; ++u) {
-                    a.x += v[s][u].x; a.y += v[s][u].y; a.z += v[s][u].z; a.w += v[s][u].w;
+                    add_bytes8(a, v[s][u].x, v[s][u].y);
+                    add_bytes8(b, v[s][u].z, v[s][u].w);
                 }
                 s_acc4[g] = a;
+                s_acc4[g + units] = b;
             }
         }
     }
@@ -177,53 +188,161 @@ __device__ __forceinline__ void dense_dispatch16(int nb, uint4 *s_acc4, const ui
     }
 }
 
-// ACC32 twin (long queries only): plain loop, 8 documents = two 128-bit accumulator words
+// ACC32 twin (long queries only): plain loop; the unit's two 8-document halves go to accumulator words
+// 2u, 2u+1 and 2(u+H), 2(u+H)+1
 template <bool INIT>
 __device__ __forceinline__ void dense_pass32(uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff, int nb,
-                                             uint32_t groups)
+                                             uint32_t units)
 {
-    for (uint32_t g = threadIdx.x; g < groups; g += kScoreThreads) {
-        uint32_t a[8];
+    for (uint32_t g = threadIdx.x; g < units; g += kScoreThreads) {
+        uint32_t a[16];
         if (INIT) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = 0;
+            for (int i = 0; i < 16; ++i) a[i] = 0;
         } else {
-            const uint4 lo = s_acc4[2 * g], hi = s_acc4[2 * g + 1];
-            a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
-            a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 lo = s_acc4[2 * (g + h * units)], hi = s_acc4[2 * (g + h * units) + 1];
+                a[8 * h + 0] = lo.x; a[8 * h + 1] = lo.y; a[8 * h + 2] = lo.z; a[8 * h + 3] = lo.w;
+                a[8 * h + 4] = hi.x; a[8 * h + 5] = hi.y; a[8 * h + 6] = hi.z; a[8 * h + 7] = hi.w;
+            }
         }
         for (int j = 0; j < nb; ++j) {
             const uint4 v = ldg_stream_v4(payload4 + doff[j] + g);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                a[2 * i] += w[i] & 0xFFFFu;
-                a[2 * i + 1] += w[i] >> 16;
-            }
+            for (int i = 0; i < 16; ++i) a[i] += (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
         }
-        s_acc4[2 * g] = make_uint4(a[0], a[1], a[2], a[3]);
-        s_acc4[2 * g + 1] = make_uint4(a[4], a[5], a[6], a[7]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            s_acc4[2 * (g + h * units)] = make_uint4(a[8 * h + 0], a[8 * h + 1], a[8 * h + 2], a[8 * h + 3]);
+            s_acc4[2 * (g + h * units) + 1] = make_uint4(a[8 * h + 4], a[8 * h + 5], a[8 * h + 6], a[8 * h + 7]);
+        }
     }
 }
 
-// ---- phase 3 helper -------------------------------------------------------------------------
-__device__ __forceinline__ void emit_candidate(uint32_t score, uint32_t docid, uint64_t theta, uint64_t *cand,
-                                               uint32_t cnt0, uint32_t *s_emit)
-{
-    const uint64_t key = make_key(score, docid);
-    if (key >= theta) cand[cnt0 + atomicAdd(s_emit, 1u)] = key;
-}
+// ---- phase 3 helpers ------------------------------------------------------------------------
+// Accumulators are read in groups of one 128-bit word: 8 documents (u16 pairs) or 4 (u32).
+template <bool ACC32> __device__ __forceinline__ constexpr int group_docs() { return ACC32 ? 4 : 8; }
 
-// the 8 packed u16 accumulators of group g: append those above tm
-__device__ __forceinline__ void emit_group16(const uint4 x, uint32_t g, uint32_t tm, uint32_t doc_base, uint64_t theta,
-                                             uint64_t *cand, uint32_t cnt0, uint32_t *s_emit)
+template <bool ACC32> __device__ __forceinline__ uint32_t group_score(const uint4 &x, int i)
 {
     const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    if (ACC32) return w[i];
+    return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+}
+
+// slow path (list already holds more than kHistBins hit groups): one shared-memory atomic per candidate
+template <bool ACC32>
+__device__ __forceinline__ void emit_group(const uint4 &x, uint32_t g, uint32_t ths, uint32_t doc_base, uint64_t theta,
+                                           uint64_t *cand, uint32_t cnt0, uint32_t *s_emit)
+{
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t lo = w[i] & 0xFFFFu, hi = w[i] >> 16;
-        if (lo > tm) emit_candidate(lo, doc_base + 8 * g + 2 * i, theta, cand, cnt0, s_emit);
-        if (hi > tm) emit_candidate(hi, doc_base + 8 * g + 2 * i + 1, theta, cand, cnt0, s_emit);
+    for (int i = 0; i < group_docs<ACC32>(); ++i) {
+        const uint32_t sc = group_score<ACC32>(x, i);
+        if (sc >= ths) {
+            const uint64_t key = make_key(sc, doc_base + group_docs<ACC32>() * g + i);
+            if (key >= theta) cand[cnt0 + atomicAdd(s_emit, 1u)] = key;
+        }
+    }
+}
+
+// One pass over the tile's accumulators: groups holding a document with score >= ths are REMEMBERED in
+// s_hits (first kHistBins of them; *s_nhits counts all). Emitting on the spot would run the key / compare /
+// append sequence with one or two lanes active; expand_hits() does it with every lane busy.
+// INPLACE: groups beyond the kHistBins slots are emitted on the spot instead of being dropped.
+template <bool ACC32>
+__device__ __forceinline__ bool group_hit(const uint4 &x, uint32_t ths, uint32_t tm2)
+{
+    if (!ACC32) {  // per-lane max of the four words (3-input SIMD max), one more max against the threshold
+        const uint32_t m = __vmaxu2(__vmaxu2(x.x, x.y), __vmaxu2(x.z, x.w));
+        return __vmaxu2(m, tm2) != tm2;
+    }
+    return max(max(x.x, x.y), max(x.z, x.w)) >= ths;
+}
+
+// The hot loop only sets a bit per hit group in a per-thread register mask (no branch, no atomic); after every
+// 32 steps the warp compacts its masks into s_hits with one prefix sum and one shared-memory atomic.
+template <bool ACC32, bool INPLACE>
+__device__ __forceinline__ void scan_groups(const uint4 *s_acc4, uint32_t T, uint32_t ths, uint32_t *s_hits,
+                                            uint32_t *s_nhits, uint32_t doc_base, uint64_t theta, uint64_t *cand,
+                                            uint32_t cnt0, uint32_t *s_emit)
+{
+    const uint32_t groups = T / group_docs<ACC32>();  // a multiple of 32: every lane of a warp runs the same steps
+    const uint32_t tm = ths - 1u, tm2 = tm | (tm << 16);  // u16 half > tm  <=>  half >= ths
+    const uint32_t lane = lane_id();
+    for (uint32_t c0 = threadIdx.x; c0 < groups; c0 += 32 * kScoreThreads) {  // chunk = 32 steps of the block
+        uint32_t mask = 0;
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 4) {
+            if (c0 + i0 * kScoreThreads < groups) {  // warp-uniform
+                uint4 x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t g = c0 + (i0 + i) * kScoreThreads;
+                    x[i] = g < groups ? s_acc4[g] : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (group_hit<ACC32>(x[i], ths, tm2)) mask |= 1u << (i0 + i);
+            }
+        }
+        if (!__any_sync(0xffffffffu, mask != 0)) continue;  // the usual case once the query has a threshold
+        const uint32_t c = __popc(mask);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += up;
+        }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(s_nhits, incl);
+        uint32_t slot = __shfl_sync(0xffffffffu, base, 31) + incl - c;
+        while (mask) {
+            const uint32_t g = c0 + (uint32_t)(__ffs(mask) - 1) * kScoreThreads;
+            mask &= mask - 1u;
+            if (slot < (uint32_t)kHistBins) s_hits[slot] = g;
+            else if (INPLACE) emit_group<ACC32>(s_acc4[g], g, ths, doc_base, theta, cand, cnt0, s_emit);
+            ++slot;
+        }
+    }
+}
+
+// Appends the candidates of the remembered groups: one group per lane, ONE shared-memory atomic per warp
+// (warp prefix sum of the per-lane counts), keys written to cand[cnt0 + ...] in arbitrary order.
+template <bool ACC32>
+__device__ __forceinline__ void expand_hits(const uint4 *s_acc4, const uint32_t *s_hits, uint32_t n_hits, uint32_t ths,
+                                            uint32_t doc_base, uint64_t theta, uint64_t *cand, uint32_t cnt0,
+                                            uint32_t *s_emit)
+{
+    const uint32_t lane = lane_id();
+    for (uint32_t j0 = threadIdx.x - lane; j0 < n_hits; j0 += kScoreThreads) {  // warp-uniform trip count
+        const uint32_t j = j0 + lane;
+        uint32_t flags = 0, g = 0;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (j < n_hits) {
+            g = s_hits[j];
+            x = s_acc4[g];
+#pragma unroll
+            for (int i = 0; i < group_docs<ACC32>(); ++i) {
+                const uint32_t sc = group_score<ACC32>(x, i);
+                if (sc >= ths && make_key(sc, doc_base + group_docs<ACC32>() * g + i) >= theta) flags |= 1u << i;
+            }
+        }
+        const uint32_t c = __popc(flags);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += up;
+        }
+        uint32_t base = 0;
+        if (lane == 31 && incl) base = atomicAdd(s_emit, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t pos = cnt0 + base + incl - c;
+#pragma unroll
+        for (int i = 0; i < group_docs<ACC32>(); ++i)
+            if (flags & (1u << i)) cand[pos++] = make_key(group_score<ACC32>(x, i), doc_base + group_docs<ACC32>() * g + i);
     }
 }
 
@@ -238,8 +357,8 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     __shared__ uint32_t s_sunits[kMaxSeg];     // sparse segments: total 16 B units
     __shared__ uint32_t s_seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
     __shared__ uint32_t s_spref[kMaxSeg + 1];  // exclusive prefix of s_sunits
-    __shared__ uint32_t s_nd, s_ns, s_emit, s_npost, s_ready, s_nhits;
-    __shared__ uint32_t s_hist[kHistBins];
+    __shared__ uint32_t s_nd, s_ns, s_emit, s_ready, s_nhits;
+    __shared__ __align__(16) uint32_t s_hist[kHistBins];  // score histogram / hit-group list / radix-select scratch
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tmp[2];
 
@@ -260,7 +379,6 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
 
     DI_PROF_DECL;
-    if (tid == 0) s_npost = 0;
     uint64_t theta = 0;
     uint32_t cnt0 = 0;
     bool first = true, touched = false, have_state = false;
@@ -274,13 +392,11 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
                 const SegDesc d = desc[t];
                 if (d.n_flag & kDenseFlag) {
                     s_doff[atomicAdd(&s_nd, 1u)] = d.off16;
-                    atomicAdd(&s_npost, d.n_flag & ~kDenseFlag);
                 } else if (d.n_flag) {
                     const uint32_t j = atomicAdd(&s_ns, 1u);
                     s_soff[j] = d.off16;
                     s_sunits[j] = d.n_flag & 0xFFFFu;
                     s_seven[j] = d.n_flag >> 16;
-                    atomicAdd(&s_npost, (d.n_flag & 0xFFFFu) * 4u);  // upper bound on the postings
                 }
             }
         }
@@ -302,14 +418,14 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
 
         // ---- phase 1: dense segments; the very first pass stores (and thereby zeroes) the accumulators
         if (!ACC32) {
-            if (first) dense_dispatch16<true>(nd < 4 ? (int)nd : 4, s_acc4, payload4, s_doff, T >> 3);
+            if (first) dense_dispatch16<true>(nd < 4 ? (int)nd : 4, s_acc4, payload4, s_doff, T >> kDenseUnitShift);
             // later batches read-modify-write the same words the same thread wrote: no barrier needed
             for (uint32_t j0 = first ? 4 : 0; j0 < nd; j0 += 4) {
-                dense_dispatch16<false>(nd - j0 < 4 ? (int)(nd - j0) : 4, s_acc4, payload4, s_doff + j0, T >> 3);
+                dense_dispatch16<false>(nd - j0 < 4 ? (int)(nd - j0) : 4, s_acc4, payload4, s_doff + j0, T >> kDenseUnitShift);
             }
         } else {
-            if (first) dense_pass32<true>(s_acc4, payload4, s_doff, (int)nd, T >> 3);
-            else if (nd) dense_pass32<false>(s_acc4, payload4, s_doff, (int)nd, T >> 3);
+            if (first) dense_pass32<true>(s_acc4, payload4, s_doff, (int)nd, T >> kDenseUnitShift);
+            else if (nd) dense_pass32<false>(s_acc4, payload4, s_doff, (int)nd, T >> kDenseUnitShift);
         }
         __syncthreads();
         DI_PROF_MARK(1);  // dense
@@ -391,86 +507,46 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     if (theta != 0 && key_docid(theta) < doc_base) ++ths;
     if (tid == 0) { s_emit = 0; s_nhits = 0; }
     uint64_t theta_pre = 0;
-
-    if (theta == 0 && cnt0 + min(T, s_npost) > p.c0) {
-        // No threshold yet and this tile alone could flood the list (typically the first tile of a
-        // query with a frequent term): pre-select inside the tile with a score histogram. Keeping every
-        // document of the bins that hold the tile's k best is exact (at least k of them score >= the cut).
-        int shift = 0;
-        const uint32_t max_score = 255u * (uint32_t)min((uint64_t)(qe - qb), (uint64_t)65535);
-        while ((max_score >> shift) >= (uint32_t)kHistBins) ++shift;
-        for (uint32_t i = tid; i < (uint32_t)kHistBins; i += kScoreThreads) s_hist[i] = 0;
-        __syncthreads();
-        if (!ACC32) {
-            for (uint32_t g = tid; g < (T >> 1); g += kScoreThreads) {
-                const uint32_t w = s_acc[g];
-                if (w & 0xFFFFu) atomicAdd(&s_hist[(w & 0xFFFFu) >> shift], 1u);
-                if (w >> 16) atomicAdd(&s_hist[(w >> 16) >> shift], 1u);
-            }
-        } else {
-            for (uint32_t g = tid; g < T; g += kScoreThreads) {
-                const uint32_t w = s_acc[g];
-                if (w) atomicAdd(&s_hist[w >> shift], 1u);
-            }
-        }
-        __syncthreads();
-        const uint32_t bin = block_find_bin_from_top(s_hist, kHistBins, p.k, s_tmp);
-        ths = max(1u, bin << shift);
-        // at least k documents of this tile score >= ths, so (ths, any docid) is already a valid lower
-        // bound of the final k-th key: publish it, the next tiles then skip this pre-selection
-        if (bin) theta_pre = (uint64_t)ths << 32;
-    }
     __syncthreads();
-    DI_PROF_MARK(3);  // state wait + tile-local pre-selection
+    DI_PROF_MARK(3);  // state wait
 
-    if (!ACC32) {
-        const uint32_t tm = ths - 1u, tm2 = tm | (tm << 16);  // half > tm  <=>  half >= ths
-        // 8 u16 accumulators per 128-bit load, two loads per step. Fast path per load: per-lane max of
-        // the four words (two 3-input SIMD max instructions), one more max against the threshold, one compare.
-        const uint32_t groups = T >> 3;
-        for (uint32_t g0 = tid; g0 < groups; g0 += 2 * kScoreThreads) {
-            uint4 x[2];
-            x[0] = s_acc4[g0];
-            x[1] = g0 + kScoreThreads < groups ? s_acc4[g0 + kScoreThreads] : make_uint4(0, 0, 0, 0);
+    // s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
+    scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
+    __syncthreads();
+    if (s_nhits > (uint32_t)kHistBins) {
+        // Flooded: more groups than slots hold a document at or above the threshold (the first tiles of a
+        // frequent-term query whose bound is still loose).
+        if ((uint32_t)theta == 0u) {
+            // No exact k-th key yet (nothing, or only a seed bound): pre-select inside the tile with a score
+            // histogram. Keeping every document of the bins that hold the tile's k best is exact (at least k
+            // of them score >= the cut), and the cut is a valid bound for the tiles that follow.
+            int shift = 0;
+            const uint32_t max_score = 255u * (uint32_t)min((uint64_t)(qe - qb), (uint64_t)65535);
+            while ((max_score >> shift) >= (uint32_t)kHistBins) ++shift;
+            for (uint32_t i = tid; i < (uint32_t)kHistBins; i += kScoreThreads) s_hist[i] = 0;
+            __syncthreads();
+            for (uint32_t g = tid; g < T / group_docs<ACC32>(); g += kScoreThreads) {
+                const uint4 x = s_acc4[g];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t m = __vmaxu2(__vmaxu2(x[h].x, x[h].y), __vmaxu2(x[h].z, x[h].w));
-                if (__vmaxu2(m, tm2) != tm2) {  // rare: some document of the 8 is at or above the threshold
-                    const uint32_t g = g0 + h * kScoreThreads;
-#if DI_DEFER_EMIT
-                    // Only REMEMBER the group here. Emitting inside this divergent branch would run the whole
-                    // key/compare/append sequence with one or two lanes active; the groups are expanded below
-                    // with every lane busy. s_hist is free between the pre-selection and the radix select.
-                    const uint32_t hit = atomicAdd(&s_nhits, 1u);
-                    if (hit < (uint32_t)kHistBins) {
-                        s_hist[hit] = g;
-                        continue;
-                    }
-                    // more hit groups than slots (first tiles of a frequent-term query): emit in place
-#endif
-                    emit_group16(x[h], g, tm, doc_base, theta, cand, cnt0, &s_emit);
+                for (int i = 0; i < group_docs<ACC32>(); ++i) {
+                    const uint32_t sc = group_score<ACC32>(x, i);
+                    if (sc >= ths) atomicAdd(&s_hist[sc >> shift], 1u);
                 }
             }
-        }
-#if DI_DEFER_EMIT
-        __syncthreads();
-        const uint32_t n_hits = min(s_nhits, (uint32_t)kHistBins);
-        for (uint32_t j = tid; j < n_hits; j += kScoreThreads) {  // one remembered group per lane
-            const uint32_t g = s_hist[j];
-            emit_group16(s_acc4[g], g, tm, doc_base, theta, cand, cnt0, &s_emit);
-        }
-#endif
-    } else {
-        for (uint32_t g = tid; g < (T >> 2); g += kScoreThreads) {
-            const uint4 x = s_acc4[g];
-            if (max(max(x.x, x.y), max(x.z, x.w)) >= ths) {
-                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (w[i] >= ths) emit_candidate(w[i], doc_base + 4 * g + i, theta, cand, cnt0, &s_emit);
+            __syncthreads();
+            const uint32_t bin = block_find_bin_from_top(s_hist, kHistBins, p.k, s_tmp);  // 0: fewer than k documents
+            if ((bin << shift) > ths) {
+                ths = bin << shift;
+                theta_pre = (uint64_t)ths << 32;
             }
         }
+        __syncthreads();  // everybody has read s_nhits
+        if (tid == 0) s_nhits = 0;
+        __syncthreads();
+        scan_groups<ACC32, true>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
+        __syncthreads();
     }
+    expand_hits<ACC32>(s_acc4, s_hist, min(s_nhits, (uint32_t)kHistBins), ths, doc_base, theta, cand, cnt0, &s_emit);
     __syncthreads();
     DI_PROF_MARK(4);  // accumulator scan + emission
     uint32_t n = cnt0 + s_emit;  // <= c0 + tile_docs <= cap
@@ -479,11 +555,11 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
         uint64_t kth;
         if (n <= (T * (ACC32 ? 4u : 2u)) / 8u) {
             // the accumulators are dead now: their shared memory stages the whole list (the usual case)
-            kth = block_cut_to_k_staged(cand, n, p.k, p.top_shift, reinterpret_cast<uint64_t *>(s_acc4), s_hist, s_tmp,
+            kth = block_cut_to_k_staged(cand, n, p.k, reinterpret_cast<uint64_t *>(s_acc4), s_hist, s_tmp,
                                         &s_emit);
             n = p.k;
         } else {
-            kth = block_select_kth<true>(cand, n, p.k, p.top_shift, s_hist, s_tmp);
+            kth = block_select_kth<true>(cand, n, p.k, s_hist, s_tmp);
             n = block_compact_ge<true>(cand, n, kth, s_scan);
         }
         if (tid == 0) p.theta[sq] = kth;  // >= theta_pre: k of the emitted keys are at or above that bound

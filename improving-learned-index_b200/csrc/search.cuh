@@ -21,11 +21,11 @@ constexpr uint32_t kSortSmemKeys = 4096;
 // One CTA per query: cut the candidate list to the k best and sort them descending by key
 // (score desc, docid asc). Sorting happens in shared memory when the list fits.
 __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *cand_all, const uint32_t *cnt, uint32_t cap,
-                                                                    uint32_t k, int top_shift, uint32_t smem_keys,
+                                                                    uint32_t k, uint32_t smem_keys,
                                                                     uint64_t *out_keys, uint32_t *out_counts)
 {
     extern __shared__ uint64_t s_keys[];  // smem_keys entries
-    __shared__ uint32_t s_hist[256];
+    __shared__ __align__(16) uint32_t s_hist[kSelectSmemWords];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tmp[2];
     const uint32_t q = blockIdx.x;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = cand[i];
         __syncthreads();
         if (n > k) {
-            const uint64_t kth = block_select_kth(s_keys, n, k, top_shift, s_hist, s_tmp);
+            const uint64_t kth = block_select_kth(s_keys, n, k, s_hist, s_tmp);
             n = block_compact_ge(s_keys, n, kth, s_scan);
         }
         uint32_t np2 = 1;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *
         return;
     }
     if (n > k) {
-        const uint64_t kth = block_select_kth(cand, n, k, top_shift, s_hist, s_tmp);
+        const uint64_t kth = block_select_kth(cand, n, k, s_hist, s_tmp);
         n = block_compact_ge(cand, n, kth, s_scan);
     }
     uint32_t np2 = 1;

@@ -9,14 +9,41 @@ namespace di {
 
 // ---------------------------------------------------------------------------- exact selection
 // k-th largest of n unique 64-bit keys (n >= k >= 1): MSB-first radix select, 8 bits per pass.
+//  * The first digit starts at the highest bit in which the keys DIFFER (one OR-reduction pass): candidate
+//    scores cluster in a narrow range, so a digit aligned to the key layout would put every key into two or
+//    three bins (32-way same-address shared-memory atomics) and decide nothing.
+//  * As soon as the bin holding the k-th key has at most kSelectSmall keys, they are gathered and ranked
+//    directly instead of running the remaining passes (usually after the first pass).
 // GLOBAL_CG: keys live in global memory written by other SMs during this launch -> read through L2.
+// s_hist: kSelectSmemWords 32-bit words, 8-byte aligned.
+constexpr uint32_t kSelectSmall = 64;
+constexpr int kSelectSmemWords = 256 + 2 * (kSelectSmall + 1) + 2;
+
 template <bool GLOBAL_CG = false>
-__device__ uint64_t block_select_kth(const uint64_t *keys, uint32_t n, uint32_t k, int top_shift,
-                                     uint32_t *s_hist /*256*/, uint32_t *s_tmp /*2*/)
+__device__ uint64_t block_select_kth(const uint64_t *keys, uint32_t n, uint32_t k, uint32_t *s_hist, uint32_t *s_tmp /*2*/)
 {
-    uint64_t prefix = 0, mask = 0;
+    uint64_t *s_small = reinterpret_cast<uint64_t *>(s_hist + 256);  // [kSelectSmall] gathered keys, then the result
+    uint32_t *s_ctl = s_hist + 256 + 2 * (kSelectSmall + 1);         // [0] keys in the chosen bin, [1] gather cursor
+    const uint64_t first = GLOBAL_CG ? ld_cg_u64(keys) : keys[0];
+    if (threadIdx.x < 2) s_tmp[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t diff = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) diff |= (GLOBAL_CG ? ld_cg_u64(keys + i) : keys[i]) ^ first;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, o);
+    if (lane_id() == 0 && diff) {
+        if ((uint32_t)diff) atomicOr(&s_tmp[0], (uint32_t)diff);
+        if ((uint32_t)(diff >> 32)) atomicOr(&s_tmp[1], (uint32_t)(diff >> 32));
+    }
+    __syncthreads();
+    diff = ((uint64_t)s_tmp[1] << 32) | s_tmp[0];
+    __syncthreads();  // s_tmp is reused below
+    if (diff == 0) return first;  // n == 1
+    const int msb = 63 - __clzll((long long)diff);
+    uint64_t mask = msb == 63 ? 0ull : ~((2ull << msb) - 1ull);  // the bits above msb are common to all keys
+    uint64_t prefix = first & mask;
     uint32_t remaining = k;
-    for (int shift = top_shift; shift >= 0; shift -= 8) {
+    for (int shift = msb > 7 ? msb - 7 : 0;; shift = shift > 8 ? shift - 8 : 0) {
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -46,6 +73,8 @@ __device__ uint64_t block_select_kth(const uint64_t *keys, uint32_t n, uint32_t 
                     if (r <= c[j]) {
                         s_tmp[0] = 255 - 8 * lane - j;
                         s_tmp[1] = r;
+                        s_ctl[0] = c[j];
+                        s_ctl[1] = 0;
                         break;
                     }
                     r -= c[j];
@@ -56,9 +85,30 @@ __device__ uint64_t block_select_kth(const uint64_t *keys, uint32_t n, uint32_t 
         prefix |= (uint64_t)s_tmp[0] << shift;
         mask |= 0xFFull << shift;
         remaining = s_tmp[1];
+        const uint32_t in_bin = s_ctl[0];
+        if (shift == 0) {
+            __syncthreads();
+            return prefix;
+        }
+        if (in_bin <= kSelectSmall) {  // gather the bin's keys and rank them directly
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint64_t key = GLOBAL_CG ? ld_cg_u64(keys + i) : keys[i];
+                if ((key & mask) == prefix) s_small[atomicAdd(&s_ctl[1], 1u)] = key;
+            }
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < in_bin; t += blockDim.x) {
+                const uint64_t mine = s_small[t];
+                uint32_t above = 0;
+                for (uint32_t j = 0; j < in_bin; ++j) above += s_small[j] > mine;
+                if (above + 1 == remaining) s_small[kSelectSmall] = mine;  // keys are unique: exactly one writer
+            }
+            __syncthreads();
+            const uint64_t kth = s_small[kSelectSmall];
+            __syncthreads();
+            return kth;
+        }
         __syncthreads();
     }
-    return prefix;
 }
 
 // keeps keys >= theta, in place, order preserved; returns how many were kept
@@ -82,17 +132,31 @@ __device__ uint32_t block_compact_ge(uint64_t *keys, uint32_t n, uint64_t theta,
 // Cuts a candidate list (global memory, n unique keys, n >= k) to its k best through a shared-memory
 // staging buffer of at least n keys: one coalesced read, the radix-select passes run on shared memory,
 // one write of the k survivors to keys[0..k) (unordered). Returns the k-th largest key.
-__device__ __forceinline__ uint64_t block_cut_to_k_staged(uint64_t *keys, uint32_t n, uint32_t k, int top_shift,
-                                                          uint64_t *s_keys, uint32_t *s_hist /*256*/,
-                                                          uint32_t *s_tmp /*2*/, uint32_t *s_counter)
+__device__ __forceinline__ uint64_t block_cut_to_k_staged(uint64_t *keys, uint32_t n, uint32_t k, uint64_t *s_keys,
+                                                          uint32_t *s_hist /*kSelectSmemWords*/, uint32_t *s_tmp /*2*/,
+                                                          uint32_t *s_counter)
 {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = ld_cg_u64(keys + i);  // other SMs wrote them
+    for (uint32_t i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {  // other SMs wrote them; 4 loads in flight
+        uint64_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = i0 + j * blockDim.x < n ? ld_cg_u64(keys + i0 + j * blockDim.x) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j * blockDim.x < n) s_keys[i0 + j * blockDim.x] = v[j];
+    }
     if (threadIdx.x == 0) *s_counter = 0;
     __syncthreads();
-    const uint64_t kth = block_select_kth(s_keys, n, k, top_shift, s_hist, s_tmp);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t key = s_keys[i];
-        if (key >= kth) keys[atomicAdd(s_counter, 1u)] = key;
+    const uint64_t kth = block_select_kth(s_keys, n, k, s_hist, s_tmp);
+    const uint32_t lane = lane_id();
+    for (uint32_t i0 = threadIdx.x - lane; i0 < n; i0 += blockDim.x) {  // warp-uniform; one atomic per warp
+        const uint32_t i = i0 + lane;
+        const uint64_t key = i < n ? s_keys[i] : 0ull;
+        const bool keep = i < n && key >= kth;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        uint32_t base = 0;
+        if (lane == 0 && bal) base = atomicAdd(s_counter, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) keys[base + __popc(bal & lanemask_lt())] = key;
     }
     __syncthreads();
     return kth;

@@ -111,8 +111,9 @@ int di_serialize_dev(const uint64_t *d_term_offsets, const uint32_t *d_docids, c
  */
 typedef struct di_index_params {
     uint32_t tile_docs;      /* documents per tile: power of two in [256, 32768]; 0 = default (16384) */
-    uint32_t dense_ratio;    /* a (term, tile) segment with n postings is stored as a dense u16 array
-                                when n * dense_ratio >= tile_docs; 0 = default (4); 0xFFFFFFFF = never */
+    uint32_t dense_ratio;    /* a (term, tile) segment with n postings is stored as a dense array (one byte per
+                                document of the tile) when n * dense_ratio >= tile_docs; 0 = default (8);
+                                0xFFFFFFFF = never */
     uint32_t cand_slack;     /* per-query candidate slots kept between tiles; 0 = default (max(2k, 256)) */
     uint32_t reserved;
 } di_index_params;

@@ -234,6 +234,47 @@ def test_duplicate_postings_and_hidden_zeros():
         assert d[2, :c[2]].tolist() == want[0][0, :want[2][0]].tolist()
 
 
+@pytest.mark.parametrize("tile_docs,cand_slack", [(0, 0), (1024, 0), (512, 40)])
+def test_threshold_seeds_keep_results_exact(tile_docs, cand_slack):
+    """Frequent terms (df >= 4096) get a per-term impact table and every query starts from a proven lower
+    bound on its k-th best score (build.cuh, threshold seeds). Tiny vocabulary = every term is frequent and the
+    first tiles flood the candidate lists; results must still equal exhaustive scoring for every k."""
+    n_docs, V = 30_000, 60
+    x = quantized_csr(n_docs, V, 30, 61)
+    index = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], tile_docs=tile_docs, cand_slack=cand_slack)
+    queries = syn.make_queries(70, vocab_size=V, seed=62)
+    queries[0] = [int(np.argmax(np.diff(x["toff"].astype(np.int64))))]          # the hottest term alone
+    queries[1] = queries[0] * 3                                                  # ... three times
+    queries[2] = []
+    for k in (1, 50, 1000, 4500, n_docs):
+        assert_same_results(index.search(queries, k),
+                            oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], n_docs, queries, k), f"k={k}")
+    one = [queries[5]]                                                           # a single query runs in tile lanes
+    assert_same_results(index.search(one, 300), oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], n_docs, one, 300), "lanes")
+    index.close()
+
+
+def test_duplicate_document_in_a_frequent_list_gets_no_seed():
+    """k postings with impact >= v prove k DOCUMENTS only if no document is listed twice. Term 0 lists
+    document 5 twice with impact 200 and 5000 other documents with impact 1: the 2nd best score is 1, not 200."""
+    n = 5001
+    others = np.array([d for d in range(n) if d != 5], dtype=np.uint32)
+    toff = np.array([0, n + 1], dtype=np.uint64)
+    docs = np.concatenate([np.array([5, 5], dtype=np.uint32), others])
+    vals = np.concatenate([np.array([200, 200], dtype=np.uint8), np.ones(n - 1, dtype=np.uint8)])
+    index = engine.DeviceIndex.from_csr(toff, docs, vals, tile_docs=1024)
+    for k in (1, 2, 3, 100):
+        got = index.search([[0]], k)
+        assert_same_results(got, oracle.score_topk_csr(toff, docs, vals, n, [[0]], k), f"k={k}")
+    d, s, c = index.search([[0]], 3)
+    assert d[0, :3].tolist() == [5, 0, 1] and s[0, :3].tolist() == [400, 1, 1]
+    # without the duplicate the bound is used and must be just as exact
+    toff2 = np.array([0, n], dtype=np.uint64)
+    index2 = engine.DeviceIndex.from_csr(toff2, docs[1:], vals[1:], tile_docs=1024)
+    d, s, c = index2.search([[0]], 3)
+    assert d[0, :3].tolist() == [5, 0, 1] and s[0, :3].tolist() == [200, 1, 1]
+
+
 def test_shards_and_merge_equal_single_index():
     """K5: docid-range shards searched separately + merged == one index (single GPU, 3 shards)."""
     torch = pytest.importorskip("torch")
