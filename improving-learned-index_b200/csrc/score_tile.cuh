@@ -140,11 +140,10 @@ __device__ __forceinline__ void add_bytes8(uint4 &a, uint32_t lo, uint32_t hi)
     a.w += __byte_perm(hi, 0, 0x4342);
 }
 
-template <int NB, bool INIT>
-__device__ __forceinline__ void dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
-                                             const uint4 *p3, uint32_t units)
+// FULL: units is a multiple of the step (U * threads), so no load or store needs a bounds predicate
+template <int NB, bool INIT, bool FULL>
+__device__ __forceinline__ void dense_steps16(uint4 *s_acc4, const uint4 *const (&ptr)[4], uint32_t units)
 {
-    const uint4 *ptr[4] = {p0, p1, p2, p3};
     // U units per step so that about 8 independent 128-bit loads are in flight per thread whatever
     // the number of dense terms (a work item is latency-bound: few CTAs per SM, L2-resident postings)
     constexpr int U = NB <= 1 ? 8 : (NB == 2 ? 4 : 2);
@@ -154,12 +153,13 @@ __device__ __forceinline__ void dense_pass16(uint4 *s_acc4, const uint4 *p0, con
         for (int s = 0; s < U; ++s) {
             const uint32_t g = g0 + s * kScoreThreads;
 #pragma unroll
-            for (int u = 0; u < NB; ++u) v[s][u] = g < units ? ldg_stream_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < NB; ++u)
+                v[s][u] = (FULL || g < units) ? ldg_stream_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int s = 0; s < U; ++s) {
             const uint32_t g = g0 + s * kScoreThreads;
-            if (g < units) {
+            if (FULL || g < units) {
                 uint4 a = INIT ? make_uint4(0, 0, 0, 0) : s_acc4[g];
                 uint4 b = INIT ? make_uint4(0, 0, 0, 0) : s_acc4[g + units];
 #pragma unroll
@@ -172,6 +172,16 @@ __device__ __forceinline__ void dense_pass16(uint4 *s_acc4, const uint4 *p0, con
             }
         }
     }
+}
+
+template <int NB, bool INIT>
+__device__ __forceinline__ void dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
+                                             const uint4 *p3, uint32_t units)
+{
+    const uint4 *const ptr[4] = {p0, p1, p2, p3};
+    // tiles of >= 16 K documents (the default) have only full steps; INIT = false is the rare fifth dense term
+    if (INIT && units % (8 * kScoreThreads) == 0) dense_steps16<NB, INIT, true>(s_acc4, ptr, units);
+    else dense_steps16<NB, INIT, false>(s_acc4, ptr, units);
 }
 
 template <bool INIT>
