@@ -356,6 +356,34 @@ def run_b200(args):
         if world == 1 and args.cpu_sample > 0:
             out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(
                 args, toff, docids, vals, queries, index, torch)
+    if world > 1 and args.verify_sharded:
+        # every rank's merged result vs ONE index over all documents built on rank 0's GPU (itself checked against
+        # the oracle in the 1-GPU run): the sharded path must be bit-identical
+        m_keys, m_counts = searcher.search_tensors(d_flat, d_offs, Q, max_len, k)
+        m_keys, m_counts = m_keys.clone(), m_counts.clone()
+        same = None
+        if rank == 0:
+            t_all, v_all, o_all = build_shard_arrays(0, N, N, V, args.draws, torch, dev, quantize_fn)
+            P_all = t_all.numel()
+            toff_a = torch.empty(V + 1, dtype=torch.int64, device=dev)
+            docs_a = torch.empty(P_all, dtype=torch.int32, device=dev)
+            vals_a = torch.empty(P_all, dtype=torch.uint8, device=dev)
+            _native.check(L.di_invert_dev(t_all.data_ptr(), v_all.data_ptr(), o_all.data_ptr(), N, V, P_all,
+                                          toff_a.data_ptr(), docs_a.data_ptr(), vals_a.data_ptr(), stream))
+            del t_all, v_all, o_all
+            whole = engine.DeviceIndex.from_csr_device(toff_a, docs_a, vals_a, V, P_all, doc_lo=0, doc_hi=N)
+            w_keys = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+            w_counts = torch.zeros(Q, dtype=torch.int32, device=dev)
+            whole.search_device(d_flat, d_offs, Q, max_len, k, w_keys, w_counts, stream)
+            torch.cuda.synchronize()
+            valid = torch.arange(k, device=dev)[None, :] < w_counts[:, None]
+            same = bool(torch.equal(w_counts, m_counts) and torch.equal(w_keys[valid], m_keys[valid]))
+            whole.close()
+            out["sharded_parity"] = {"queries_checked": Q, "bit_exact": same,
+                                     "against": "one index over all documents on rank 0 (same kernels, 1 shard)"}
+        dist.barrier()
+        if same is False:
+            raise SystemExit("PARITY FAILURE: the sharded result differs from the single-index result")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -458,6 +486,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="queries per search call (0 = all queries at once)")
     ap.add_argument("--cand-slack", type=int, default=0, help="candidate slots kept per query between tiles (0 = default)")
     ap.add_argument("--verify-build", action="store_true", help="compare the full GPU inversion with the CPU oracle (~1 min)")
+    ap.add_argument("--verify-sharded", action="store_true",
+                    help="N > 1: compare the merged result of every query with a single index built on rank 0")
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
     ap.add_argument("--ref-queries-per-step", type=int, default=32)
     args = ap.parse_args()

@@ -8,12 +8,14 @@ postings), then the per-shard best keys — (score << 32 | ~docid), sorted — a
 (NCCL over NVLink on GPUs; gloo in the CPU tests) and merged by K5 into the global top-k, which
 is identical to the single-GPU result because the key order is total.
 
-Two rounds keep it exact AND cheap. Round 1 asks every shard for only k_in < k keys (about
-1.25 k / G + 64: with G shards each holds ~k/G of the global top-k), which cuts the per-shard selection
-work and the gathered bytes by ~G/1.25. The merge proves the result complete per query: a shard that
-filled its row could only hide keys below its last returned key, so the merged top-k is exact iff that
-key is <= the merged k-th (merge_check_kernel). The (rare, e.g. docid-clustered relevance) queries that
-fail the proof are re-run in round 2 with full rows of k keys.
+Two gathers keep it exact AND cheap. Every shard selects its own top-k once, but only the first k_in < k
+columns of its (sorted) rows are gathered at first (about 1.25 k / G + 64: with G shards each holds ~k/G of
+the global top-k), which cuts the gathered bytes and the merge work by ~G/1.25. The merge proves the result
+complete per query: a shard that filled its k_in columns could only hide keys below the last one it sent, so
+the merged top-k is exact iff that key is <= the merged k-th (merge_check_kernel). For the queries that fail
+the proof (with docid-ordered ties the boundary tie group of a short query sits in the lowest docid range,
+so one shard holds most of the top-k) the full rows — already computed — are gathered and merged; nothing
+is searched twice.
 
 The collective and the two compute steps are injected, so the plumbing (ranges, tensor layout of
 the gather, count handling, the two-round protocol) is testable on CPU with world_size 2 while the
@@ -52,7 +54,8 @@ def unpack_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 
 
 class ShardedSearcher:
-    """search(): local best keys on this rank's shard -> all_gather -> merge (+ proof, + round 2).
+    """search(): local best keys on this rank's shard -> all_gather of the first columns -> merge + proof
+    (-> all_gather of the full rows of the unproven queries -> merge).
     Call on every rank with the same queries; every rank gets the global result.
 
     local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, out_keys, out_counts[, theta_init=]) fills this
@@ -74,7 +77,7 @@ class ShardedSearcher:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._buffers = {}
         self.rows_per_shard = rows_per_shard   # optional override of shard_k: k -> keys per shard in round 1
-        self.round2_queries = 0          # how many queries the last search had to re-run
+        self.round2_queries = 0          # how many queries of the last search needed their full rows gathered
 
     @classmethod
     def for_device_index(cls, index: "engine.DeviceIndex", device, group=None) -> "ShardedSearcher":
@@ -95,58 +98,62 @@ class ShardedSearcher:
             self._buffers[key] = self.torch.zeros(shape, dtype=dtype, device=self.device)
         return self._buffers[key]
 
-    def _round(self, d_q_terms, d_q_offsets, n_queries, max_len, k_in, k, tag, theta_init=None):
-        """One gather + merge with rows of k_in keys. Returns (keys [Q,k], counts [Q], incomplete [Q])."""
+    def _flat(self, name, numel, dtype):
+        """Flat scratch buffer of at least `numel` elements (grown geometrically, so batches of varying size
+        do not accumulate one buffer per size)."""
+        buf = self._buffers.get(name)
+        if buf is None or buf.numel() < numel or buf.dtype != dtype:
+            buf = self.torch.zeros(max(int(numel * 1.5), 1), dtype=dtype, device=self.device)
+            self._buffers[name] = buf
+        return buf[:numel]
+
+    def _gather_merge(self, keys, counts, n_queries, k_in, k, tag, prove):
+        """All-gather rows of k_in keys (keys [Q, k_in] contiguous, counts [Q]) and merge them into the global
+        top-k. Returns (keys [Q, k], counts [Q], incomplete [Q] or None)."""
         torch, dist = self.torch, self.dist
-        keys = self._buf(tag + "keys", (n_queries, k_in), torch.int64)
-        counts = self._buf(tag + "counts", (n_queries,), torch.int32)
-        if theta_init is None:
-            self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k_in, keys, counts)
-        else:
-            self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k_in, keys, counts, theta_init=theta_init)
-        g_keys = self._buf(tag + "g_keys", (self.world, n_queries, k_in), torch.int64)
-        g_counts = self._buf(tag + "g_counts", (self.world, n_queries), torch.int32)
+        g_keys = self._flat(tag + "g_keys", self.world * n_queries * k_in, torch.int64)
+        g_counts = self._flat(tag + "g_counts", self.world * n_queries, torch.int32)
         # concatenated-along-dim-0 form: accepted by both the NCCL and the gloo backend
         dist.all_gather_into_tensor(g_keys.view(self.world * n_queries, k_in), keys, group=self.group)
-        dist.all_gather_into_tensor(g_counts.view(self.world * n_queries), counts, group=self.group)
-        out_keys = self._buf(tag + "out_keys", (n_queries, k), torch.int64)
-        out_counts = self._buf(tag + "out_counts", (n_queries,), torch.int32)
-        incomplete = self._buf(tag + "incomplete", (n_queries,), torch.int32)
-        self.merge(g_keys, g_counts, self.world, n_queries, k_in, k, out_keys, out_counts, incomplete)
-        return out_keys, out_counts, incomplete
+        dist.all_gather_into_tensor(g_counts, counts, group=self.group)
+        out_keys = self._flat(tag + "out_keys", n_queries * k, torch.int64).view(n_queries, k)
+        out_counts = self._flat(tag + "out_counts", n_queries, torch.int32)
+        incomplete = self._flat(tag + "incomplete", n_queries, torch.int32)
+        self.merge(g_keys.view(self.world, n_queries, k_in), g_counts.view(self.world, n_queries), self.world, n_queries,
+                   k_in, k, out_keys, out_counts, incomplete)
+        return out_keys, out_counts, incomplete if prove else None
 
     def search_tensors(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
         """Device-level entry: returns (keys [Q,k] int64, counts [Q] int32) tensors holding the GLOBAL top-k.
         The returned tensors are owned by the searcher and overwritten by the next call."""
         torch = self.torch
         self.round2_queries = 0
+        keys = self._flat("keys", n_queries * k, torch.int64).view(n_queries, k)
+        counts = self._flat("counts", n_queries, torch.int32)
+        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)   # this shard's sorted top-k
         if self.world == 1:
-            keys = self._buf("keys", (n_queries, k), torch.int64)
-            counts = self._buf("counts", (n_queries,), torch.int32)
-            self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)
             return keys, counts
         k_in = min(k, self.rows_per_shard(k)) if self.rows_per_shard else shard_k(k, self.world)
-        out_keys, out_counts, incomplete = self._round(d_q_terms, d_q_offsets, n_queries, max_len, k_in, k, "r1_")
-        if k_in < k:
-            # the flags derive from gathered data, identical on every rank: all ranks take the same branch
-            redo = torch.nonzero(incomplete).flatten()
-            if redo.numel():
-                self.round2_queries = int(redo.numel())
-                offs = d_q_offsets.to(torch.int64)
-                lens = (offs[1:] - offs[:-1])[redo]
-                new_offs = torch.zeros(redo.numel() + 1, dtype=torch.int64, device=self.device)
-                torch.cumsum(lens, 0, out=new_offs[1:])
-                idx = torch.repeat_interleave(offs[:-1][redo] - new_offs[:-1], lens) + torch.arange(
-                    int(new_offs[-1]), device=self.device)
-                sub_terms = d_q_terms[idx] if idx.numel() else d_q_terms[:1]
-                # round 1 already proves a lower bound of each flagged query's final k-th key: the k-th key of
-                # its (incomplete) merge, all of whose keys exist. Round 2 only has to surface documents above it.
-                full = out_counts[redo] == k
-                theta = torch.where(full, out_keys[redo, k - 1], torch.zeros_like(out_keys[redo, k - 1])).contiguous()
-                k2, c2, _ = self._round(sub_terms.contiguous(), new_offs, int(redo.numel()), max_len, k, k, "r2_",
-                                        theta_init=theta)
-                out_keys[redo] = k2
-                out_counts[redo] = c2
+        if k_in == k:
+            out_keys, out_counts, _ = self._gather_merge(keys, counts, n_queries, k, k, "r1_", prove=False)
+            return out_keys, out_counts
+        head = self._flat("head", n_queries * k_in, torch.int64).view(n_queries, k_in)
+        head.copy_(keys[:, :k_in])
+        head_counts = self._flat("head_counts", n_queries, torch.int32)
+        torch.clamp(counts, max=k_in, out=head_counts)
+        out_keys, out_counts, incomplete = self._gather_merge(head, head_counts, n_queries, k_in, k, "r1_", prove=True)
+        # the flags derive from gathered data, identical on every rank: all ranks take the same branch
+        redo = torch.nonzero(incomplete).flatten()
+        if redo.numel():
+            n_redo = int(redo.numel())
+            self.round2_queries = n_redo
+            rows = self._flat("rows", n_redo * k, torch.int64).view(n_redo, k)
+            torch.index_select(keys, 0, redo, out=rows)
+            row_counts = self._flat("row_counts", n_redo, torch.int32)
+            torch.index_select(counts, 0, redo, out=row_counts)
+            k2, c2, _ = self._gather_merge(rows, row_counts, n_redo, k, k, "r2_", prove=False)
+            out_keys[redo] = k2
+            out_counts[redo] = c2
         return out_keys, out_counts
 
     def search(self, queries: Sequence[Sequence[int]], k: int):
