@@ -35,16 +35,24 @@ __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *
     if (n <= smem_keys) {  // usual case: everything happens in shared memory after one coalesced read
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = cand[i];
         __syncthreads();
+        uint64_t *keys = s_keys;
         if (n > k) {
             const uint64_t kth = block_select_kth(s_keys, n, k, s_hist, s_tmp);
-            n = block_compact_ge(s_keys, n, kth, s_scan);
+            uint32_t k_pow2 = 1;
+            while (k_pow2 < k) k_pow2 <<= 1;
+            if (n + k_pow2 <= smem_keys) {  // room behind the list: pack the k survivors there (any order, sorted next)
+                keys = s_keys + n;
+                n = block_compact_ge_unordered(s_keys, n, kth, keys, s_tmp);
+            } else {
+                n = block_compact_ge(s_keys, n, kth, s_scan);
+            }
         }
         uint32_t np2 = 1;
         while (np2 < n) np2 <<= 1;
-        for (uint32_t i = n + threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = 0ull;
+        for (uint32_t i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
         __syncthreads();
-        bitonic_sort_desc(s_keys, np2);
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = s_keys[i];
+        bitonic_sort_desc(keys, np2);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = keys[i];
         if (threadIdx.x == 0) out_counts[q] = n;
         return;
     }

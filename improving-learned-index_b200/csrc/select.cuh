@@ -162,25 +162,53 @@ __device__ __forceinline__ uint64_t block_cut_to_k_staged(uint64_t *keys, uint32
     return kth;
 }
 
+// In-place bitonic sort, descending, n_pow2 keys (shared or global memory). Thread t of a stage handles the pair
+// (i, i | j) where i is t with a zero inserted at bit log2(j): every iteration does a compare-exchange, and
+// the iterations of a thread are independent (unrolled, loads first).
 template <typename Ptr>
 __device__ void bitonic_sort_desc(Ptr a, uint32_t n_pow2)
 {
+    const uint32_t half = n_pow2 >> 1;
     for (uint32_t k2 = 2; k2 <= n_pow2; k2 <<= 1) {
         for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-                const uint32_t ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t x = a[i], y = a[ixj];
-                    const bool desc_block = (i & k2) == 0;
-                    if (desc_block ? (x < y) : (x > y)) {
-                        a[i] = y;
-                        a[ixj] = x;
-                    }
+#pragma unroll 4
+            for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
+                const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+                const uint32_t ixj = i | j;
+                const uint64_t x = a[i], y = a[ixj];
+                const bool desc_block = (i & k2) == 0;
+                if (desc_block ? (x < y) : (x > y)) {
+                    a[i] = y;
+                    a[ixj] = x;
                 }
             }
             __syncthreads();
         }
     }
+}
+
+// keys >= theta of src[0, n) -> dst[0, ...) in arbitrary order (dst must not overlap src); one shared-memory
+// atomic per warp. Returns how many were kept. s_counter: one shared word.
+__device__ __forceinline__ uint32_t block_compact_ge_unordered(const uint64_t *src, uint32_t n, uint64_t theta, uint64_t *dst,
+                                                               uint32_t *s_counter)
+{
+    if (threadIdx.x == 0) *s_counter = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    for (uint32_t i0 = threadIdx.x - lane; i0 < n; i0 += blockDim.x) {  // warp-uniform
+        const uint32_t i = i0 + lane;
+        const uint64_t key = i < n ? src[i] : 0ull;
+        const bool keep = i < n && key >= theta;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        uint32_t base = 0;
+        if (lane == 0 && bal) base = atomicAdd(s_counter, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) dst[base + __popc(bal & lanemask_lt())] = key;
+    }
+    __syncthreads();
+    const uint32_t kept = *s_counter;
+    __syncthreads();
+    return kept;
 }
 
 // largest bin b such that hist[b] + hist[b+1] + ... >= k, or 0 when the whole histogram holds fewer
