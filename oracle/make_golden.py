@@ -13,6 +13,8 @@ What is recorded (all produced by unmodified reference functions):
   zeros.json      collection holding literal 0 impacts: reader hides them (inverted_index.py:50-51)
   sparse.json     SparseSearch.search (nano_beir_evaluator.py:103-137) with a replaying fake model
   metrics.json    Metrics.evaluate sums (metrics.py:26-57) on a small run file + qrels
+  maxp.json       aggregate_run.main (aggregate_run.py:5-58): passage run file -> MaxP document run file
+                  (``python oracle/make_golden.py --only maxp`` regenerates just this one)
 """
 from __future__ import annotations
 
@@ -95,10 +97,51 @@ def build_with_reference(ref, workdir: Path, lines, max_val=None, prequantized=F
     }
 
 
+def make_maxp(tmp: Path):
+    """Run the reference's MaxP aggregation CLI (aggregate_run.py:5-58) on a small passage run file."""
+    spec = importlib.util.spec_from_file_location("ref_aggregate_run", tmp / "src/deep_impact/aggregate_run.py")
+    agg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(agg)
+    wdir = tmp / "work" / "maxp"
+    wdir.mkdir(parents=True, exist_ok=True)
+    rng = np.random.default_rng(11)
+    # passage ids "doc<d>#<p>", a few documents without '#', one id with two '#'
+    mapping = [f"doc{d}#{p}" for d in range(12) for p in range(3)] + ["solo1", "solo2", "a#b#c"]
+    rng.shuffle(mapping)
+    run_rows = []
+    for qid in ("10", "9", "100", "7"):
+        pids = rng.choice(len(mapping) + 3, size=25, replace=False)          # some pids are not in the mapping
+        scores = np.sort(rng.integers(0, 400, size=25))[::-1]
+        for rank, (pid, sc) in enumerate(zip(pids.tolist(), scores.tolist()), start=1):
+            run_rows.append(f"{qid}\t{pid}\t{rank}\t{sc}")
+    run_rows.insert(5, "short\trow")                                            # skipped: fewer than 4 columns
+    run_rows.append("7\t3\t26\t-4.5")                                           # a negative score never wins
+    run_rows.append("11\t2\t1\t0")                                              # a query whose only score is 0
+    (wdir / "run.tsv").write_text('\n'.join(run_rows) + '\n', encoding='utf-8')
+    (wdir / "mapping.txt").write_text('\n'.join(mapping) + '\n', encoding='utf-8')
+    outs = {}
+    for top_k in (1000, 3):
+        argv = sys.argv
+        sys.argv = ["aggregate_run", "--run_file", str(wdir / "run.tsv"), "--mapping", str(wdir / "mapping.txt"),
+                    "--output", str(wdir / f"out{top_k}.tsv"), "--top_k", str(top_k)]
+        try:
+            agg.main()
+        finally:
+            sys.argv = argv
+        outs[str(top_k)] = (wdir / f"out{top_k}.tsv").read_text(encoding='utf-8').split('\n')[:-1]
+    json.dump({"run": run_rows, "mapping": mapping, "out": outs}, open(GOLDEN / "maxp.json", "w"), indent=1)
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     syn = _load_pkg_synthetic()
     tmp = Path(tempfile.mkdtemp(prefix="di_ref_"))
+    if sys.argv[1:3] == ["--only", "maxp"]:
+        shutil.copytree(REFERENCE / "src", tmp / "src")
+        make_maxp(tmp)
+        shutil.rmtree(tmp)
+        print("wrote", GOLDEN / "maxp.json")
+        return
     ref = _import_reference(tmp)
     quant, create, inv, coll, nano, metrics = ref
     work = tmp / "work"
@@ -249,6 +292,7 @@ def main():
         "recall": {str(d): round(m.recall_sums[d] / n_q, 3) for d in m.recall_sums},
     }, open(GOLDEN / "metrics.json", "w"), indent=1)
 
+    make_maxp(tmp)
     shutil.rmtree(tmp)
     print("golden fixtures written to", GOLDEN)
     for f in sorted(GOLDEN.iterdir()):

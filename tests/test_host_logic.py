@@ -177,3 +177,18 @@ def test_fast_parser_errors_and_fallback(tmp_path):
     c = C.parse_bytes("x: 1, đ: 2\ny: 3\nz: 4\n".encode(), C.SEQUENCE)
     c.write_quantized(np.array([5, 0, -1, 9], dtype=np.int32), tmp_path / "out")
     assert (tmp_path / "out").read_text(encoding="utf-8") == "x: 5\n\nz: 9\n"
+
+
+def test_maxp_aggregation_matches_reference_output(golden, tmp_path):
+    """aggregate_run (MaxP, aggregate_run.py:5-58): same rows as the reference script wrote for the same files."""
+    from improving_learned_index_b200.aggregate_run import aggregate_run
+    g = golden("maxp")
+    (tmp_path / "run.tsv").write_text('\n'.join(g["run"]) + '\n', encoding='utf-8')
+    (tmp_path / "mapping.txt").write_text('\n'.join(g["mapping"]) + '\n', encoding='utf-8')
+    for top_k, want in g["out"].items():
+        n = aggregate_run(tmp_path / "run.tsv", tmp_path / "mapping.txt", tmp_path / "out.tsv", int(top_k))
+        got = (tmp_path / "out.tsv").read_text(encoding='utf-8').split('\n')[:-1]
+        assert got == want and n == len(want)
+    (tmp_path / "mixed.tsv").write_text("a\t0\t1\t2.0\n7\t0\t1\t1.0\n")
+    with pytest.raises(TypeError):            # aggregate_run.py:52 cannot order 'a' against 7 either
+        aggregate_run(tmp_path / "mixed.tsv", tmp_path / "mapping.txt", tmp_path / "o2.tsv")
