@@ -1,13 +1,10 @@
 // search.cuh — K4 (final exact select + sort of each query's candidates) and K5 (cross-shard
 // merge). K3 and the tile-local half of K4 live in score_tile.cuh.
 //
-// Launch structure of a search: one score_tile_kernel launch per document tile, grid = queries.
-// Launching tile by tile keeps every CTA of a launch on the SAME tile, so a tile's postings are
-// read from HBM once and then served from L2 to all queries of the batch; and it makes each
-// query's candidate list single-writer (exactly one CTA per query per launch), so the running
-// threshold needs no inter-CTA protocol. finalize_topk_kernel then cuts every list to the k best
-// keys and sorts them (score descending, docid ascending) — replacing heapq.nlargest of
-// inverted_index.py:62 / nano_beir_evaluator.py:128-131.
+// A search = seed_theta_kernel (proven starting thresholds) -> query_order_kernel -> ONE
+// score_persistent_kernel launch over all (query, tile) work items (score_tile.cuh) -> finalize_topk_kernel,
+// which cuts every candidate list to the k best keys and sorts them (score descending, docid ascending)
+// — replacing heapq.nlargest of inverted_index.py:62 / nano_beir_evaluator.py:128-131.
 #pragma once
 
 #include "score_tile.cuh"
