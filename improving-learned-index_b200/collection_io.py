@@ -3,8 +3,10 @@
 The reference parses "term: score, term: score" lines with Python string methods
 (deep_impact_collection.py:21-25, quantize.py:21-22, 41-43, create.py:19-35). At MS MARCO scale that is
 ~10^9 split() calls, so the parsing (host work, no GPU involved) is done in C++ with the same
-tokenisation rules. Inputs the fast parser does not model (numeric literals such as "1_000") fall back to
-`parse_python`, which is the reference's own logic line by line.
+tokenisation rules, on all host threads (the file is cut into one piece per thread after a newline; the
+result does not depend on the number of threads). Inputs the fast parser does not model (numeric literals
+such as "1_000", bytes that are not UTF-8) fall back to `parse_python`, which is the reference's own logic
+line by line.
 """
 from __future__ import annotations
 
@@ -137,10 +139,10 @@ def _universal_lines(text: str):
 
 def parse_file(path: Union[str, Path], mode: int) -> ParsedCollection:
     data = Path(path).read_bytes()
-    text = data.decode('utf-8')          # UnicodeDecodeError for invalid input, as when the reference reads the file
     try:
-        return parse_bytes(data, mode)
+        return parse_bytes(data, mode)   # validates UTF-8 itself (all host threads) and defers if it is not
     except N.NativeError as e:
         if e.code != N.ERR_UNSUPPORTED:
             raise
+    text = data.decode('utf-8')          # UnicodeDecodeError for invalid input, as when the reference reads the file
     return parse_python(text, mode)

@@ -25,6 +25,7 @@
 #include <new>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -138,16 +139,53 @@ struct di_collection {
     std::vector<uint64_t> vocab_offsets{0};
 };
 
-extern "C" int di_collection_parse(const char *text, uint64_t n_bytes, int mode, di_collection_t **out)
+namespace {
+
+// Strict UTF-8, as CPython's decoder accepts it (no overlong forms, no surrogates, nothing above U+10FFFF)
+bool valid_utf8(std::string_view s)
 {
-    if (!out || (!text && n_bytes)) return fail(DI_ERR_ARG, "line %llu: %s", 0, "NULL argument");
-    *out = nullptr;
-    if (mode != DI_PARSE_DICT && mode != DI_PARSE_SEQUENCE) return fail(DI_ERR_ARG, "line %llu: %s", 0, "bad mode");
-    di_collection *c = new (std::nothrow) di_collection();
-    if (!c) return fail(DI_ERR_NOMEM, "line %llu: %s", 0, "out of memory");
-    c->mode = mode;
-    // term interning: open-addressing table of temp ids, keys are views into `text` (alive during this call)
-    std::vector<std::string_view> terms;   // temp id -> term
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(s.data()), *end = p + s.size();
+    while (p < end) {
+        if (end - p >= 8) {  // ASCII run, 8 bytes at a time
+            uint64_t w;
+            memcpy(&w, p, 8);
+            if (!(w & 0x8080808080808080ull)) { p += 8; continue; }
+        }
+        const unsigned char c = *p;
+        if (c < 0x80) { ++p; continue; }
+        auto cont = [&](int i, unsigned char lo, unsigned char hi) { return p + i < end && p[i] >= lo && p[i] <= hi; };
+        if (c >= 0xC2 && c <= 0xDF) { if (!cont(1, 0x80, 0xBF)) return false; p += 2; }
+        else if (c == 0xE0) { if (!cont(1, 0xA0, 0xBF) || !cont(2, 0x80, 0xBF)) return false; p += 3; }
+        else if ((c >= 0xE1 && c <= 0xEC) || c == 0xEE || c == 0xEF) { if (!cont(1, 0x80, 0xBF) || !cont(2, 0x80, 0xBF)) return false; p += 3; }
+        else if (c == 0xED) { if (!cont(1, 0x80, 0x9F) || !cont(2, 0x80, 0xBF)) return false; p += 3; }
+        else if (c == 0xF0) { if (!cont(1, 0x90, 0xBF) || !cont(2, 0x80, 0xBF) || !cont(3, 0x80, 0xBF)) return false; p += 4; }
+        else if (c >= 0xF1 && c <= 0xF3) { if (!cont(1, 0x80, 0xBF) || !cont(2, 0x80, 0xBF) || !cont(3, 0x80, 0xBF)) return false; p += 4; }
+        else if (c == 0xF4) { if (!cont(1, 0x80, 0x8F) || !cont(2, 0x80, 0xBF) || !cont(3, 0x80, 0xBF)) return false; p += 4; }
+        else return false;
+    }
+    return true;
+}
+
+// One contiguous piece of the file (cut after a '\n'), parsed by one thread: documents, postings with
+// piece-local term ids, and the piece's own term table. Pieces share nothing until the merge.
+struct Piece {
+    std::string_view text;
+    std::vector<uint64_t> doc_ends;          // postings of the piece before the end of each document
+    std::vector<uint32_t> term_ids;          // piece-local ids, remapped to final ranks by the merge
+    std::vector<double> scores;
+    std::vector<std::string_view> terms;     // piece-local id -> term (views into the file text)
+    uint64_t lines = 0;                      // lines consumed (the failing line included)
+    int rc = DI_OK;
+    const char *what = "";
+    bool bad_utf8 = false;
+};
+
+void parse_piece(Piece &pc, int mode)
+{
+    pc.bad_utf8 = !valid_utf8(pc.text);
+    if (pc.bad_utf8) return;
+    // term interning: open-addressing table of local ids, keys are views into the text
+    std::vector<std::string_view> &terms = pc.terms;
     std::vector<uint32_t> table(1u << 16, 0xFFFFFFFFu);
     std::vector<uint64_t> hashes;
     auto hash_of = [](std::string_view t) {
@@ -181,63 +219,143 @@ extern "C" int di_collection_parse(const char *text, uint64_t n_bytes, int mode,
             if (hashes[id] == h && terms[id] == t) return id;
         }
     };
+    auto stop = [&](int code, const char *what) { pc.rc = code; pc.what = what; };
     std::vector<uint64_t> seen_in_doc;     // DICT mode: 1 + index of the term's posting if seen in the current doc
-    uint64_t line_no = 0;
     size_t pos = 0;
-    int rc = DI_OK;
-    const std::string_view all(text ? text : "", (size_t)n_bytes);
-    while (pos < all.size() && rc == DI_OK) {
+    const std::string_view all = pc.text;
+    while (pos < all.size() && pc.rc == DI_OK) {
         size_t eol = pos;
         while (eol < all.size() && all[eol] != '\n' && all[eol] != '\r') ++eol;
         const std::string_view raw = all.substr(pos, eol - pos);
         pos = eol < all.size() ? eol + ((all[eol] == '\r' && eol + 1 < all.size() && all[eol + 1] == '\n') ? 2 : 1) : eol;
-        ++line_no;
+        ++pc.lines;
         const std::string_view line = strip(raw);
-        const size_t doc_begin = c->term_ids.size();
+        const size_t doc_begin = pc.term_ids.size();
         if (line.empty()) {
-            if (mode == DI_PARSE_SEQUENCE) { rc = fail(DI_ERR_FORMAT, "line %llu: %s", line_no, "not enough values to unpack (expected 2, got 1)"); break; }
-            c->doc_offsets.push_back(doc_begin);
+            if (mode == DI_PARSE_SEQUENCE) { stop(DI_ERR_FORMAT, "not enough values to unpack (expected 2, got 1)"); break; }
+            pc.doc_ends.push_back(doc_begin);
             continue;
         }
         size_t p = 0;
-        while (rc == DI_OK) {
+        while (pc.rc == DI_OK) {
             size_t sep = line.find(", ", p);
             std::string_view pair = line.substr(p, sep == std::string_view::npos ? std::string_view::npos : sep - p);
             if (mode == DI_PARSE_SEQUENCE) pair = strip(pair);
             const size_t colon = pair.find(": ");
-            if (colon == std::string_view::npos) { rc = fail(DI_ERR_FORMAT, "line %llu: %s", line_no, "not enough values to unpack (expected 2, got 1)"); break; }
-            if (pair.find(": ", colon + 2) != std::string_view::npos) { rc = fail(DI_ERR_FORMAT, "line %llu: %s", line_no, "too many values to unpack (expected 2)"); break; }
+            if (colon == std::string_view::npos) { stop(DI_ERR_FORMAT, "not enough values to unpack (expected 2, got 1)"); break; }
+            if (pair.find(": ", colon + 2) != std::string_view::npos) { stop(DI_ERR_FORMAT, "too many values to unpack (expected 2)"); break; }
             const std::string_view term = pair.substr(0, colon);
             double v = 0;
             const int fr = parse_float(pair.substr(colon + 2), &v);
-            if (fr == 1) { rc = fail(DI_ERR_FORMAT, "line %llu: %s", line_no, "could not convert string to float"); break; }
-            if (fr == 2) { rc = fail(DI_ERR_UNSUPPORTED, "line %llu: %s", line_no, "numeric literal outside the fast parser's grammar"); break; }
+            if (fr == 1) { stop(DI_ERR_FORMAT, "could not convert string to float"); break; }
+            if (fr == 2) { stop(DI_ERR_UNSUPPORTED, "numeric literal outside the fast parser's grammar"); break; }
             const uint32_t id = intern_term(term);
             bool replaced = false;
             if (mode == DI_PARSE_DICT) {  // dict: last value wins, first position kept
                 if (seen_in_doc.size() <= id) seen_in_doc.resize((size_t)id * 2 + 64, 0);
                 const uint64_t at = seen_in_doc[id];      // postings before doc_begin belong to earlier docs
-                if (at > doc_begin) { c->scores[at - 1] = v; replaced = true; }
-                else seen_in_doc[id] = c->term_ids.size() + 1;
+                if (at > doc_begin) { pc.scores[at - 1] = v; replaced = true; }
+                else seen_in_doc[id] = pc.term_ids.size() + 1;
             }
-            if (!replaced) { c->term_ids.push_back(id); c->scores.push_back(v); }
+            if (!replaced) { pc.term_ids.push_back(id); pc.scores.push_back(v); }
             if (sep == std::string_view::npos) break;
             p = sep + 2;
         }
-        c->doc_offsets.push_back(c->term_ids.size());
+        if (pc.rc == DI_OK) pc.doc_ends.push_back(pc.term_ids.size());
     }
-    if (rc != DI_OK) { delete c; return rc; }
-    // final ids: rank in sorted (bytewise == code point for UTF-8) order, as sorted(set(terms)) gives
-    std::vector<uint32_t> order(terms.size());
-    for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return terms[a] < terms[b]; });
-    std::vector<uint32_t> rank(terms.size());
-    for (uint32_t r = 0; r < order.size(); ++r) {
-        rank[order[r]] = r;
-        c->vocab_blob.append(terms[order[r]]);
-        c->vocab_offsets.push_back(c->vocab_blob.size());
+}
+
+unsigned parse_threads(uint64_t n_bytes)
+{
+    // DI_B200_PARSE_THREADS pins the number of pieces (tests cut tiny inputs into many pieces with it)
+    if (const char *e = getenv("DI_B200_PARSE_THREADS")) return (unsigned)std::min(256, std::max(1, atoi(e)));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint64_t by_size = std::max<uint64_t>(1, n_bytes >> 20);  // at least 1 MB of text per thread
+    return (unsigned)std::min<uint64_t>(std::min<uint64_t>(hw, 256), by_size);
+}
+
+template <typename F> void run_parallel(unsigned n, F &&body)
+{
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n; ++t) pool.emplace_back([&body, t] { body(t); });
+    body(0);
+    for (std::thread &t : pool) t.join();
+}
+
+}  // namespace
+
+// The file is cut into one piece per host thread (after a '\n'; a "\r\n" pair is never split, and a lone '\r'
+// still ends a line inside its piece), the pieces are parsed independently, and the merge gives every term
+// its rank in the sorted global vocabulary. The outcome — arrays, vocabulary, or the FIRST error of the file
+// with its line number — does not depend on the number of threads.
+extern "C" int di_collection_parse(const char *text, uint64_t n_bytes, int mode, di_collection_t **out)
+{
+    if (!out || (!text && n_bytes)) return fail(DI_ERR_ARG, "line %llu: %s", 0, "NULL argument");
+    *out = nullptr;
+    if (mode != DI_PARSE_DICT && mode != DI_PARSE_SEQUENCE) return fail(DI_ERR_ARG, "line %llu: %s", 0, "bad mode");
+    di_collection *c = new (std::nothrow) di_collection();
+    if (!c) return fail(DI_ERR_NOMEM, "line %llu: %s", 0, "out of memory");
+    c->mode = mode;
+    const std::string_view all(text ? text : "", (size_t)n_bytes);
+    const unsigned n_pieces = parse_threads(n_bytes);
+    std::vector<Piece> pieces(n_pieces);
+    size_t begin = 0;
+    for (unsigned i = 0; i < n_pieces; ++i) {
+        size_t end = all.size();
+        if (i + 1 < n_pieces) {
+            end = std::max(begin, (size_t)((uint64_t)all.size() * (i + 1) / n_pieces));
+            const size_t nl = all.find('\n', end);
+            end = nl == std::string_view::npos ? all.size() : nl + 1;
+        }
+        pieces[i].text = all.substr(begin, end - begin);
+        begin = end;
     }
-    for (uint32_t &t : c->term_ids) t = rank[t];
+    try {
+        run_parallel(n_pieces, [&](unsigned i) { parse_piece(pieces[i], mode); });
+        // invalid UTF-8 anywhere: the caller's decode raises, whatever else the file holds
+        for (const Piece &pc : pieces)
+            if (pc.bad_utf8) { delete c; return fail(DI_ERR_UNSUPPORTED, "line %llu: %s", 0, "input is not valid UTF-8"); }
+        uint64_t lines_before = 0;
+        for (const Piece &pc : pieces) {  // the first error in file order, with its global line number
+            if (pc.rc != DI_OK) { delete c; return fail(pc.rc, "line %llu: %s", lines_before + pc.lines, pc.what); }
+            lines_before += pc.lines;
+        }
+        // global vocabulary: sorted (bytewise == code point order for UTF-8) union of the pieces' terms,
+        // as sorted(set(terms)) gives; final id = rank
+        std::vector<std::string_view> vocab;
+        for (const Piece &pc : pieces) vocab.insert(vocab.end(), pc.terms.begin(), pc.terms.end());
+        std::sort(vocab.begin(), vocab.end());
+        vocab.erase(std::unique(vocab.begin(), vocab.end()), vocab.end());
+        for (const std::string_view t : vocab) {
+            c->vocab_blob.append(t);
+            c->vocab_offsets.push_back(c->vocab_blob.size());
+        }
+        std::vector<uint64_t> post_base(n_pieces + 1, 0), doc_base(n_pieces + 1, 0);
+        for (unsigned i = 0; i < n_pieces; ++i) {
+            post_base[i + 1] = post_base[i] + pieces[i].term_ids.size();
+            doc_base[i + 1] = doc_base[i] + pieces[i].doc_ends.size();
+        }
+        c->term_ids.resize(post_base[n_pieces]);
+        c->scores.resize(post_base[n_pieces]);
+        c->doc_offsets.resize(doc_base[n_pieces] + 1);
+        c->doc_offsets[0] = 0;
+        run_parallel(n_pieces, [&](unsigned i) {
+            Piece &pc = pieces[i];
+            std::vector<uint32_t> rank(pc.terms.size());
+            for (size_t k = 0; k < pc.terms.size(); ++k)
+                rank[k] = (uint32_t)(std::lower_bound(vocab.begin(), vocab.end(), pc.terms[k]) - vocab.begin());
+            uint32_t *ids = c->term_ids.data() + post_base[i];
+            for (size_t k = 0; k < pc.term_ids.size(); ++k) ids[k] = rank[pc.term_ids[k]];
+            if (!pc.scores.empty()) memcpy(c->scores.data() + post_base[i], pc.scores.data(), pc.scores.size() * sizeof(double));
+            uint64_t *offs = c->doc_offsets.data() + doc_base[i] + 1;
+            for (size_t d = 0; d < pc.doc_ends.size(); ++d) offs[d] = post_base[i] + pc.doc_ends[d];
+            std::vector<uint32_t>().swap(pc.term_ids);
+            std::vector<double>().swap(pc.scores);
+        });
+    } catch (const std::bad_alloc &) {
+        delete c;
+        return fail(DI_ERR_NOMEM, "line %llu: %s", 0, "out of memory");
+    }
     *out = c;
     return DI_OK;
 }
@@ -266,34 +384,55 @@ extern "C" int di_collection_arrays(const di_collection_t *c, const uint64_t **d
 }
 
 // quantize.py:40-47 — one output line per document: "term: value" for every value > 0, joined by ", ".
+// Formatting is done by all host threads on blocks of ~2 M postings; the blocks are written in order.
 extern "C" int di_collection_write_quantized(const di_collection_t *c, const int32_t *values, const char *path)
 {
     if (!c || (!values && !c->term_ids.empty()) || !path) return fail(DI_ERR_ARG, "line %llu: %s", 0, "NULL argument");
     FILE *f = fopen(path, "wb");
     if (!f) return fail(DI_ERR_ARG, "line %llu: cannot open %s for writing", 0, path);
-    std::string buf;
-    buf.reserve(1 << 20);
-    char num[16];
-    for (size_t d = 0; d + 1 < c->doc_offsets.size(); ++d) {
-        bool first = true;
-        for (uint64_t i = c->doc_offsets[d]; i < c->doc_offsets[d + 1]; ++i) {
-            if (values[i] <= 0) continue;
-            if (!first) buf += ", ";
-            first = false;
-            const uint32_t t = c->term_ids[i];
-            buf.append(c->vocab_blob, c->vocab_offsets[t], c->vocab_offsets[t + 1] - c->vocab_offsets[t]);
-            buf += ": ";
-            int len = 0;  // values[i] > 0 here
-            for (uint32_t x = (uint32_t)values[i]; x; x /= 10) num[sizeof num - 1 - len++] = (char)('0' + x % 10);
-            buf.append(num + sizeof num - len, (size_t)len);
-        }
-        buf += '\n';
-        if (buf.size() > (1 << 20) - 4096) {
-            if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); return fail(DI_ERR_ARG, "line %llu: %s", d, "short write"); }
-            buf.clear();
-        }
+    const size_t n_docs = c->doc_offsets.size() - 1;
+    constexpr uint64_t kBlockPostings = 2u << 20;
+    std::vector<size_t> block_begin{0};  // first document of every block
+    while (block_begin.back() < n_docs) {
+        const uint64_t target = c->doc_offsets[block_begin.back()] + kBlockPostings;
+        size_t next = (size_t)(std::upper_bound(c->doc_offsets.begin(), c->doc_offsets.end(), target) - c->doc_offsets.begin());
+        next = std::min(n_docs, std::max(next, block_begin.back() + 1));
+        // blocks of empty documents: at most 1 M lines each
+        block_begin.push_back(std::min(next, block_begin.back() + (1u << 20)));
     }
-    const bool ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    const size_t n_blocks = block_begin.size() - 1;
+    auto format_block = [&](size_t b, std::string &buf) {
+        buf.clear();
+        char num[16];
+        for (size_t d = block_begin[b]; d < block_begin[b + 1]; ++d) {
+            bool first = true;
+            for (uint64_t i = c->doc_offsets[d]; i < c->doc_offsets[d + 1]; ++i) {
+                if (values[i] <= 0) continue;
+                if (!first) buf += ", ";
+                first = false;
+                const uint32_t t = c->term_ids[i];
+                buf.append(c->vocab_blob, c->vocab_offsets[t], c->vocab_offsets[t + 1] - c->vocab_offsets[t]);
+                buf += ": ";
+                int len = 0;  // values[i] > 0 here
+                for (uint32_t x = (uint32_t)values[i]; x; x /= 10) num[sizeof num - 1 - len++] = (char)('0' + x % 10);
+                buf.append(num + sizeof num - len, (size_t)len);
+            }
+            buf += '\n';
+        }
+    };
+    const unsigned n_threads = (unsigned)std::max<size_t>(1, std::min<size_t>(parse_threads(c->term_ids.size() * 16ull), n_blocks));
+    bool ok = true;
+    try {
+        std::vector<std::string> bufs(n_threads);
+        for (size_t b0 = 0; b0 < n_blocks && ok; b0 += n_threads) {
+            const unsigned n = (unsigned)std::min<size_t>(n_threads, n_blocks - b0);
+            run_parallel(n, [&](unsigned t) { format_block(b0 + t, bufs[t]); });
+            for (unsigned t = 0; t < n && ok; ++t) ok = fwrite(bufs[t].data(), 1, bufs[t].size(), f) == bufs[t].size();
+        }
+    } catch (const std::bad_alloc &) {
+        fclose(f);
+        return fail(DI_ERR_NOMEM, "line %llu: %s", 0, "out of memory");
+    }
     if (fclose(f) != 0 || !ok) return fail(DI_ERR_ARG, "line %llu: %s", 0, "short write");
     return DI_OK;
 }

@@ -126,8 +126,10 @@ def test_fast_parser_equals_reference_shaped_parser_on_golden(golden):
                 assert _same(C.parse_bytes(text.encode(), C.SEQUENCE), C.parse_python(text, C.SEQUENCE))
 
 
-def test_fast_parser_fuzz_against_python():
+@pytest.mark.parametrize("pieces", ["1", "3"])
+def test_fast_parser_fuzz_against_python(monkeypatch, pieces):
     from improving_learned_index_b200 import collection_io as C
+    monkeypatch.setenv("DI_B200_PARSE_THREADS", pieces)
     rng = np.random.default_rng(3)
     terms = ["a", "b c", "đá", "x|y", "t:1", "q,r", "naïve", "end ", "　lead", "tab\tin", "colon:", " sp"]
     nums = ["1", "0.5", "2.50", "1e3", "-3.25", "+7", ".5", "5.", "1E-2", "0", "inf", "-Infinity", "nan", "12.0", " 3 ", "4\t"]
@@ -177,6 +179,64 @@ def test_fast_parser_errors_and_fallback(tmp_path):
     c = C.parse_bytes("x: 1, đ: 2\ny: 3\nz: 4\n".encode(), C.SEQUENCE)
     c.write_quantized(np.array([5, 0, -1, 9], dtype=np.int32), tmp_path / "out")
     assert (tmp_path / "out").read_text(encoding="utf-8") == "x: 5\n\nz: 9\n"
+
+
+def test_fast_parser_is_independent_of_the_thread_count(monkeypatch, tmp_path):
+    """The file is cut into one piece per host thread; arrays, vocabulary, the quantized text and the first
+    error (with its line number) must not depend on how many pieces there are."""
+    from improving_learned_index_b200 import collection_io as C
+    from improving_learned_index_b200 import synthetic as syn
+    c = syn.make_collection(400, vocab_size=300, draws_per_doc=25, seed=9)
+    lines = c.lines()
+    lines[17] = ""                                   # empty documents (DICT) ...
+    lines[18] = ""
+    lines[40] = lines[40] + ", " + lines[40]         # ... and a document that repeats its terms
+    for eol in ("\n", "\r\n", "\r"):
+        text = eol.join(lines) + eol
+        monkeypatch.setenv("DI_B200_PARSE_THREADS", "1")
+        base = C.parse_bytes(text.encode(), C.DICT)
+        want = C.parse_python(text, C.DICT)
+        assert _same(base, want)
+        vals = (np.arange(base.term_ids.size) % 7).astype(np.int32)
+        base.write_quantized(vals, tmp_path / "q1")
+        for n in (2, 3, 7, 64, 256):
+            monkeypatch.setenv("DI_B200_PARSE_THREADS", str(n))
+            got = C.parse_bytes(text.encode(), C.DICT)
+            assert _same(got, base), (eol, n)
+            got.write_quantized(vals, tmp_path / "qn")
+            assert (tmp_path / "qn").read_bytes() == (tmp_path / "q1").read_bytes()
+    # first error in file order, same message whatever the cut
+    bad = list(lines)
+    bad[17] = bad[18] = "x: 1"
+    bad[300] = "broken pair"
+    bad[350] = "y: z"
+    text = "\n".join(bad) + "\n"
+    msgs = set()
+    for n in (1, 2, 5, 64):
+        monkeypatch.setenv("DI_B200_PARSE_THREADS", str(n))
+        with pytest.raises(ValueError) as e:
+            C.parse_bytes(text.encode(), C.SEQUENCE)
+        msgs.add(str(e.value))
+    assert len(msgs) == 1 and "line 301:" in msgs.pop()
+
+
+def test_fast_parser_utf8_check_agrees_with_cpython(monkeypatch):
+    """Invalid UTF-8 anywhere makes the fast parser defer (the caller's decode then raises UnicodeDecodeError)."""
+    from improving_learned_index_b200 import collection_io as C
+    good = ["é", "\u0800", "\ud7ff", "\ue000", "\uffff", "\U00010000", "\U0010ffff", "a" * 9 + "đ"]
+    bad = [b"\x80", b"\xc0\xaf", b"\xc1\xbf", b"\xe0\x80\xaf", b"\xe0\x9f\xbf", b"\xed\xa0\x80", b"\xed\xbf\xbf",
+           b"\xf0\x8f\xbf\xbf", b"\xf4\x90\x80\x80", b"\xf5\x80\x80\x80", b"\xe2\x82", b"\xf0\x9f\x98", b"\xff"]
+    for n in ("1", "4"):
+        monkeypatch.setenv("DI_B200_PARSE_THREADS", n)
+        for t in good:
+            assert C.parse_bytes(f"{t}: 1\nb: 2\n".encode("utf-8"), C.DICT).vocab() == sorted([t, "b"])
+        for raw in bad:
+            for data in (raw + b": 1\nb: 2\n", b"b: 2\nlonger line here: 3\n" + raw + b": 1", b"a: 1, " + raw + b"\n"):
+                with pytest.raises(UnicodeDecodeError):
+                    data.decode("utf-8")
+                with pytest.raises(_native.NativeError) as e:
+                    C.parse_bytes(data, C.DICT)
+                assert e.value.code == _native.ERR_UNSUPPORTED
 
 
 def test_maxp_aggregation_matches_reference_output(golden, tmp_path):
