@@ -220,6 +220,9 @@ void parse_piece(Piece &pc, int mode)
         }
     };
     auto stop = [&](int code, const char *what) { pc.rc = code; pc.what = what; };
+    // "term: 1.234, " is rarely shorter than 12 bytes: one allocation instead of ~30 doublings
+    pc.term_ids.reserve(pc.text.size() / 12 + 16);
+    pc.scores.reserve(pc.text.size() / 12 + 16);
     std::vector<uint64_t> seen_in_doc;     // DICT mode: 1 + index of the term's posting if seen in the current doc
     size_t pos = 0;
     const std::string_view all = pc.text;
