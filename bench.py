@@ -488,7 +488,7 @@ def main():
     ap.add_argument("--verify-build", action="store_true", help="compare the full GPU inversion with the CPU oracle (~1 min)")
     ap.add_argument("--verify-sharded", action="store_true",
                     help="N > 1: compare the merged result of every query with a single index built on rank 0")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="queries in the timed CPU baseline / parity sample")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
     ap.add_argument("--ref-queries-per-step", type=int, default=32)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools/gpu_round.sh TAG [baseline.so ...]  — tests + A/B of library variants + phase profile
+# usage: tools/gpu_round2.sh TAG [baseline.so ...]  — tests + A/B of library variants + phase profile
 set -u
 O=gpurun_out; mkdir -p $O
 D=improving-learned-index_b200
