@@ -81,6 +81,8 @@ SIGNATURES = {
     "di_unpack_keys_dev": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "di_merge_topk_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                          _vp, _vp, _vp, _vp]),
+    "di_merge_rows_p2p_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint32, _vp, _vp, _vp, _vp]),
     "di_get_timings": (ctypes.c_int, [_vp, ctypes.POINTER(Timings)]),
     "di_collection_parse": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_vp)]),
     "di_collection_free": (None, [_vp]),

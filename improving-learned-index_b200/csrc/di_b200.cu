@@ -775,6 +775,35 @@ extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_co
     return DI_OK;
 }
 
+extern "C" int di_merge_rows_p2p_dev(const uint64_t *const *d_rows, const uint32_t *const *d_counts, uint32_t n_shards,
+                                     const uint32_t *d_query_ids, uint32_t n_queries, uint32_t row_stride, uint32_t k_in,
+                                     uint32_t top_k, uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_incomplete,
+                                     void *stream)
+{
+    if (n_queries == 0 || n_shards == 0) return DI_OK;
+    if (!d_rows || !d_counts) return set_error(DI_ERR_ARG, "NULL shard pointer table");
+    if (n_shards > kMaxP2PShards) return set_error(DI_ERR_ARG, "at most %u shards, got %u", kMaxP2PShards, n_shards);
+    if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
+    if (k_in == 0 || k_in > row_stride) return set_error(DI_ERR_ARG, "k_in must be in [1, row_stride = %u], got %u", row_stride, k_in);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t cap = pow2_ceil(std::max(n_shards * k_in, top_k));
+    static thread_local DevBuf cand, cnt;  // like di_merge_topk_dev: cached per host thread, only grows
+    DI_TRY(ensure(cand, (size_t)n_queries * cap * 8));
+    DI_TRY(ensure(cnt, (size_t)n_queries * 4));
+    merge_gather_p2p_kernel<<<n_queries, 256, 0, st>>>(d_rows, d_counts, n_shards, d_query_ids, row_stride, k_in,
+                                                      cand.as<uint64_t>(), cnt.as<uint32_t>(), cap);
+    DI_KERNEL_CHECK();
+    DI_TRY(launch_finalize(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k, /*max_n=*/n_shards * k_in, n_queries,
+                           d_keys_out, d_counts_out, st));
+    if (d_incomplete) {
+        merge_check_p2p_kernel<<<grid_for(n_queries, 256), 256, 0, st>>>(d_rows, d_counts, n_shards, d_query_ids, n_queries,
+                                                                        row_stride, k_in, top_k, d_keys_out, d_counts_out,
+                                                                        d_incomplete);
+        DI_KERNEL_CHECK();
+    }
+    return DI_OK;
+}
+
 extern "C" int di_get_timings(di_index_t *ix, di_timings *out)
 {
     if (!ix || !out) return set_error(DI_ERR_ARG, "NULL argument");

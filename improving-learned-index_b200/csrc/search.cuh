@@ -123,4 +123,60 @@ __global__ void merge_check_kernel(const uint64_t *__restrict__ keys_in, const u
     }
 }
 
+// ---------------------------------------------------------------------------- K5 over peer memory
+// The gather half of the merge WITHOUT a collective: rows[s] / counts[s] point at shard s's sorted key rows
+// ([.][row_stride]) and counts where that shard's search wrote them — on a peer GPU, mapped into this process
+// (NVLink loads). One CTA per query reads the first min(count, k_in) keys of every shard's row straight into
+// the merge list; finalize_topk_kernel then selects + sorts as in the all-gather form. query_ids (nullable)
+// restricts the merge to a subset of the queries (the unproven ones, second pass with k_in = row_stride).
+constexpr uint32_t kMaxP2PShards = 64;
+
+__global__ void __launch_bounds__(256) merge_gather_p2p_kernel(const uint64_t *const *__restrict__ rows,
+                                                               const uint32_t *const *__restrict__ counts, uint32_t n_shards,
+                                                               const uint32_t *__restrict__ query_ids, uint32_t row_stride,
+                                                               uint32_t k_in, uint64_t *__restrict__ cand,
+                                                               uint32_t *__restrict__ cnt, uint32_t cap)
+{
+    __shared__ uint32_t s_pref[kMaxP2PShards + 1];
+    __shared__ const uint64_t *s_row[kMaxP2PShards];
+    const uint32_t i = blockIdx.x, q = query_ids ? query_ids[i] : i;
+    if (threadIdx.x < n_shards) {  // one remote 4-byte read per shard, all in flight together
+        const uint32_t c = counts[threadIdx.x][q];
+        s_pref[threadIdx.x + 1] = c < k_in ? c : k_in;
+        s_row[threadIdx.x] = rows[threadIdx.x] + (uint64_t)q * row_stride;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_pref[0] = 0;
+        for (uint32_t s = 0; s < n_shards; ++s) s_pref[s + 1] += s_pref[s];
+    }
+    __syncthreads();
+    const uint32_t total = s_pref[n_shards];
+    uint32_t s = 0;
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {  // flattened over the shards: loads of different peers overlap
+        while (j >= s_pref[s + 1]) ++s;
+        cand[(uint64_t)i * cap + j] = s_row[s][j - s_pref[s]];
+    }
+    if (threadIdx.x == 0) cnt[i] = total;
+}
+
+// proof of completeness for the peer-memory form (see merge_check_kernel): keys_out / counts_out / incomplete are
+// indexed like the launch (row i = query query_ids[i]).
+__global__ void merge_check_p2p_kernel(const uint64_t *const *__restrict__ rows, const uint32_t *const *__restrict__ counts,
+                                       uint32_t n_shards, const uint32_t *__restrict__ query_ids, uint32_t n_queries,
+                                       uint32_t row_stride, uint32_t k_in, uint32_t k_out,
+                                       const uint64_t *__restrict__ keys_out, const uint32_t *__restrict__ counts_out,
+                                       uint32_t *__restrict__ incomplete)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_queries; i += gridDim.x * blockDim.x) {
+        const uint32_t q = query_ids ? query_ids[i] : i;
+        const uint32_t n = counts_out[i];
+        const uint64_t kth = n == k_out ? keys_out[(uint64_t)i * k_out + k_out - 1] : 0ull;  // 0: fewer than k found
+        uint32_t bad = 0;
+        for (uint32_t s = 0; s < n_shards; ++s)  // a shard holding more than k_in keys hides those below the k_in-th
+            if (counts[s][q] > k_in && rows[s][(uint64_t)q * row_stride + k_in - 1] > kth) bad = 1;
+        incomplete[i] = bad;
+    }
+}
+
 }  // namespace di

@@ -193,3 +193,12 @@ def merge_topk_device(d_keys_in, d_counts_in, n_shards: int, n_queries: int, top
     d_incomplete[q] = 1 marks queries whose merge could not be proven exact (re-run them with full rows)."""
     N.check(N.lib().di_merge_topk_dev(N.ptr(d_keys_in), N.ptr(d_counts_in), n_shards, n_queries, k_in or top_k, top_k,
                                       N.ptr(d_keys_out), N.ptr(d_counts_out), N.ptr(d_incomplete), stream))
+
+
+def merge_rows_p2p_device(d_row_ptrs, d_count_ptrs, n_shards: int, n_queries: int, row_stride: int, k_in: int, top_k: int,
+                          d_keys_out, d_counts_out, stream: int = 0, d_query_ids=None, d_incomplete=None):
+    """K5 over peer memory (experimental, DI_B200_P2P=1): d_row_ptrs / d_count_ptrs are device tables of
+    n_shards pointers to the shards' own result rows (peer memory); no all-gather."""
+    N.check(N.lib().di_merge_rows_p2p_dev(N.ptr(d_row_ptrs), N.ptr(d_count_ptrs), n_shards, N.ptr(d_query_ids), n_queries,
+                                          row_stride, k_in, top_k, N.ptr(d_keys_out), N.ptr(d_counts_out),
+                                          N.ptr(d_incomplete), stream))

@@ -17,12 +17,17 @@ the proof (with docid-ordered ties the boundary tie group of a short query sits 
 so one shard holds most of the top-k) the full rows — already computed — are gathered and merged; nothing
 is searched twice.
 
+Experimental (DI_B200_P2P=1, not yet validated on hardware in round 1): the shards' rows live in torch symmetric
+memory and K5 reads the peers' rows directly over NVLink (`di_merge_rows_p2p_dev`) after one cross-GPU barrier —
+no all-gather, no staging copy, and the second pass reads the unproven queries' full rows in place.
+
 The collective and the two compute steps are injected, so the plumbing (ranges, tensor layout of
 the gather, count handling, the two-round protocol) is testable on CPU with world_size 2 while the
 CUDA path plugs in DeviceIndex.search_device and engine.merge_topk_device.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Sequence, Tuple
 
 import numpy as np
@@ -66,7 +71,7 @@ class ShardedSearcher:
     incomplete [Q] int32) writes the global top-k and flags the queries whose merge is not proven exact.
     """
 
-    def __init__(self, local_search: Callable, merge: Callable, device, group=None, rows_per_shard=None):
+    def __init__(self, local_search: Callable, merge: Callable, device, group=None, rows_per_shard=None, p2p_merge=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -78,6 +83,8 @@ class ShardedSearcher:
         self._buffers = {}
         self.rows_per_shard = rows_per_shard   # optional override of shard_k: k -> keys per shard in round 1
         self.round2_queries = 0          # how many queries of the last search needed their full rows gathered
+        self.p2p_merge = p2p_merge       # experimental: merge straight from the peers' symmetric-memory rows
+        self._p2p = None
 
     @classmethod
     def for_device_index(cls, index: "engine.DeviceIndex", device, group=None) -> "ShardedSearcher":
@@ -90,7 +97,13 @@ class ShardedSearcher:
         def merge(g_keys, g_counts, n_shards, n_q, k_in, k, out_keys, out_counts, incomplete):
             engine.merge_topk_device(g_keys, g_counts, n_shards, n_q, k, out_keys, out_counts,
                                      torch.cuda.current_stream().cuda_stream, k_in=k_in, d_incomplete=incomplete)
-        return cls(local_search, merge, device, group)
+        p2p_merge = None
+        if os.environ.get("DI_B200_P2P") == "1":
+            def p2p_merge(row_ptrs, count_ptrs, n_shards, query_ids, n_q, row_stride, k_in, k, out_keys, out_counts, incomplete):
+                engine.merge_rows_p2p_device(row_ptrs, count_ptrs, n_shards, n_q, row_stride, k_in, k, out_keys, out_counts,
+                                             torch.cuda.current_stream().cuda_stream, d_query_ids=query_ids,
+                                             d_incomplete=incomplete)
+        return cls(local_search, merge, device, group, p2p_merge=p2p_merge)
 
     def _buf(self, name, shape, dtype):
         key = (name, tuple(shape))
@@ -123,11 +136,52 @@ class ShardedSearcher:
                    k_in, k, out_keys, out_counts, incomplete)
         return out_keys, out_counts, incomplete if prove else None
 
+    def _search_tensors_p2p(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
+        """Peer-memory form of search_tensors (world > 1, CUDA): rows are written into symmetric memory, one
+        cross-GPU barrier, then K5 reads the peers' rows over NVLink. Two buffer sets alternate, so the barrier of
+        the next call is what protects a set from being overwritten while a peer still reads it."""
+        import torch.distributed._symmetric_memory as symm
+        torch = self.torch
+        if self._p2p is None or self._p2p["q"] < n_queries or self._p2p["k"] != k:   # collective: same sizes on every rank
+            q_cap = n_queries + n_queries // 4 + 1
+            group = self.group if self.group is not None else self.dist.group.WORLD
+            sets = []
+            for _ in range(2):
+                rows = symm.empty(q_cap * k, dtype=torch.int64, device=self.device)
+                cnts = symm.empty(q_cap, dtype=torch.int32, device=self.device)
+                sets.append((rows, cnts, symm.rendezvous(rows, group), symm.rendezvous(cnts, group)))
+            self._p2p = {"q": q_cap, "k": k, "sets": sets, "calls": 0}
+        rows, cnts, h_rows, h_cnts = self._p2p["sets"][self._p2p["calls"] % 2]
+        self._p2p["calls"] += 1
+        keys, counts = rows[:n_queries * k].view(n_queries, k), cnts[:n_queries]
+        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)
+        h_rows.barrier(channel=0)            # every shard's rows and counts are written
+        k_in = min(k, self.rows_per_shard(k)) if self.rows_per_shard else shard_k(k, self.world)
+        out_keys = self._flat("p_out_keys", n_queries * k, torch.int64).view(n_queries, k)
+        out_counts = self._flat("p_out_counts", n_queries, torch.int32)
+        incomplete = self._flat("p_incomplete", n_queries, torch.int32) if k_in < k else None
+        self.p2p_merge(h_rows.buffer_ptrs_dev, h_cnts.buffer_ptrs_dev, self.world, None, n_queries, k, k_in, k,
+                       out_keys, out_counts, incomplete)
+        if incomplete is not None:
+            redo = torch.nonzero(incomplete).flatten()
+            if redo.numel():
+                n_redo = int(redo.numel())
+                self.round2_queries = n_redo
+                k2 = self._flat("p_k2", n_redo * k, torch.int64).view(n_redo, k)
+                c2 = self._flat("p_c2", n_redo, torch.int32)
+                self.p2p_merge(h_rows.buffer_ptrs_dev, h_cnts.buffer_ptrs_dev, self.world, redo.to(torch.int32), n_redo, k, k, k,
+                               k2, c2, None)
+                out_keys[redo] = k2
+                out_counts[redo] = c2
+        return out_keys, out_counts
+
     def search_tensors(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
         """Device-level entry: returns (keys [Q,k] int64, counts [Q] int32) tensors holding the GLOBAL top-k.
         The returned tensors are owned by the searcher and overwritten by the next call."""
         torch = self.torch
         self.round2_queries = 0
+        if self.p2p_merge is not None and self.world > 1:
+            return self._search_tensors_p2p(d_q_terms, d_q_offsets, n_queries, max_len, k)
         keys = self._flat("keys", n_queries * k, torch.int64).view(n_queries, k)
         counts = self._flat("counts", n_queries, torch.int32)
         self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)   # this shard's sorted top-k

@@ -186,6 +186,21 @@ int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_counts_in,
                       uint32_t n_shards, uint32_t n_queries, uint32_t k_in, uint32_t top_k,
                       uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_incomplete, void *stream);
 
+/* K5 over peer memory (no collective): d_rows[s] / d_counts[s] are DEVICE-resident tables of n_shards pointers to
+ * every shard's sorted key rows ([.][row_stride]) and counts where that shard's own di_search_dev wrote them
+ * — peer GPU memory mapped into this process (e.g. torch symmetric memory `buffer_ptrs_dev`); the caller orders
+ * the shards' searches before this call with a cross-GPU barrier. One kernel reads the first min(count, k_in)
+ * keys of each row over NVLink while it builds the merge list, then selects + sorts like di_merge_topk_dev.
+ * d_query_ids (NULL = all queries 0..n_queries-1) merges only the listed queries; output rows, counts and
+ * flags are indexed by position in that list. d_incomplete as in di_merge_topk_dev (never set when
+ * k_in == row_stride). EXPERIMENTAL in round 1: compiled and exported, exercised only by
+ * tests/test_gpu_p2p.py and sharded.py when DI_B200_P2P=1.
+ */
+int di_merge_rows_p2p_dev(const uint64_t *const *d_rows, const uint32_t *const *d_counts, uint32_t n_shards,
+                          const uint32_t *d_query_ids, uint32_t n_queries, uint32_t row_stride, uint32_t k_in,
+                          uint32_t top_k, uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_incomplete,
+                          void *stream);
+
 /* ------------------------------------------------------------------ measurement hooks
  * Device time (CUDA events on the launching stream) of the di_search / di_search_dev calls made since the
  * previous di_get_timings() (reading clears the record). */
