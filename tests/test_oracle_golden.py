@@ -206,3 +206,30 @@ def test_sparse_search_twin(golden):
         for i, q in enumerate(qids):
             got = [[corpus_ids[int(a)], float(b)] for a, b in zip(d[i, :cnt[i]], s[i, :cnt[i]])]
             assert got == g[key][q], (key, q)
+
+
+def test_threshold_seed_is_a_lower_bound_of_the_kth_score():
+    """The claim behind the GPU path's threshold seeds (csrc/build.cuh), checked on the CPU against the oracle:
+    a query's k-th best score is at least the k-th highest impact of any single one of its terms — as long as no
+    posting list names a document twice (the counter-example below is why such an index gets no seeds)."""
+    from helpers import quantized_csr
+    from improving_learned_index_b200 import synthetic as syn
+    x = quantized_csr(3000, 120, 40, 5)
+    toff = x["toff"].astype(np.int64)
+    queries = syn.make_queries(60, vocab_size=120, seed=6)
+    for k in (1, 10, 200, 2500):
+        d, s, c, _ = oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], 3000, queries, k)
+        for qi, q in enumerate(queries):
+            bound = 0
+            for t in set(q):
+                imp = np.sort(x["vals"][toff[t]:toff[t + 1]])[::-1]
+                if imp.size >= k:
+                    bound = max(bound, int(imp[k - 1]))
+            if bound:
+                assert c[qi] == k and s[qi, k - 1] >= bound, (k, qi)
+    # one term, document 5 listed twice with impact 200, every other document once with impact 1: two postings
+    # reach 200 but only ONE document does; the 2nd best score is 1
+    docs = np.array([5, 5] + [d for d in range(50) if d != 5], dtype=np.uint32)
+    vals = np.array([200, 200] + [1] * 49, dtype=np.uint8)
+    d, s, c, _ = oracle.score_topk_csr(np.array([0, 51], dtype=np.uint64), docs, vals, 50, [[0]], 2)
+    assert s[0, :2].tolist() == [400, 1] and np.sort(vals)[::-1][1] == 200
