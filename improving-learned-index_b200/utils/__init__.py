@@ -1,0 +1,1 @@
+"""On-disk format constants and the query / qrels / run-file wire formats."""
