@@ -7,12 +7,14 @@ All ids are strings, as in the reference.
 from __future__ import annotations
 
 import json
+import logging
 from pathlib import Path
 from typing import Dict, Iterator, Optional, Set, Tuple, Union
 
 from .defaults import COLLECTION_TYPES
 
 PathLike = Union[str, Path]
+logger = logging.getLogger(__name__)
 
 
 class QueryParser:
@@ -69,6 +71,9 @@ class QueryRelevanceDataset:
                 cols = line.strip().split('\t')
                 assert int(cols[1]) == 0 and int(cols[3]) == 1, "Qrels file is not in the expected format"
                 self.qrels.setdefault(str(cols[0]), set()).add(str(cols[2]))
+        # datasets.py:161-162: logged there; an empty qrels file is a ZeroDivisionError there and here
+        self.average_positive_per_query = round(sum(len(p) for p in self.qrels.values()) / len(self.qrels), 2)
+        logger.info(f"Loaded {len(self.qrels)} queries with {self.average_positive_per_query} positive passages/query on average")
 
     def __len__(self) -> int:
         return len(self.qrels)

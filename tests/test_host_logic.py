@@ -75,6 +75,10 @@ def test_query_and_run_files(tmp_path):
     (tmp_path / "bad").write_text("7\t1\t11\t1\n")
     with pytest.raises(AssertionError):
         QueryRelevanceDataset(tmp_path / "bad")
+    (tmp_path / "empty").write_text("")
+    with pytest.raises(ZeroDivisionError):           # datasets.py:161 averages over zero queries
+        QueryRelevanceDataset(tmp_path / "empty")
+    assert rel.average_positive_per_query == 1.5
     run = RunFile(tmp_path / "run")
     run.writelines("7", [(11, 300), (3, 200)])
     run.write("8", 5, 1, 10)
