@@ -158,6 +158,10 @@ int di_index_term_df(const di_index_t *index, const uint32_t *term_ids, uint64_t
  * Query q owns term ids q_terms[q_offsets[q] .. q_offsets[q+1]); DI_OOV_TERM entries are skipped.
  * Outputs are row-major [n_queries][top_k]; rows are valid up to out_counts[q].
  * top_k <= 65536.
+ * Scoring is exhaustive; a document is left out of a candidate list only when it is PROVEN to be outside the
+ * top_k: below the running k-th best key, or below the query's seed bound (the k-th highest impact of one of
+ * its frequent terms, from per-term impact tables built with the index; skipped for an index in which a posting
+ * list names a document twice). The result is identical to scoring everything and sorting.
  */
 int di_search(di_index_t *index, const uint32_t *q_terms, const uint64_t *q_offsets,
               uint32_t n_queries, uint32_t top_k,
