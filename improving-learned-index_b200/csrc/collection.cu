@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <new>
 #include <string>
 #include <string_view>
@@ -174,6 +175,7 @@ struct Piece {
     std::vector<uint32_t> term_ids;          // piece-local ids, remapped to final ranks by the merge
     std::vector<double> scores;
     std::vector<std::string_view> terms;     // piece-local id -> term (views into the file text)
+    std::vector<std::string_view> sorted;    // the same terms in bytewise order (sorted by the piece's own thread)
     uint64_t lines = 0;                      // lines consumed (the failing line included)
     int rc = DI_OK;
     const char *what = "";
@@ -266,6 +268,10 @@ void parse_piece(Piece &pc, int mode)
         }
         if (pc.rc == DI_OK) pc.doc_ends.push_back(pc.term_ids.size());
     }
+    if (pc.rc == DI_OK) {
+        pc.sorted = pc.terms;
+        std::sort(pc.sorted.begin(), pc.sorted.end());
+    }
 }
 
 unsigned parse_threads(uint64_t n_bytes)
@@ -325,10 +331,13 @@ extern "C" int di_collection_parse(const char *text, uint64_t n_bytes, int mode,
         }
         // global vocabulary: sorted (bytewise == code point order for UTF-8) union of the pieces' terms,
         // as sorted(set(terms)) gives; final id = rank
-        std::vector<std::string_view> vocab;
-        for (const Piece &pc : pieces) vocab.insert(vocab.end(), pc.terms.begin(), pc.terms.end());
-        std::sort(vocab.begin(), vocab.end());
-        vocab.erase(std::unique(vocab.begin(), vocab.end()), vocab.end());
+        std::vector<std::string_view> vocab, merged;
+        for (const Piece &pc : pieces) {  // union of the pieces' sorted term lists: linear per piece
+            merged.clear();
+            merged.reserve(vocab.size() + pc.sorted.size());
+            std::set_union(vocab.begin(), vocab.end(), pc.sorted.begin(), pc.sorted.end(), std::back_inserter(merged));
+            vocab.swap(merged);
+        }
         for (const std::string_view t : vocab) {
             c->vocab_blob.append(t);
             c->vocab_offsets.push_back(c->vocab_blob.size());
