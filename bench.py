@@ -50,9 +50,11 @@ def zipf_tables(vocab_size, torch, dev):
     return (torch.from_numpy(cdf).to(dev), torch.from_numpy(perm.astype(np.int64)).to(dev))
 
 
-def gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, dev):
+def gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, dev, unique=0):
     """Documents [lo, hi) of chunk `chunk_id` (rows are generated for the whole chunk so that any
-    shard split sees identical documents). Returns per-doc kept counts, term ids, float64 impacts."""
+    shard split sees identical documents). Returns term ids, float64 impacts and the keep mask, every row
+    sorted by term id. unique > 0: a document keeps the first `unique` DISTINCT terms of its `draws` Zipf draws
+    (configs[1]: "~120 unique expanded terms/doc"); unique == 0: all distinct terms of the draws (round 1)."""
     cdf, perm = tables
     c0 = chunk_id * CHUNK_DOCS
     n = min(CHUNK_DOCS, n_docs_total - c0)
@@ -66,17 +68,34 @@ def gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, 
     zero = torch.rand((n, draws), generator=g, device=dev, dtype=torch.float32) < 0.01
     m[zero] = 0
     del z, zero
-    terms, order = torch.sort(terms, dim=1)
-    m = torch.gather(m, 1, order)
-    del order
-    keep = torch.ones_like(terms, dtype=torch.bool)
-    keep[:, 1:] = terms[:, 1:] != terms[:, :-1]
+    if unique:
+        # first occurrence of every term in DRAW order, then the first `unique` of those
+        st, order = torch.sort(terms, dim=1, stable=True)
+        first_sorted = torch.ones_like(st, dtype=torch.bool)
+        first_sorted[:, 1:] = st[:, 1:] != st[:, :-1]
+        first = torch.zeros_like(first_sorted).scatter_(1, order, first_sorted)
+        del st, order, first_sorted
+        chosen = first & (torch.cumsum(first, dim=1) <= unique)
+        del first
+        terms = torch.where(chosen, terms, torch.full_like(terms, vocab_size))   # dropped draws sort to the end
+        terms, order = torch.sort(terms, dim=1)
+        m = torch.gather(m, 1, order)
+        del order, chosen
+        keep = terms < vocab_size
+        width = min(draws, unique)                       # at most `unique` kept columns, all at the front
+        terms, m, keep = terms[:, :width].contiguous(), m[:, :width].contiguous(), keep[:, :width].contiguous()
+    else:
+        terms, order = torch.sort(terms, dim=1)
+        m = torch.gather(m, 1, order)
+        del order
+        keep = torch.ones_like(terms, dtype=torch.bool)
+        keep[:, 1:] = terms[:, 1:] != terms[:, :-1]
     sl = slice(lo - c0, hi - c0)
     return terms[sl], (m[sl] / 1000.0), keep[sl]
 
 
 
-def build_shard_arrays(doc_lo, doc_hi, n_docs_total, vocab_size, draws, torch, dev, quantize_fn):
+def build_shard_arrays(doc_lo, doc_hi, n_docs_total, vocab_size, draws, torch, dev, quantize_fn, unique=0):
     """Doc-major arrays of the shard [doc_lo, doc_hi): term ids (u32 as int32 bits), u8 impacts (quantized by
     `quantize_fn`, postings with value 0 dropped as quantize.py:45 does), u64 doc offsets (local docs)."""
     tables = zipf_tables(vocab_size, torch, dev)
@@ -84,7 +103,7 @@ def build_shard_arrays(doc_lo, doc_hi, n_docs_total, vocab_size, draws, torch, d
     for chunk_id in range(doc_lo // CHUNK_DOCS, (doc_hi - 1) // CHUNK_DOCS + 1):
         lo = max(doc_lo, chunk_id * CHUNK_DOCS)
         hi = min(doc_hi, (chunk_id + 1) * CHUNK_DOCS)
-        terms, impacts, keep = gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, dev)
+        terms, impacts, keep = gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, dev, unique)
         q = quantize_fn(impacts.reshape(-1).contiguous()).reshape(impacts.shape)
         keep &= q > 0
         t_parts.append(terms[keep].to(torch.int32))
@@ -95,6 +114,15 @@ def build_shard_arrays(doc_lo, doc_hi, n_docs_total, vocab_size, draws, torch, d
     offs = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=offs[1:])
     return torch.cat(t_parts), torch.cat(v_parts), offs
+
+
+def workload_config(args, k):
+    name = ("configs[3]: 100K queries of ~6 terms, batches of %d" % args.batch if args.workload == "c4"
+            else "configs[1]: MS MARCO passage-shaped synthetic index")
+    return {"workload": "%s, Zipf(1) terms, top-%d" % (name, k), "docs": args.docs, "vocab": args.vocab,
+            "draws_per_doc": args.draws,
+            "unique_terms_per_doc": args.unique_terms or "all distinct terms of the draws (~91 of 120; round-1 workload)",
+            "queries": args.queries, "top_k": k}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -135,14 +163,15 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
-def measured_traffic(n_docs, n_queries, top_k, world):
-    """dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r1_traffic.json) — only when it was taken on this very configuration."""
+def committed_profile(n_docs, n_queries, top_k, world, unique_terms):
+    """Numbers that only a profiler can give, read from the committed `ncu --set full` summary of the dominant
+    kernel (profiles/r2_k3_limiter.json, written by tools/ncu_summary.py) — used only when that capture was taken
+    on this very configuration: DRAM bytes per launch and the SM-side utilisation figures that name the limiter."""
     try:
-        t = json.load(open(REPO / "profiles" / "r1_traffic.json"))
+        t = json.load(open(REPO / "profiles" / "r2_k3_limiter.json"))
         c = t["config"]
-        if (c["docs"], c["queries"], c["top_k"], c["n_gpus"]) == (n_docs, n_queries, top_k, world):
-            return t["dram_bytes_read"] + t["dram_bytes_write"]     # bytes per launch (one launch = one step)
+        if (c["docs"], c["queries"], c["top_k"], c["n_gpus"], c.get("unique_terms", 0)) == (n_docs, n_queries, top_k, world, unique_terms):
+            return t
     except Exception:
         pass
     return None
@@ -175,7 +204,7 @@ def run_b200(args):
         out = torch.empty(x.numel(), dtype=torch.int32, device=dev)
         _native.check(L.di_quantize_f64_dev(x.data_ptr(), x.numel(), IMPACT_CLIP, out.data_ptr(), stream))
         return out
-    terms, imps, offs = build_shard_arrays(doc_lo, doc_hi, N, V, args.draws, torch, dev, quantize_fn)
+    terms, imps, offs = build_shard_arrays(doc_lo, doc_hi, N, V, args.draws, torch, dev, quantize_fn, args.unique_terms)
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     P = terms.numel()
@@ -216,6 +245,13 @@ def run_b200(args):
                                                cand_slack=args.cand_slack)
     t_tile = time.time() - t1
     info = index.info()
+    build_info = {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "invert_ms_first_call": round(invert_runs[0], 1),
+                  "tile_layout_s": round(t_tile, 3), "invert_postings_per_s": round(P / (invert_ms * 1e-3)),
+                  "invert_gbs_at_17B": round(17 * P / (invert_ms * 1e-3) / 1e9, 1)}
+    n_idx = torch.tensor([info["n_postings"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_idx, op=dist.ReduceOp.SUM)
+    total_postings_index = int(n_idx.item())
 
     # ---- queries
     queries = synthetic.make_queries(args.queries, vocab_size=V, seed=7)
@@ -287,6 +323,7 @@ def run_b200(args):
             score_ms.append(t["score_ms"])
             final_ms.append(t["finalize_ms"])
             launches = t                     # kernels this rank's library launched in this step
+            n_launches = t["score_launches"] + t["other_launches"] + (3 * len(batches) if world > 1 else 0)
         barrier()
         # ---- timed: end to end through the host-buffer call
         step_e2e()
@@ -315,47 +352,60 @@ def run_b200(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # per-GPU roofline of the dominant kernel (score_tile): this rank's postings bytes / its launch time
-        achieved = ALGO_BYTES_PER_POSTING * local_postings / (np.mean(score_ms) * 1e-3) / 1e9
+        # per-GPU roofline of the dominant kernel (score_persistent_kernel): this rank's ALGORITHMIC postings bytes
+        # (5 B per posting traversed) / its launch time. The kernel serves every posting of a tile to the
+        # whole batch from L2 and stores hot lists as one byte per document, so `frac` can exceed 1: it says how much
+        # HBM traffic a one-query-at-a-time streaming scorer would need, not how busy the DRAM is. `dram_frac` is the
+        # measured DRAM traffic / time / peak and `limiter` names what actually bounds the kernel (ncu, profiles/).
+        score_s = float(np.mean(score_ms)) * 1e-3
+        achieved = ALGO_BYTES_PER_POSTING * local_postings / score_s / 1e9
+        prof = committed_profile(N, Q, k, world, args.unique_terms)
+        traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"] if prof else None
+        cfg = workload_config(args, k)
+        cfg.update({"postings": total_postings_index, "batch": B, "sharding": f"docid-range x{world}",
+                    "tile_docs": info["tile_docs"],
+                    "l2": "index payload (%.1f GB/GPU) exceeds L2 and a 256 MB buffer is written between timed steps"
+                          % (info["payload_bytes"] / 1e9)})
         out = {
-            "metric": "QPS top-1000 on 8.8M-doc MS MARCO-shaped index",
+            "metric": "QPS top-%d on 8.8M-doc MS MARCO-shaped index" % k,
             "value": round(Q * args.steps / (total_dev_ms * 1e-3), 2), "unit": "queries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(total_dev_ms / args.steps, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8 impacts, u16/int32 accumulators", "data": "synthetic",
-            "config": {"workload": "configs[1]: MS MARCO passage-shaped synthetic index, Zipf(1) terms, top-%d" % k,
-                       "docs": N, "vocab": V, "draws_per_doc": args.draws,
-                       "queries": Q, "top_k": k, "batch": B, "sharding": f"docid-range x{world}", "tile_docs": info["tile_docs"],
-                       "l2": "index payload (%.1f GB/GPU) exceeds L2 and a 256 MB buffer is written between timed steps"
-                             % (info["payload_bytes"] / 1e9)},
+            "config": cfg,
             "e2e": {"value": round(Q * args.steps / (total_e2e_ms * 1e-3), 2), "unit": "queries/s",
                     "h2d_bytes_per_step": int(h_flat.numel() * 4 + h_offs.numel() * 8),
                     "d2h_bytes_per_step": int(Q * k * 8 + Q * 4)},
             # kernels of this repo launched inside the `value` timed region, all ranks
-            "gpu_launches": int((launches["score_launches"] + launches["other_launches"] + (3 if world > 1 else 0))
-                                * args.steps * world),
+            "gpu_launches": int(n_launches * args.steps * world),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": measured_traffic(N, Q, k, world),
+                         "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "frac_is": "algorithmic postings bytes / time / peak (SURVEY 8d); > 1 = traffic the L2-resident "
+                                    "batch and the byte-per-document lists do not send to HBM",
+                         "dram_frac": round(traffic / score_s / 1e9 / peak, 4) if traffic else None,
+                         "limiter": prof.get("limiter") if prof else None,
+                         "limiter_frac": prof.get("limiter_frac") if prof else None,
+                         "sm": prof.get("sm") if prof else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                          "kernel": "score_persistent_kernel", "launches_per_step": launches["score_launches"],
                          "algorithmic_bytes_per_step_this_gpu": ALGO_BYTES_PER_POSTING * local_postings,
                          "score_ms_per_step": round(float(np.mean(score_ms)), 3),
-                         "finalize_ms_per_step": round(float(np.mean(final_ms)), 3)},
+                         "finalize_ms_per_step": round(float(np.mean(final_ms)), 3),
+                         "tile_lanes": launches["lanes"]},
             "clocks": clocks.summary(),
             "index": {"postings_this_gpu": info["n_postings"], "payload_gb": round(info["payload_bytes"] / 1e9, 3),
                       "dense_segments": info["n_dense_segments"], "sparse_segments": info["n_sparse_segments"],
                       "dense_posting_frac": round(info["n_dense_postings"] / max(info["n_postings"], 1), 3),
                       "tiles": info["n_tiles"]},
-            "build": {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "invert_ms_first_call": round(invert_runs[0], 1), "tile_layout_s": round(t_tile, 2),
-                      "invert_postings_per_s": round(P / (invert_ms * 1e-3)), "invert_gbs_at_17B": round(17 * P / (invert_ms * 1e-3) / 1e9, 1)},
+            "build": build_info,
             "postings_per_query": round(total_postings / Q),
             "build_parity": build_parity,
             "round2_queries_last_step": searcher.round2_queries,
         }
         if world == 1 and args.cpu_sample > 0:
             out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(
-                args, toff, docids, vals, queries, index, torch)
+                args, toff, docids, vals, queries, (h_docs, h_scores, h_counts), torch)
     if world > 1 and args.verify_sharded:
         # every rank's merged result vs ONE index over all documents built on rank 0's GPU (itself checked against
         # the oracle in the 1-GPU run): the sharded path must be bit-identical
@@ -363,7 +413,7 @@ def run_b200(args):
         m_keys, m_counts = m_keys.clone(), m_counts.clone()
         same = None
         if rank == 0:
-            t_all, v_all, o_all = build_shard_arrays(0, N, N, V, args.draws, torch, dev, quantize_fn)
+            t_all, v_all, o_all = build_shard_arrays(0, N, N, V, args.draws, torch, dev, quantize_fn, args.unique_terms)
             P_all = t_all.numel()
             toff_a = torch.empty(V + 1, dtype=torch.int64, device=dev)
             docs_a = torch.empty(P_all, dtype=torch.int32, device=dev)
@@ -391,9 +441,10 @@ def run_b200(args):
         print(json.dumps(out))
 
 
-def cpu_baseline_and_parity(args, toff, docids, vals, queries, index, torch):
-    """Oracle (C port, all host threads) on a bounded query sample of the same index; the GPU results for
-    the same sample must match bit for bit (full-size parity check)."""
+def cpu_baseline_and_parity(args, toff, docids, vals, queries, timed_result, torch):
+    """Oracle (C port, all host threads) on a bounded query sample of the same index. The GPU rows compared with
+    it are taken FROM THE OUTPUT OF THE LAST TIMED END-TO-END STEP (the full batch through the host-buffer
+    C-ABI call), so the parity claim covers exactly the code path that produced the number."""
     from oracle import oracle
     h_toff = toff.cpu().numpy().astype(np.uint64)
     h_docs = docids.cpu().numpy().view(np.uint32)
@@ -401,23 +452,35 @@ def cpu_baseline_and_parity(args, toff, docids, vals, queries, index, torch):
     rng = np.random.default_rng(123)
     pick = sorted(rng.choice(len(queries), size=min(args.cpu_sample, len(queries)), replace=False).tolist())
     sample = [queries[i] for i in pick]
-    threads = oracle.max_threads()
+    threads = host_threads()
     t0 = time.perf_counter()
     o_docs, o_scores, o_counts, o_post = oracle.score_topk_csr(h_toff, h_docs, h_vals, args.docs, sample, args.top_k,
                                                               n_threads=threads)
     dt = time.perf_counter() - t0
-    g_docs, g_scores, g_counts = index.search(sample, args.top_k)
-    ok = bool(np.array_equal(g_counts, o_counts))
-    for i in range(len(sample)):
+    g_docs, g_scores, g_counts = (t.numpy() for t in timed_result)
+    ok = True
+    for i, qi in enumerate(pick):
         n = int(o_counts[i])
-        ok = ok and np.array_equal(g_docs[i, :n], o_docs[i, :n]) and np.array_equal(g_scores[i, :n], o_scores[i, :n])
+        ok = (ok and int(g_counts[qi]) == n and np.array_equal(g_docs[qi, :n].view(np.uint32), o_docs[i, :n])
+              and np.array_equal(g_scores[qi, :n], o_scores[i, :n]))
     base = {"value": round(len(sample) / dt, 3), "unit": "queries/s", "cores": threads, "kind": "port",
             "sample": f"{len(sample)} of the {len(queries)} queries (seed 123), full index, oracle/di_oracle.c with OpenMP",
             "postings_per_s": round(float(o_post.sum()) / dt), "seconds": round(dt, 2)}
-    parity = {"queries_checked": len(sample), "bit_exact": ok, "against": "oracle/di_oracle.c (pinned to reference golden vectors)"}
+    parity = {"queries_checked": len(sample), "bit_exact": bool(ok), "path": "timed batch",
+              "rows_from": "output buffers of the last timed end-to-end step (%d queries per call)" % (args.batch or len(queries)),
+              "against": "oracle/di_oracle.c (pinned to reference golden vectors)"}
     if not ok:
-        raise SystemExit("PARITY FAILURE at full size: GPU results differ from the oracle")
+        raise SystemExit("PARITY FAILURE at full size: GPU results of the timed batch differ from the oracle")
     return base, parity
+
+
+def host_threads():
+    """Host threads the CPU legs use: every core this process may run on — NOT OMP_NUM_THREADS, which torchrun
+    sets to 1 for its workers."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
@@ -438,12 +501,12 @@ def run_reference(args):
     def quantize_fn(x):      # CPU oracle arithmetic (quantize.py:13-14), not the CUDA kernel
         q = oracle.quantize(x.cpu().numpy(), scale_max)
         return torch.from_numpy(q.astype(np.int32)).to(x.device)
-    terms, imps, offs = build_shard_arrays(0, N, N, V, args.draws, torch, dev, quantize_fn)
+    terms, imps, offs = build_shard_arrays(0, N, N, V, args.draws, torch, dev, quantize_fn, args.unique_terms)
     toff, docids, vals = oracle.invert(terms.cpu().numpy().view(np.uint32), imps.cpu().numpy(),
                                        offs.cpu().numpy().astype(np.uint64), V)
     del terms, imps, offs
     queries = synthetic.make_queries(args.queries, vocab_size=V, seed=7)
-    threads = oracle.max_threads()
+    threads = host_threads()           # explicit: under torchrun OMP_NUM_THREADS is 1
     per_step = max(1, min(args.ref_queries_per_step, len(queries)))
     rng = np.random.default_rng(123)
     times, n_done = [], 0
@@ -457,13 +520,11 @@ def run_reference(args):
             times.append(dt)
             n_done += per_step
     qps = n_done / sum(times)
-    out = {"impl": "reference", "metric": "QPS top-1000 on 8.8M-doc MS MARCO-shaped index", "value": round(qps, 3),
+    out = {"impl": "reference", "metric": "QPS top-%d on 8.8M-doc MS MARCO-shaped index" % k, "value": round(qps, 3),
            "unit": "queries/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(1e3 * sum(times) / args.steps, 2), "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "u8 impacts, int32 accumulators", "data": "synthetic",
-           "config": {"workload": "configs[1]: MS MARCO passage-shaped synthetic index, Zipf(1) terms, top-%d" % k,
-                      "docs": N, "vocab": V, "draws_per_doc": args.draws, "queries": len(queries), "top_k": k,
-                      "queries_per_step": per_step},
+           "config": dict(workload_config(args, k), queries_per_step=per_step, postings=int(docids.size)),
            "cpu_baseline": {"value": round(qps, 3), "unit": "queries/s", "cores": threads, "kind": "port",
                             "sample": f"{per_step} random queries of the {len(queries)} per step, full 8.8M-doc index"},
            "e2e": {"value": round(qps, 3), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -478,9 +539,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--docs", type=int, default=8_841_823)
     ap.add_argument("--vocab", type=int, default=30522)
-    ap.add_argument("--draws", type=int, default=120)
-    ap.add_argument("--queries", type=int, default=6980)
-    ap.add_argument("--top-k", type=int, default=1000)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 = BASELINE configs[1]/[2] (6,980 queries, top-1000, one batch); "
+                         "c4 = configs[3] (100,000 queries of ~6 terms, batches of 4,096, top-100)")
+    ap.add_argument("--unique-terms", type=int, default=120,
+                    help="distinct terms kept per document (configs[1]: ~120); 0 = round-1 workload: all distinct "
+                         "terms of --draws 120 draws (~91 per document)")
+    ap.add_argument("--draws", type=int, default=0, help="Zipf draws per document (0 = 208 with --unique-terms, else 120)")
+    ap.add_argument("--queries", type=int, default=0)
+    ap.add_argument("--top-k", type=int, default=0)
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--dense-ratio", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0, help="queries per search call (0 = all queries at once)")
@@ -491,6 +558,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
     ap.add_argument("--ref-queries-per-step", type=int, default=32)
     args = ap.parse_args()
+    if args.draws == 0:
+        args.draws = 208 if args.unique_terms else 120
+    c4 = args.workload == "c4"
+    args.queries = args.queries or (100_000 if c4 else 6980)
+    args.top_k = args.top_k or (100 if c4 else 1000)
+    if c4 and not args.batch:
+        args.batch = 4096
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

@@ -25,6 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 OOV = 0xFFFFFFFF
 ALL_DOCS = 0xFFFFFFFF
+INDEX_NO_SEEDS, INDEX_PER_TILE = 1, 2
 
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _u32p = ctypes.POINTER(ctypes.c_uint32)
@@ -36,7 +37,7 @@ _vp = ctypes.c_void_p
 
 class IndexParams(ctypes.Structure):
     _fields_ = [("tile_docs", ctypes.c_uint32), ("dense_ratio", ctypes.c_uint32),
-                ("cand_slack", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("cand_slack", ctypes.c_uint32), ("flags", ctypes.c_uint32)]
 
 
 class IndexInfo(ctypes.Structure):
@@ -50,7 +51,8 @@ class IndexInfo(ctypes.Structure):
 
 class Timings(ctypes.Structure):
     _fields_ = [("score_ms", ctypes.c_float), ("finalize_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
-                ("score_launches", ctypes.c_uint32), ("other_launches", ctypes.c_uint32)]
+                ("score_launches", ctypes.c_uint32), ("other_launches", ctypes.c_uint32),
+                ("lanes", ctypes.c_uint32), ("acc32", ctypes.c_uint32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/di_b200.h declares

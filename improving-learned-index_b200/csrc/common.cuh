@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -68,6 +69,39 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         bytes = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// RAII scratch from the device's stream-ordered memory pool: allocated and freed in stream order, so an
+// asynchronous call can own scratch without a cache shared between devices, streams or threads.
+struct StreamBuf {
+    void *p = nullptr;
+    cudaStream_t st;
+    explicit StreamBuf(cudaStream_t s) : st(s) {}
+    StreamBuf(const StreamBuf &) = delete;
+    StreamBuf &operator=(const StreamBuf &) = delete;
+    ~StreamBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t n)
+    {
+        static std::atomic<uint64_t> pool_tuned{0};  // keep freed blocks in the pool instead of returning them at every sync
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const uint64_t bit = 1ull << (dev & 63);
+        if (!(pool_tuned.load(std::memory_order_acquire) & bit)) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_tuned.fetch_or(bit, std::memory_order_release);
+        }
+        cudaError_t e = cudaMallocAsync(&p, n ? n : 16, st);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return set_error(DI_ERR_NOMEM, "cudaMallocAsync(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+        }
+        return DI_OK;
     }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };

@@ -1,6 +1,7 @@
 // di_b200.cu — the C ABI declared in include/di_b200.h. Host-side orchestration only; the
 // kernels live in build.cuh / search.cuh / scan_sort.cuh. Compiled for sm_100a.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -18,7 +19,9 @@ struct di_index {
     int device = 0;
     uint32_t n_terms = 0, doc_lo = 0, doc_hi = 0;
     uint32_t n_tiles = 0, tile_docs = 0, tile_shift = 0, max_docid_plus1 = 0;
-    uint32_t dense_ratio = 8, cand_slack = 0;
+    uint32_t dense_ratio = 8, cand_slack = 0, flags = 0;
+    bool has_dup_postings = false;  // some posting list names a document twice: no seeds, 32-bit accumulators
+    uint32_t last_lanes = 0, last_acc32 = 0;
     uint64_t n_postings = 0, payload_bytes = 0, table_bytes = 0;
     uint64_t n_dense_segments = 0, n_sparse_segments = 0, n_dense_postings = 0;
     SegDesc *d_desc = nullptr;
@@ -249,9 +252,8 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
             return set_error(DI_ERR_RANGE, "shard spans more than 65535 tiles of %u docs; raise tile_docs or shard further",
                              ix->tile_docs);
         // threshold seeds: impact histograms of the frequent terms over the same visible postings
-        static const bool no_seeds = getenv("DI_B200_NO_SEEDS") != nullptr;  // tuning switch only
         const uint64_t max_slots = std::min<uint64_t>(V, n_post / kSeedMinDf);
-        if (max_slots && !no_seeds) {
+        if (max_slots && !(ix->flags & DI_INDEX_NO_SEEDS)) {
             DevBuf d_cnt;
             DI_TRY(d_cnt.alloc(4));
             DI_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4, st));
@@ -309,6 +311,7 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
     DI_CUDA(cudaMemcpyAsync(&total16, d_size.as<uint32_t>() + n_segs, 4, cudaMemcpyDeviceToHost, st));
     DI_CUDA(cudaMemcpyAsync(&stats, d_stats.p, sizeof stats, cudaMemcpyDeviceToHost, st));
     DI_CUDA(cudaStreamSynchronize(st));
+    ix->has_dup_postings = stats.n_dup_segments != 0;
     if (stats.n_dup_segments && ix->d_seed_cum) {  // a posting list that names a document twice: k postings != k documents
         cudaFree(ix->d_seed_cum);
         cudaFree(ix->d_seed_slot);
@@ -350,6 +353,9 @@ static int new_index(uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const d
     while ((1u << ix->tile_shift) < tile_docs) ++ix->tile_shift;
     ix->dense_ratio = params && params->dense_ratio ? params->dense_ratio : 8u;
     ix->cand_slack = params ? params->cand_slack : 0u;
+    ix->flags = params ? params->flags : 0u;
+    if (getenv("DI_B200_NO_SEEDS")) ix->flags |= DI_INDEX_NO_SEEDS;   // tuning switches only
+    if (getenv("DI_B200_PER_TILE")) ix->flags |= DI_INDEX_PER_TILE;
     cudaDeviceGetAttribute(&ix->smem_opt_in, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device);
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -387,11 +393,14 @@ extern "C" int di_index_create_csr(const uint64_t *term_offsets, const uint32_t 
     DI_TRY(d_to.alloc(((size_t)n_terms + 1) * sizeof(uint64_t)));
     DI_TRY(d_d.alloc(P * sizeof(uint32_t)));
     DI_TRY(d_v.alloc(P));
+    // the build runs on the index's own non-blocking stream, which is NOT ordered after the legacy stream:
+    // finish the pageable copies before the first kernel can read them
     DI_CUDA(cudaMemcpy(d_to.p, term_offsets, ((size_t)n_terms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     if (P) {
         DI_CUDA(cudaMemcpy(d_d.p, docids, P * sizeof(uint32_t), cudaMemcpyHostToDevice));
         DI_CUDA(cudaMemcpy(d_v.p, impacts, P, cudaMemcpyHostToDevice));
     }
+    DI_CUDA(cudaDeviceSynchronize());
     return di_index_create_csr_dev(d_to.as<uint64_t>(), d_d.as<uint32_t>(), d_v.as<uint8_t>(), n_terms, P, doc_lo, doc_hi,
                                    params, out);
 }
@@ -484,10 +493,14 @@ static uint32_t pow2_ceil(uint32_t x)
 static int launch_finalize(uint64_t *cand, const uint32_t *cnt, uint32_t cap, uint32_t top_k,
                            uint32_t max_n, uint32_t n_queries, uint64_t *out_keys, uint32_t *out_counts, cudaStream_t st)
 {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    // function attributes belong to a device: remember per device (not per thread) that the opt-in is done
+    static std::atomic<uint64_t> attr_done{0};
+    int dev = 0;
+    DI_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
         DI_CUDA(cudaFuncSetAttribute(finalize_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-        attr_set = true;
+        attr_done.fetch_or(bit, std::memory_order_release);
     }
     uint32_t smem_keys = kSortSmemKeys;
     while (smem_keys < max_n && smem_keys < 16384) smem_keys <<= 1;
@@ -515,7 +528,8 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     // timings accumulate over calls until di_get_timings() reads (and clears) them
     if (n_queries == 0) return DI_OK;
 
-    const bool acc32 = max_query_len > 257;  // 257 * 255 = 65535 still fits a u16 accumulator
+    // 257 * 255 = 65535 still fits a u16 accumulator — as long as a term adds to a document at most once
+    const bool acc32 = max_query_len > 257 || ix->has_dup_postings;
     const size_t acc_bytes = (size_t)ix->tile_docs * (acc32 ? 4 : 2);
     if ((int)acc_bytes + 4096 > ix->smem_opt_in)
         return set_error(DI_ERR_ARG, "tile of %u docs needs %zu B of shared memory for %d-bit accumulators (limit %d); "
@@ -539,7 +553,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
                                      cudaSharedmemCarveoutMaxShared));
         ix->attr_set16 = true;
     }
-    static const bool per_tile_launches = getenv("DI_B200_PER_TILE") != nullptr;
+    const bool per_tile_launches = (ix->flags & DI_INDEX_PER_TILE) != 0;
     int ctas_per_sm = 0, n_sms = 0;
     if (acc32)
         DI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, score_persistent_kernel<true>, kScoreThreads, acc_bytes));
@@ -564,6 +578,8 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     const uint32_t tiles_per_lane = ix->n_tiles ? (ix->n_tiles + lanes - 1) / lanes : 0;
     if (tiles_per_lane) lanes = (ix->n_tiles + tiles_per_lane - 1) / tiles_per_lane;
     const size_t n_virtual = (size_t)batch * lanes;
+    ix->last_lanes = lanes;
+    ix->last_acc32 = acc32 ? 1u : 0u;
     DI_TRY(ensure(ix->ws_cand, n_virtual * per_query));
     DI_TRY(ensure(ix->ws_cnt, n_virtual * 4));
     DI_TRY(ensure(ix->ws_theta, n_virtual * 8));
@@ -757,11 +773,12 @@ extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_co
     if (k_in == 0 || k_in > 65536) return set_error(DI_ERR_ARG, "k_in must be in [1, 65536], got %u", k_in);
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t cap = pow2_ceil(std::max(n_shards * k_in, top_k));
-    // scratch is cached per host thread (one process per GPU drives one merge stream) and only
-    // grows, so the steady state has no allocation and the call stays asynchronous
-    static thread_local DevBuf cand, cnt;
-    DI_TRY(ensure(cand, (size_t)n_queries * cap * 8));
-    DI_TRY(ensure(cnt, (size_t)n_queries * 4));
+    // scratch comes from the device's stream-ordered pool: it belongs to this call's device and stream, so
+    // merges on several devices or streams of one thread cannot share (and race on) it; after the first call
+    // the pool serves it without a driver allocation and the call stays asynchronous
+    StreamBuf cand(st), cnt(st);
+    DI_TRY(cand.alloc((size_t)n_queries * cap * 8));
+    DI_TRY(cnt.alloc((size_t)n_queries * 4));
     merge_gather_kernel<<<n_queries, 256, 0, st>>>(d_keys_in, d_counts_in, n_shards, n_queries, k_in, cand.as<uint64_t>(),
                                                   cnt.as<uint32_t>(), cap);
     DI_KERNEL_CHECK();
@@ -787,9 +804,9 @@ extern "C" int di_merge_rows_p2p_dev(const uint64_t *const *d_rows, const uint32
     if (k_in == 0 || k_in > row_stride) return set_error(DI_ERR_ARG, "k_in must be in [1, row_stride = %u], got %u", row_stride, k_in);
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t cap = pow2_ceil(std::max(n_shards * k_in, top_k));
-    static thread_local DevBuf cand, cnt;  // like di_merge_topk_dev: cached per host thread, only grows
-    DI_TRY(ensure(cand, (size_t)n_queries * cap * 8));
-    DI_TRY(ensure(cnt, (size_t)n_queries * 4));
+    StreamBuf cand(st), cnt(st);  // like di_merge_topk_dev
+    DI_TRY(cand.alloc((size_t)n_queries * cap * 8));
+    DI_TRY(cnt.alloc((size_t)n_queries * 4));
     merge_gather_p2p_kernel<<<n_queries, 256, 0, st>>>(d_rows, d_counts, n_shards, d_query_ids, row_stride, k_in,
                                                       cand.as<uint64_t>(), cnt.as<uint32_t>(), cap);
     DI_KERNEL_CHECK();
@@ -824,6 +841,8 @@ extern "C" int di_get_timings(di_index_t *ix, di_timings *out)
     }
     out->score_launches = ix->score_launches;
     out->other_launches = ix->other_launches;
+    out->lanes = ix->last_lanes;
+    out->acc32 = ix->last_acc32;
     ix->n_batches = 0;
     ix->score_launches = ix->other_launches = 0;
     return DI_OK;

@@ -4,17 +4,20 @@
 // Replaces the two hot loops of InvertedIndex.score (inverted_index.py:57-60: read the term's
 // postings, scores[doc] += impact) and of SparseSearch.search (nano_beir_evaluator.py:118-121).
 //
-// One CTA = one (query, tile) work item.
-//   phase 1  dense segments (one impact byte per document of the tile, 128-bit loads) are widened and
-//            summed in registers and STORED into the shared-memory accumulators — this also zeroes them;
-//   phase 2  sparse segments (u32 postings) of all the query's terms are flattened into one index
+// One CTA = one (query, tile) work item. The shared-memory accumulators are ZERO when an item starts
+// (invariant of the 16-bit form: every pass that reads an accumulator word leaves a zero behind).
+//   phase 1  sparse segments (u32 postings) of all the query's terms are flattened into one index
 //            space, streamed with 128-bit loads and added with shared-memory atomics;
-//   phase 3  the accumulators are scanned once (a register bit mask per thread marks the groups that hold
-//            a document at or above the query's threshold); those groups are then expanded with every lane
-//            busy and the surviving keys (score, ~docid) appended to the query's candidate list in global
-//            memory. Every query starts from a PROVEN threshold (build.cuh, threshold seeds).
+//   phase 2  ONE fused pass over the tile: dense segments (one impact byte per document, 128-bit loads)
+//            are widened and summed in registers on top of the accumulator words, the sums are tested
+//            against the query's threshold while still in registers (a bit per 8-document group in a
+//            per-thread mask), and the word is written back as zero — or as the sum for the rare group
+//            that holds a candidate. No separate store / scan passes, no barrier between them;
+//   phase 3  the hit groups are expanded with every lane busy and the surviving keys (score, ~docid)
+//            appended to the query's candidate list in global memory. Every query starts from a PROVEN
+//            threshold (build.cuh, threshold seeds).
 // Accumulators are u16 pairs packed in 32-bit words (ACC32 = false; queries of <= 257 terms cannot
-// overflow 16 bits) or u32 (ACC32 = true).
+// overflow 16 bits) or u32 (ACC32 = true: long queries, zeroed at item start, separate scan pass).
 #pragma once
 
 #include "build.cuh"
@@ -127,11 +130,34 @@ __global__ void __launch_bounds__(1024) query_order_kernel(const uint32_t *__res
     }
 }
 
-// ---- phase 1 helpers: NB dense segments, 16 documents per 128-bit load -----------------------
+// ---- accumulator groups ----------------------------------------------------------------------
+// Accumulators are handled in groups of one 128-bit word: 8 documents (u16 pairs) or 4 (u32).
+template <bool ACC32> __device__ __forceinline__ constexpr int group_docs() { return ACC32 ? 4 : 8; }
+
+template <bool ACC32> __device__ __forceinline__ uint32_t group_score(const uint4 &x, int i)
+{
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    if (ACC32) return w[i];
+    return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+}
+
+// does the group hold a document with score >= ths?  (tm2 = (ths - 1) in both u16 halves)
+template <bool ACC32>
+__device__ __forceinline__ bool group_hit(const uint4 &x, uint32_t ths, uint32_t tm2)
+{
+    if (!ACC32) {  // per-lane max of the four words (3-input SIMD max), one more max against the threshold
+        const uint32_t m = __vmaxu2(__vmaxu2(x.x, x.y), __vmaxu2(x.z, x.w));
+        return __vmaxu2(m, tm2) != tm2;
+    }
+    return max(max(x.x, x.y), max(x.z, x.w)) >= ths;
+}
+
+// ---- dense segments, 16 documents per 128-bit load ---------------------------------------------
 // A dense segment stores one BYTE per document of the tile. 16-byte unit u holds documents 8u .. 8u+7 and
 // 8(u+H) .. 8(u+H)+7 (H = tile_docs / 16 units), i.e. the accumulator words s_acc4[u] and s_acc4[u + H]: a
-// warp's stores stay contiguous (no bank conflicts) and a byte pair widens to a packed u16 accumulator word
-// with one PRMT.
+// warp's accesses stay contiguous (no bank conflicts) and a byte pair widens to a packed u16 accumulator word
+// with one PRMT. Thread t always owns the units u = t (mod block size), whatever NB is, so consecutive passes
+// over the same words need no barrier.
 __device__ __forceinline__ void add_bytes8(uint4 &a, uint32_t lo, uint32_t hi)
 {
     a.x += __byte_perm(lo, 0, 0x4140);
@@ -140,14 +166,20 @@ __device__ __forceinline__ void add_bytes8(uint4 &a, uint32_t lo, uint32_t hi)
     a.w += __byte_perm(hi, 0, 0x4342);
 }
 
-// FULL: units is a multiple of the step (U * threads), so no load or store needs a bounds predicate
-template <int NB, bool INIT, bool FULL>
-__device__ __forceinline__ void dense_steps16(uint4 *s_acc4, const uint4 *const (&ptr)[4], uint32_t units)
+// Adds NB dense segments on top of the accumulator words.
+//   FUSE = false: plain read-modify-write (dense terms beyond the four of the fused pass).
+//   FUSE = true : the sums are tested against the threshold in registers; a word goes back as ZERO unless its
+//                 group holds a candidate (then the sums are kept for expand_hits). Returns the thread's hit
+//                 mask: bit 2j (+1) = the group of its j-th unit in the lower (upper) half of the tile.
+// FULL: units is a multiple of the step (U * threads), so no load or store needs a bounds predicate.
+template <int NB, bool FUSE, bool FULL>
+__device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *const (&ptr)[4], uint32_t units, uint32_t tm2)
 {
     // U units per step so that about 8 independent 128-bit loads are in flight per thread whatever
     // the number of dense terms (a work item is latency-bound: few CTAs per SM, L2-resident postings)
     constexpr int U = NB <= 1 ? 8 : (NB == 2 ? 4 : 2);
-    for (uint32_t g0 = threadIdx.x; g0 < units; g0 += U * kScoreThreads) {
+    uint32_t mask = 0, ord = 0;
+    for (uint32_t g0 = threadIdx.x; g0 < units; g0 += U * kScoreThreads, ord += U) {
         uint4 v[U][NB > 0 ? NB : 1];
 #pragma unroll
         for (int s = 0; s < U; ++s) {
@@ -160,62 +192,64 @@ __device__ __forceinline__ void dense_steps16(uint4 *s_acc4, const uint4 *const 
         for (int s = 0; s < U; ++s) {
             const uint32_t g = g0 + s * kScoreThreads;
             if (FULL || g < units) {
-                uint4 a = INIT ? make_uint4(0, 0, 0, 0) : s_acc4[g];
-                uint4 b = INIT ? make_uint4(0, 0, 0, 0) : s_acc4[g + units];
+                uint4 a = s_acc4[g];
+                uint4 b = s_acc4[g + units];
 #pragma unroll
                 for (int u = 0; u < NB; ++u) {
                     add_bytes8(a, v[s][u].x, v[s][u].y);
                     add_bytes8(b, v[s][u].z, v[s][u].w);
                 }
-                s_acc4[g] = a;
-                s_acc4[g + units] = b;
+                if (!FUSE) {
+                    s_acc4[g] = a;
+                    s_acc4[g + units] = b;
+                } else {
+                    const bool ha = group_hit<false>(a, 0, tm2), hb = group_hit<false>(b, 0, tm2);
+                    s_acc4[g] = ha ? a : make_uint4(0, 0, 0, 0);
+                    s_acc4[g + units] = hb ? b : make_uint4(0, 0, 0, 0);
+                    mask |= ((ha ? 1u : 0u) | (hb ? 2u : 0u)) << (2 * (ord + s));
+                }
             }
         }
     }
+    return mask;
 }
 
-template <int NB, bool INIT>
-__device__ __forceinline__ void dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
-                                             const uint4 *p3, uint32_t units)
+template <int NB, bool FUSE>
+__device__ __forceinline__ uint32_t dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
+                                                 const uint4 *p3, uint32_t units, uint32_t tm2)
 {
     const uint4 *const ptr[4] = {p0, p1, p2, p3};
-    // tiles of >= 16 K documents (the default) have only full steps; INIT = false is the rare fifth dense term
-    if (INIT && units % (8 * kScoreThreads) == 0) dense_steps16<NB, INIT, true>(s_acc4, ptr, units);
-    else dense_steps16<NB, INIT, false>(s_acc4, ptr, units);
+    // tiles of >= 16 K documents (the default) have only full steps
+    if (FUSE && units % (8 * kScoreThreads) == 0) return dense_steps16<NB, FUSE, true>(s_acc4, ptr, units, tm2);
+    return dense_steps16<NB, FUSE, false>(s_acc4, ptr, units, tm2);
 }
 
-template <bool INIT>
-__device__ __forceinline__ void dense_dispatch16(int nb, uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff,
-                                                 uint32_t groups)
+template <bool FUSE>
+__device__ __forceinline__ uint32_t dense_dispatch16(int nb, uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff,
+                                                     uint32_t units, uint32_t tm2)
 {
     const uint4 *p0 = payload4 + doff[0], *p1 = payload4 + doff[1], *p2 = payload4 + doff[2], *p3 = payload4 + doff[3];
     switch (nb) {  // nb is uniform across the CTA
-        case 4: dense_pass16<4, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
-        case 3: dense_pass16<3, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
-        case 2: dense_pass16<2, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
-        case 1: dense_pass16<1, INIT>(s_acc4, p0, p1, p2, p3, groups); break;
-        default: if (INIT) dense_pass16<0, true>(s_acc4, p0, p1, p2, p3, groups); break;
+        case 4: return dense_pass16<4, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
+        case 3: return dense_pass16<3, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
+        case 2: return dense_pass16<2, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
+        case 1: return dense_pass16<1, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
+        default: return FUSE ? dense_pass16<0, true>(s_acc4, p0, p1, p2, p3, units, tm2) : 0u;
     }
 }
 
-// ACC32 twin (long queries only): plain loop; the unit's two 8-document halves go to accumulator words
-// 2u, 2u+1 and 2(u+H), 2(u+H)+1
-template <bool INIT>
+// ACC32 twin (long queries only): plain read-modify-write loop; the unit's two 8-document halves go to
+// accumulator words 2u, 2u+1 and 2(u+H), 2(u+H)+1
 __device__ __forceinline__ void dense_pass32(uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff, int nb,
                                              uint32_t units)
 {
     for (uint32_t g = threadIdx.x; g < units; g += kScoreThreads) {
         uint32_t a[16];
-        if (INIT) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = 0;
-        } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint4 lo = s_acc4[2 * (g + h * units)], hi = s_acc4[2 * (g + h * units) + 1];
-                a[8 * h + 0] = lo.x; a[8 * h + 1] = lo.y; a[8 * h + 2] = lo.z; a[8 * h + 3] = lo.w;
-                a[8 * h + 4] = hi.x; a[8 * h + 5] = hi.y; a[8 * h + 6] = hi.z; a[8 * h + 7] = hi.w;
-            }
+        for (int h = 0; h < 2; ++h) {
+            const uint4 lo = s_acc4[2 * (g + h * units)], hi = s_acc4[2 * (g + h * units) + 1];
+            a[8 * h + 0] = lo.x; a[8 * h + 1] = lo.y; a[8 * h + 2] = lo.z; a[8 * h + 3] = lo.w;
+            a[8 * h + 4] = hi.x; a[8 * h + 5] = hi.y; a[8 * h + 6] = hi.z; a[8 * h + 7] = hi.w;
         }
         for (int j = 0; j < nb; ++j) {
             const uint4 v = ldg_stream_v4(payload4 + doff[j] + g);
@@ -231,17 +265,7 @@ __device__ __forceinline__ void dense_pass32(uint4 *s_acc4, const uint4 *payload
     }
 }
 
-// ---- phase 3 helpers ------------------------------------------------------------------------
-// Accumulators are read in groups of one 128-bit word: 8 documents (u16 pairs) or 4 (u32).
-template <bool ACC32> __device__ __forceinline__ constexpr int group_docs() { return ACC32 ? 4 : 8; }
-
-template <bool ACC32> __device__ __forceinline__ uint32_t group_score(const uint4 &x, int i)
-{
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-    if (ACC32) return w[i];
-    return (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
-}
-
+// ---- hit groups -> candidates ----------------------------------------------------------------
 // slow path (list already holds more than kHistBins hit groups): one shared-memory atomic per candidate
 template <bool ACC32>
 __device__ __forceinline__ void emit_group(const uint4 &x, uint32_t g, uint32_t ths, uint32_t doc_base, uint64_t theta,
@@ -257,24 +281,38 @@ __device__ __forceinline__ void emit_group(const uint4 &x, uint32_t g, uint32_t 
     }
 }
 
-// One pass over the tile's accumulators: groups holding a document with score >= ths are REMEMBERED in
-// s_hits (first kHistBins of them; *s_nhits counts all). Emitting on the spot would run the key / compare /
-// append sequence with one or two lanes active; expand_hits() does it with every lane busy.
-// INPLACE: groups beyond the kHistBins slots are emitted on the spot instead of being dropped.
-template <bool ACC32>
-__device__ __forceinline__ bool group_hit(const uint4 &x, uint32_t ths, uint32_t tm2)
+// The fused pass leaves one hit mask per thread; the warp compacts them into the hit-group list s_hits with
+// one prefix sum and one shared-memory atomic (first kHistBins groups are remembered; *s_nhits counts all).
+__device__ __forceinline__ void record_hits16(uint32_t mask, uint32_t units, uint32_t *s_hits, uint32_t *s_nhits)
 {
-    if (!ACC32) {  // per-lane max of the four words (3-input SIMD max), one more max against the threshold
-        const uint32_t m = __vmaxu2(__vmaxu2(x.x, x.y), __vmaxu2(x.z, x.w));
-        return __vmaxu2(m, tm2) != tm2;
+    if (!__any_sync(0xffffffffu, mask != 0)) return;  // the usual case once the query has a threshold
+    const uint32_t lane = lane_id(), c = __popc(mask);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += up;
     }
-    return max(max(x.x, x.y), max(x.z, x.w)) >= ths;
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(s_nhits, incl);
+    uint32_t slot = __shfl_sync(0xffffffffu, base, 31) + incl - c;
+    while (mask) {
+        const uint32_t bit = (uint32_t)(__ffs(mask) - 1);
+        mask &= mask - 1u;
+        if (slot < (uint32_t)kHistBins) s_hits[slot] = threadIdx.x + (bit >> 1) * kScoreThreads + ((bit & 1u) ? units : 0u);
+        ++slot;
+    }
 }
 
-// The hot loop only sets a bit per hit group in a per-thread register mask (no branch, no atomic); after every
-// 32 steps the warp compacts its masks into s_hits with one prefix sum and one shared-memory atomic.
+// One pass over the tile's accumulators (32-bit form, and the rare flooded 16-bit tile): groups holding a
+// document with score >= ths are REMEMBERED in s_hits (first kHistBins of them; *s_nhits counts all). Emitting on
+// the spot would run the key / compare / append sequence with one or two lanes active; expand_hits() does it
+// with every lane busy. The hot loop only sets a bit per hit group in a per-thread register mask (no branch,
+// no atomic); after every 32 steps the warp compacts its masks with one prefix sum and one atomic.
+// INPLACE: groups beyond the kHistBins slots are emitted on the spot instead of being dropped.
+// The 16-bit form keeps its invariant here too: whatever is not handed to expand_hits is zeroed.
 template <bool ACC32, bool INPLACE>
-__device__ __forceinline__ void scan_groups(const uint4 *s_acc4, uint32_t T, uint32_t ths, uint32_t *s_hits,
+__device__ __forceinline__ void scan_groups(uint4 *s_acc4, uint32_t T, uint32_t ths, uint32_t *s_hits,
                                             uint32_t *s_nhits, uint32_t doc_base, uint64_t theta, uint64_t *cand,
                                             uint32_t cnt0, uint32_t *s_emit)
 {
@@ -293,11 +331,14 @@ __device__ __forceinline__ void scan_groups(const uint4 *s_acc4, uint32_t T, uin
                     x[i] = g < groups ? s_acc4[g] : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t g = c0 + (i0 + i) * kScoreThreads;
                     if (group_hit<ACC32>(x[i], ths, tm2)) mask |= 1u << (i0 + i);
+                    else if (!ACC32 && g < groups) s_acc4[g] = make_uint4(0, 0, 0, 0);
+                }
             }
         }
-        if (!__any_sync(0xffffffffu, mask != 0)) continue;  // the usual case once the query has a threshold
+        if (!__any_sync(0xffffffffu, mask != 0)) continue;
         const uint32_t c = __popc(mask);
         uint32_t incl = c;
 #pragma unroll
@@ -311,17 +352,22 @@ __device__ __forceinline__ void scan_groups(const uint4 *s_acc4, uint32_t T, uin
         while (mask) {
             const uint32_t g = c0 + (uint32_t)(__ffs(mask) - 1) * kScoreThreads;
             mask &= mask - 1u;
-            if (slot < (uint32_t)kHistBins) s_hits[slot] = g;
-            else if (INPLACE) emit_group<ACC32>(s_acc4[g], g, ths, doc_base, theta, cand, cnt0, s_emit);
+            if (slot < (uint32_t)kHistBins) {
+                s_hits[slot] = g;
+            } else {
+                if (INPLACE) emit_group<ACC32>(s_acc4[g], g, ths, doc_base, theta, cand, cnt0, s_emit);
+                if (!ACC32) s_acc4[g] = make_uint4(0, 0, 0, 0);
+            }
             ++slot;
         }
     }
 }
 
 // Appends the candidates of the remembered groups: one group per lane, ONE shared-memory atomic per warp
-// (warp prefix sum of the per-lane counts), keys written to cand[cnt0 + ...] in arbitrary order.
+// (warp prefix sum of the per-lane counts), keys written to cand[cnt0 + ...] in arbitrary order. The 16-bit
+// form zeroes each group behind itself (accumulator invariant).
 template <bool ACC32>
-__device__ __forceinline__ void expand_hits(const uint4 *s_acc4, const uint32_t *s_hits, uint32_t n_hits, uint32_t ths,
+__device__ __forceinline__ void expand_hits(uint4 *s_acc4, const uint32_t *s_hits, uint32_t n_hits, uint32_t ths,
                                             uint32_t doc_base, uint64_t theta, uint64_t *cand, uint32_t cnt0,
                                             uint32_t *s_emit)
 {
@@ -333,6 +379,7 @@ __device__ __forceinline__ void expand_hits(const uint4 *s_acc4, const uint32_t 
         if (j < n_hits) {
             g = s_hits[j];
             x = s_acc4[g];
+            if (!ACC32) s_acc4[g] = make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int i = 0; i < group_docs<ACC32>(); ++i) {
                 const uint32_t sc = group_score<ACC32>(x, i);
@@ -356,17 +403,22 @@ __device__ __forceinline__ void expand_hits(const uint4 *s_acc4, const uint32_t 
     }
 }
 
+__device__ __forceinline__ void zero_words16(uint4 *s, uint32_t n16)
+{
+    for (uint32_t i = threadIdx.x; i < n16; i += kScoreThreads) s[i] = make_uint4(0, 0, 0, 0);
+}
+
 // One (query, tile) work item; `slot` indexes the batch's launch-ordered query records.
 template <bool ACC32>
 __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, uint32_t slot, uint32_t lane, uint32_t step)
 {
+    static_assert(kMaxSeg == 32, "the segment lookup is one warp wide");
     extern __shared__ uint4 s_acc4[];  // tile accumulators
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_acc4);
     __shared__ uint32_t s_doff[kMaxSeg];       // dense segments of this round: payload offset (16 B units)
     __shared__ uint32_t s_soff[kMaxSeg];       // sparse segments: payload offset
-    __shared__ uint32_t s_sunits[kMaxSeg];     // sparse segments: total 16 B units
     __shared__ uint32_t s_seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
-    __shared__ uint32_t s_spref[kMaxSeg + 1];  // exclusive prefix of s_sunits
+    __shared__ uint32_t s_spref[kMaxSeg + 1];  // exclusive prefix of the sparse segments' unit counts
     __shared__ uint32_t s_nd, s_ns, s_emit, s_ready, s_nhits;
     __shared__ __align__(16) uint32_t s_hist[kHistBins];  // score histogram / hit-group list / radix-select scratch
     __shared__ uint32_t s_scan[33];
@@ -379,121 +431,127 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     const uint32_t q = rec->q;
     const uint32_t sq = lane * p.n_queries + q;  // this (lane, query)'s slot in the per-query state arrays
     const uint64_t qb = rec->begin, qe = rec->begin + rec->n;
-    const uint32_t T = p.tile_docs;
+    const uint32_t T = p.tile_docs, units = T >> kDenseUnitShift;
     // The query's running state (threshold, candidate list) is handed from tile to tile through
     // global memory; tile t may start once tile t-1 of the same query has published (done[q] >= t).
     // Items are dispatched in tile-major order, so this is almost always already true: probe now,
-    // and only wait (before phase 3) in the rare case it is not.
+    // and only wait (before the fused pass) in the rare case it is not.
     if (tid == 0) s_ready = p.done == nullptr || step == 0 || ld_flag_u32(p.done + sq) >= step;
     const SegDesc *__restrict__ desc = p.desc + (uint64_t)tile * p.n_terms;
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
 
     DI_PROF_DECL;
     uint64_t theta = 0;
-    uint32_t cnt0 = 0;
+    uint32_t cnt0 = 0, f0 = 0, nf = 0;  // s_doff[f0 .. f0 + nf): dense segments left for the fused pass
     bool first = true, touched = false, have_state = false;
     for (uint64_t r0 = qb; first || r0 < qe; r0 += kMaxSeg) {
-        // ---- look up this round's (term, tile) segments
-        if (tid == 0) { s_nd = 0; s_ns = 0; }
-        __syncthreads();
-        if (tid < kMaxSeg && r0 + tid < qe) {
-            const uint32_t t = (first && tid < kRecInlineTerms) ? rec->terms[tid] : p.q_terms[r0 + tid];
-            if (t < p.n_terms) {  // DI_OOV_TERM and anything out of range: no postings
-                const SegDesc d = desc[t];
-                if (d.n_flag & kDenseFlag) {
-                    s_doff[atomicAdd(&s_nd, 1u)] = d.off16;
-                } else if (d.n_flag) {
-                    const uint32_t j = atomicAdd(&s_ns, 1u);
-                    s_soff[j] = d.off16;
-                    s_sunits[j] = d.n_flag & 0xFFFFu;
-                    s_seven[j] = d.n_flag >> 16;
-                }
+        if (!first) __syncthreads();  // the previous round's readers of the segment lists are done
+        // ---- look up this round's (term, tile) segments: warp 0, one term per lane, ballot-compacted
+        if (tid < kMaxSeg) {
+            SegDesc d{0u, 0u};
+            if (r0 + tid < qe) {
+                const uint32_t t = (first && tid < kRecInlineTerms) ? rec->terms[tid] : p.q_terms[r0 + tid];
+                if (t < p.n_terms) d = desc[t];  // DI_OOV_TERM and anything out of range: no postings
             }
+            const bool is_dense = (d.n_flag & kDenseFlag) != 0, is_sparse = !is_dense && d.n_flag != 0;
+            const uint32_t bd = __ballot_sync(0xffffffffu, is_dense), bs = __ballot_sync(0xffffffffu, is_sparse);
+            const uint32_t su = is_sparse ? (d.n_flag & 0xFFFFu) : 0u;
+            uint32_t incl = su;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= (unsigned)o) incl += up;
+            }
+            if (is_dense) s_doff[__popc(bd & lanemask_lt())] = d.off16;
+            if (is_sparse) {
+                const uint32_t j = __popc(bs & lanemask_lt());
+                s_soff[j] = d.off16;
+                s_seven[j] = d.n_flag >> 16;
+                s_spref[j] = incl - su;
+            }
+            if (tid == 31) s_spref[__popc(bs)] = incl;  // total units
+            if (tid == 0) { s_nd = __popc(bd); s_ns = __popc(bs); }
         }
+        if (ACC32 && first) zero_words16(s_acc4, T / 4);  // overlaps the descriptor loads of warp 0
         __syncthreads();
         const uint32_t nd = s_nd, ns = s_ns;
-        if (first && r0 + kMaxSeg >= qe && nd + ns == 0) return false;  // query has no posting in this tile
-        if (first && s_ready) {  // state already published: fetch it now (L2), it is needed only in phase 3
+        const bool last = r0 + kMaxSeg >= qe;
+        if (first && last && nd + ns == 0) return false;  // query has no posting in this tile
+        if (first && s_ready) {  // state already published: fetch it now (L2), it is needed only by the fused pass
             theta = ld_cg_u64(p.theta + sq);
             cnt0 = ld_cg_u32(p.cnt + sq);
             have_state = true;
         }
         touched = touched || (nd + ns) != 0;
         DI_PROF_MARK(0);  // segment lookup
-        if (tid == 0) {
-            uint32_t run = 0;
-            for (uint32_t j = 0; j < ns; ++j) { s_spref[j] = run; run += s_sunits[j]; }
-            s_spref[ns] = run;
-        }
 
-        // ---- phase 1: dense segments; the very first pass stores (and thereby zeroes) the accumulators
-        if (!ACC32) {
-            if (first) dense_dispatch16<true>(nd < 4 ? (int)nd : 4, s_acc4, payload4, s_doff, T >> kDenseUnitShift);
-            // later batches read-modify-write the same words the same thread wrote: no barrier needed
-            for (uint32_t j0 = first ? 4 : 0; j0 < nd; j0 += 4) {
-                dense_dispatch16<false>(nd - j0 < 4 ? (int)(nd - j0) : 4, s_acc4, payload4, s_doff + j0, T >> kDenseUnitShift);
-            }
-        } else {
-            if (first) dense_pass32<true>(s_acc4, payload4, s_doff, (int)nd, T >> kDenseUnitShift);
-            else if (nd) dense_pass32<false>(s_acc4, payload4, s_doff, (int)nd, T >> kDenseUnitShift);
-        }
-        __syncthreads();
-        DI_PROF_MARK(1);  // dense
-
-        // ---- phase 2: sparse segments. word = impact << 16 | byte offset of the accumulator word;
+        // ---- phase 1: sparse segments. word = impact << 16 | byte offset of the accumulator word;
         //      units [0, even) of a segment hold even documents, the rest odd ones.
-        const uint32_t total = s_spref[ns];
-        // the current segment's bounds live in registers and are re-read only when a unit crosses into the
-        // next segment (segments are hundreds of units long for the terms queries actually use)
-        uint32_t seg = 0, seg_lo = 0, seg_hi = s_spref[1], seg_even = s_seven[0], seg_off = s_soff[0];
-        for (uint32_t u0 = tid; u0 < total; u0 += kSparseUnroll * kScoreThreads) {
-            uint4 v[kSparseUnroll];
-            bool odd[kSparseUnroll];
+        if (ns) {
+            const uint32_t total = s_spref[ns];
+            // the current segment's bounds live in registers and are re-read only when a unit crosses into the
+            // next segment (segments are hundreds of units long for the terms queries actually use)
+            uint32_t seg = 0, seg_lo = 0, seg_hi = s_spref[1], seg_even = s_seven[0], seg_off = s_soff[0];
+            for (uint32_t u0 = tid; u0 < total; u0 += kSparseUnroll * kScoreThreads) {
+                uint4 v[kSparseUnroll];
+                bool odd[kSparseUnroll];
 #pragma unroll
-            for (int j = 0; j < kSparseUnroll; ++j) {
-                const uint32_t u = u0 + j * kScoreThreads;
-                odd[j] = false;
-                if (u < total) {
-                    if (u >= seg_hi) {
-                        do { ++seg; seg_hi = s_spref[seg + 1]; } while (u >= seg_hi);
-                        seg_lo = s_spref[seg];
-                        seg_even = s_seven[seg];
-                        seg_off = s_soff[seg];
-                    }
-                    const uint32_t lu = u - seg_lo;
-                    odd[j] = lu >= seg_even;
-                    v[j] = ldg_stream_v4(payload4 + seg_off + lu);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kSparseUnroll; ++j) {
-                if (u0 + j * kScoreThreads < total) {
-                    const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                    if (!ACC32) {
-                        char *base = reinterpret_cast<char *>(s_acc);
-                        if (!odd[j]) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] >> 16);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] & 0xFFFF0000u);
+                for (int j = 0; j < kSparseUnroll; ++j) {
+                    const uint32_t u = u0 + j * kScoreThreads;
+                    odd[j] = false;
+                    if (u < total) {
+                        if (u >= seg_hi) {
+                            do { ++seg; seg_hi = s_spref[seg + 1]; } while (u >= seg_hi);
+                            seg_lo = s_spref[seg];
+                            seg_even = s_seven[seg];
+                            seg_off = s_soff[seg];
                         }
-                    } else {
-                        const uint32_t par = odd[j] ? 1u : 0u;
+                        const uint32_t lu = u - seg_lo;
+                        odd[j] = lu >= seg_even;
+                        v[j] = ldg_stream_v4(payload4 + seg_off + lu);
+                    }
+                }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[((w[i] & 0xFFFFu) >> 1) | par], w[i] >> 16);
+                for (int j = 0; j < kSparseUnroll; ++j) {
+                    if (u0 + j * kScoreThreads < total) {
+                        const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                        if (!ACC32) {
+                            char *base = reinterpret_cast<char *>(s_acc);
+                            if (!odd[j]) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] >> 16);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] & 0xFFFF0000u);
+                            }
+                        } else {
+                            const uint32_t par = odd[j] ? 1u : 0u;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[((w[i] & 0xFFFFu) >> 1) | par], w[i] >> 16);
+                        }
                     }
                 }
             }
+            __syncthreads();  // every atomic has landed before a thread reads its own accumulator words
         }
-        __syncthreads();
         DI_PROF_MARK(2);  // sparse
+
+        // ---- dense segments that do not go through the fused pass: plain read-modify-write
+        nf = (!ACC32 && last) ? min(nd, 4u) : 0u;
+        f0 = nd - nf;
+        if (!ACC32) {
+            for (uint32_t j0 = 0; j0 < f0; j0 += 4)
+                dense_dispatch16<false>(f0 - j0 < 4 ? (int)(f0 - j0) : 4, s_acc4, payload4, s_doff + j0, units, 0u);
+        } else if (nd) {
+            dense_pass32(s_acc4, payload4, s_doff, (int)nd, units);
+        }
+        DI_PROF_MARK(1);  // dense (read-modify-write)
         first = false;
     }
     if (!touched) return false;
 
-    // ---- phase 3: candidates. Between done[q] == tile and the publish after this item, this CTA is
+    // ---- the query's state. Between done[q] == tile and the publish after this item, this CTA is
     //      the only reader and writer of the query's list.
     if (!have_state) {
         if (tid == 0) {
@@ -515,17 +573,26 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     // visited in docid order, so the threshold's document lies in an earlier tile and every such tie in
     // this tile loses: compare against score + 1 and keep the (many) ties out of the slow path.
     if (theta != 0 && key_docid(theta) < doc_base) ++ths;
+    if (!ACC32 && ths > 0x10000u) ths = 0x10000u;  // a caller-given bound no 16-bit sum can reach: nothing hits
     if (tid == 0) { s_emit = 0; s_nhits = 0; }
     uint64_t theta_pre = 0;
     __syncthreads();
     DI_PROF_MARK(3);  // state wait
 
-    // s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
-    scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
+    // ---- phase 2: fused dense + threshold pass (16-bit), or the plain scan (32-bit).
+    //      s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
+    if (!ACC32) {
+        const uint32_t tm = ths - 1u;
+        const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, s_doff + f0, units, tm | (tm << 16));
+        record_hits16(mask, units, s_hist, &s_nhits);
+    } else {
+        scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
+    }
     __syncthreads();
     if (s_nhits > (uint32_t)kHistBins) {
         // Flooded: more groups than slots hold a document at or above the threshold (the first tiles of a
-        // frequent-term query whose bound is still loose).
+        // frequent-term query whose bound is still loose). In the 16-bit form every hit group still holds its
+        // sums (the others are zero, i.e. below any threshold), so the accumulators can simply be re-scanned.
         if ((uint32_t)theta == 0u) {
             // No exact k-th key yet (nothing, or only a seed bound): pre-select inside the tile with a score
             // histogram. Keeping every document of the bins that hold the tile's k best is exact (at least k
@@ -540,7 +607,9 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
 #pragma unroll
                 for (int i = 0; i < group_docs<ACC32>(); ++i) {
                     const uint32_t sc = group_score<ACC32>(x, i);
-                    if (sc >= ths) atomicAdd(&s_hist[sc >> shift], 1u);
+                    // scores above the query-length bound exist only when a posting list names a document twice:
+                    // the top bin is kept whole, so clamping stays exact
+                    if (sc >= ths) atomicAdd(&s_hist[min(sc >> shift, (uint32_t)kHistBins - 1u)], 1u);
                 }
             }
             __syncthreads();
@@ -558,15 +627,16 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     }
     expand_hits<ACC32>(s_acc4, s_hist, min(s_nhits, (uint32_t)kHistBins), ths, doc_base, theta, cand, cnt0, &s_emit);
     __syncthreads();
-    DI_PROF_MARK(4);  // accumulator scan + emission
+    DI_PROF_MARK(4);  // fused dense + threshold pass, emission
     uint32_t n = cnt0 + s_emit;  // <= c0 + tile_docs <= cap
     if (n > p.c0) {
         // too many live candidates: keep exactly the k best and raise the threshold to the k-th
         uint64_t kth;
         if (n <= (T * (ACC32 ? 4u : 2u)) / 8u) {
-            // the accumulators are dead now: their shared memory stages the whole list (the usual case)
+            // the accumulators are idle now: their shared memory stages the whole list (the usual case)
             kth = block_cut_to_k_staged(cand, n, p.k, reinterpret_cast<uint64_t *>(s_acc4), s_hist, s_tmp,
                                         &s_emit);
+            if (!ACC32) zero_words16(s_acc4, (n + 1u) / 2u);  // restore the invariant (ordered by the next item's barrier)
             n = p.k;
         } else {
             kth = block_select_kth<true>(cand, n, p.k, s_hist, s_tmp);
@@ -579,7 +649,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     if (tid == 0) p.cnt[sq] = n;
     DI_PROF_MARK(5);  // cut to k
 #ifdef DI_PROFILE_PHASES
-    if (tid == 0 && p.prof) atomicAdd(p.prof + (size_t)tile * 8 + 7, 1ull);  // items that reached phase 3
+    if (tid == 0 && p.prof) atomicAdd(p.prof + (size_t)tile * 8 + 7, 1ull);  // items that reached the fused pass
 #endif
     return true;  // the query's state was read after done[q] >= tile was observed
 }
@@ -588,30 +658,52 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
 template <bool ACC32>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS) score_tile_kernel(SearchArgs p, uint32_t tile)
 {
+    extern __shared__ uint4 s_acc4[];
+    if (!ACC32) {
+        zero_words16(s_acc4, p.tile_docs / 8);
+        __syncthreads();
+    }
     score_item<ACC32>(p, tile, blockIdx.x, 0, tile);  // p.done == nullptr: the launch boundary orders the tiles
 }
 
 // ---- launch form B: ONE persistent launch for all tiles of the batch ---------------------------
 // grid = resident CTAs; each CTA claims work items from a global counter in tile-major order
 // (item = tile * n_queries + slot), so at any moment the whole GPU works on one or two tiles (their
-// postings stay L2-resident) and there is no per-tile launch tail. After an item, done[q] = tile + 1
-// is published with release semantics; the next tile of the same query acquires it.
+// postings stay L2-resident) and there is no per-tile launch tail. The NEXT item is claimed while the current
+// one is processed (the atomic's round trip to L2 is off the critical path). After an item, done[q] = tile + 1
+// is published with release semantics; the next tile of the same query acquires it. Waits only ever point at
+// items with a smaller index, and claims are handed out in index order, so the protocol cannot deadlock.
 template <bool ACC32>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS)
 score_persistent_kernel(SearchArgs p, unsigned long long *counter)
 {
+    extern __shared__ uint4 s_acc4[];
     __shared__ unsigned long long s_item;
     const uint32_t n_virtual = p.lanes * p.n_queries;  // (lane, query) chains
     const unsigned long long n_items = (unsigned long long)p.tiles_per_lane * n_virtual;
+    const bool narrow = n_items <= 0xFFFFFFFFull;  // 32-bit item arithmetic (a 64-bit divide is ~100 instructions)
+    unsigned long long next = 0;
+    if (threadIdx.x == 0) next = atomicAdd(counter, 1ull);
+    if (!ACC32) zero_words16(s_acc4, p.tile_docs / 8);  // accumulator invariant: zero at every item start
     for (;;) {
         __syncthreads();  // everybody is done with the previous item's shared memory
-        if (threadIdx.x == 0) s_item = atomicAdd(counter, 1ull);
+        if (threadIdx.x == 0) {
+            s_item = next;
+            if (next < n_items) next = atomicAdd(counter, 1ull);
+        }
         __syncthreads();
         const unsigned long long item = s_item;
         if (item >= n_items) break;
         // step-major: all chains advance together, so the GPU works on `lanes` tiles at a time
-        const uint32_t step = (uint32_t)(item / n_virtual), v = (uint32_t)(item % n_virtual);
-        const uint32_t lane = v / p.n_queries, slot = v % p.n_queries;
+        uint32_t step, v;
+        if (narrow) {
+            step = (uint32_t)item / n_virtual;
+            v = (uint32_t)item - step * n_virtual;
+        } else {
+            step = (uint32_t)(item / n_virtual);
+            v = (uint32_t)(item % n_virtual);
+        }
+        const uint32_t lane = p.lanes == 1 ? 0u : v / p.n_queries, slot = v - lane * p.n_queries;
         const uint32_t tile = lane * p.tiles_per_lane + step;
         if (tile >= p.n_tiles) continue;  // the last lane may be shorter; nobody waits on these steps
         const bool synced = score_item<ACC32>(p, tile, slot, lane, step);

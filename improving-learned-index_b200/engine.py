@@ -79,19 +79,19 @@ class DeviceIndex:
 
     # ---- constructors -------------------------------------------------------
     @staticmethod
-    def _params(tile_docs, dense_ratio, cand_slack):
-        return N.IndexParams(tile_docs or 0, dense_ratio or 0, cand_slack or 0, 0)
+    def _params(tile_docs, dense_ratio, cand_slack, flags=0):
+        return N.IndexParams(tile_docs or 0, dense_ratio or 0, cand_slack or 0, flags or 0)
 
     @classmethod
     def from_csr(cls, term_offsets, docids, impacts, doc_lo: int = 0, doc_hi: int = N.ALL_DOCS,
-                 tile_docs: int = 0, dense_ratio: int = 0, cand_slack: int = 0) -> "DeviceIndex":
+                 tile_docs: int = 0, dense_ratio: int = 0, cand_slack: int = 0, flags: int = 0) -> "DeviceIndex":
         toff = N.np_c(term_offsets, np.uint64).reshape(-1)
         d = N.np_c(docids, np.uint32).reshape(-1)
         v = N.np_c(impacts, np.uint8).reshape(-1)
         if int(toff[-1]) != d.size or d.size != v.size:
             raise ValueError("term_offsets[-1] must equal len(docids) == len(impacts)")
         h = ctypes.c_void_p()
-        p = cls._params(tile_docs, dense_ratio, cand_slack)
+        p = cls._params(tile_docs, dense_ratio, cand_slack, flags)
         N.check(N.lib().di_index_create_csr(N.ptr(toff), N.ptr(d), N.ptr(v), toff.size - 1, doc_lo, doc_hi,
                                             ctypes.byref(p), ctypes.byref(h)))
         return cls(h.value)
@@ -99,25 +99,25 @@ class DeviceIndex:
     @classmethod
     def from_csr_device(cls, d_term_offsets, d_docids, d_impacts, n_terms: int, n_postings: int,
                         doc_lo: int = 0, doc_hi: int = N.ALL_DOCS, tile_docs: int = 0, dense_ratio: int = 0,
-                        cand_slack: int = 0) -> "DeviceIndex":
+                        cand_slack: int = 0, flags: int = 0) -> "DeviceIndex":
         """CSR already in device memory (torch CUDA tensors or raw device addresses). The caller
         must have synchronised the stream that produced them."""
         h = ctypes.c_void_p()
-        p = cls._params(tile_docs, dense_ratio, cand_slack)
+        p = cls._params(tile_docs, dense_ratio, cand_slack, flags)
         N.check(N.lib().di_index_create_csr_dev(N.ptr(d_term_offsets), N.ptr(d_docids), N.ptr(d_impacts), n_terms,
                                                 n_postings, doc_lo, doc_hi, ctypes.byref(p), ctypes.byref(h)))
         return cls(h.value)
 
     @classmethod
     def from_files(cls, dat, idx_pairs, doc_lo: int = 0, doc_hi: int = N.ALL_DOCS, tile_docs: int = 0,
-                   dense_ratio: int = 0, cand_slack: int = 0) -> "DeviceIndex":
+                   dense_ratio: int = 0, cand_slack: int = 0, flags: int = 0) -> "DeviceIndex":
         """From the reference's file images: inverted_index.dat bytes and inverted_index.idx as u64 pairs."""
         dat = N.np_c(dat, np.uint8).reshape(-1)
         idx = N.np_c(idx_pairs, np.uint64).reshape(-1)
         if idx.size % 2:
             raise ValueError(".idx image must hold (start, end) pairs")
         h = ctypes.c_void_p()
-        p = cls._params(tile_docs, dense_ratio, cand_slack)
+        p = cls._params(tile_docs, dense_ratio, cand_slack, flags)
         N.check(N.lib().di_index_create_files(N.ptr(dat), dat.size, N.ptr(idx), idx.size // 2, doc_lo, doc_hi,
                                               ctypes.byref(p), ctypes.byref(h)))
         return cls(h.value)

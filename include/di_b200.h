@@ -115,8 +115,10 @@ typedef struct di_index_params {
                                 document of the tile) when n * dense_ratio >= tile_docs; 0 = default (8);
                                 0xFFFFFFFF = never */
     uint32_t cand_slack;     /* per-query candidate slots kept between tiles; 0 = default (max(2k, 256)) */
-    uint32_t reserved;
+    uint32_t flags;          /* DI_INDEX_* bits; 0 = default */
 } di_index_params;
+#define DI_INDEX_NO_SEEDS 1u /* build no threshold-seed tables (every query then starts without a bound) */
+#define DI_INDEX_PER_TILE 2u /* diagnostic: one kernel launch per document tile instead of one persistent launch */
 
 typedef struct di_index_info {
     uint64_t n_postings;      /* visible postings in the shard */
@@ -214,6 +216,8 @@ typedef struct di_timings {
     float total_ms;      /* first kernel to last kernel */
     uint32_t score_launches;
     uint32_t other_launches;
+    uint32_t lanes;      /* tile lanes per query of the last search (1 = one chain of tiles per query) */
+    uint32_t acc32;      /* 1 when the last search ran with 32-bit accumulators */
 } di_timings;
 int di_get_timings(di_index_t *index, di_timings *out);
 

@@ -1,6 +1,7 @@
-"""Full-size checks (BASELINE.json configs[1]/[2]/[4]: 8 841 823 documents, ~8 x 10^8 postings) through the C ABI.
-Exact comparison with the oracle on a query sample, plus size-independent properties on all 6 980 queries:
-sorted unique keys, idempotence, and shard-and-merge == single index."""
+"""Full-size checks (BASELINE.json configs[1]..[4]: 8 841 823 documents x 120 distinct terms, ~1.05 x 10^9 postings)
+through the C ABI: the whole K2 inversion against the oracle's (configs[4]), exact comparison with the oracle on
+query samples drawn from full batches (6 980 queries top-1000 = configs[1]; 4 096 queries top-100 = configs[3]), plus
+size-independent properties on all 6 980 queries: sorted unique keys, idempotence, shard-and-merge == single index."""
 import sys
 from pathlib import Path
 
@@ -12,7 +13,7 @@ from improving_learned_index_b200 import _native, engine, synthetic as syn   # n
 from oracle import oracle                                                    # noqa: E402
 
 pytestmark = pytest.mark.gpu
-N_DOCS, VOCAB, DRAWS, N_QUERIES, K = 8_841_823, 30522, 120, 6980, 1000
+N_DOCS, VOCAB, DRAWS, UNIQUE, N_QUERIES, K = 8_841_823, 30522, 208, 120, 6980, 1000
 
 
 @pytest.fixture(scope="module")
@@ -27,7 +28,7 @@ def full():
         out = torch.empty(x.numel(), dtype=torch.int32, device=dev)
         _native.check(L.di_quantize_f64_dev(x.data_ptr(), x.numel(), bench.IMPACT_CLIP, out.data_ptr(), st))
         return out
-    terms, imps, offs = bench.build_shard_arrays(0, N_DOCS, N_DOCS, VOCAB, DRAWS, torch, dev, quantize_fn)
+    terms, imps, offs = bench.build_shard_arrays(0, N_DOCS, N_DOCS, VOCAB, DRAWS, torch, dev, quantize_fn, UNIQUE)
     P = terms.numel()
     toff = torch.empty(VOCAB + 1, dtype=torch.int64, device=dev)
     docids = torch.empty(P, dtype=torch.int32, device=dev)
@@ -36,11 +37,24 @@ def full():
     _native.check(L.di_invert_dev(terms.data_ptr(), imps.data_ptr(), offs.data_ptr(), N_DOCS, VOCAB, P,
                                   toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), st))
     torch.cuda.synchronize()
+    # the oracle's own inversion of the same doc-major arrays (create.py:31-46 restated, ~20 s single-threaded): the
+    # reference for configs[4] and the CSR every scoring comparison below runs the oracle on
+    o_toff, o_docs, o_vals = oracle.invert(terms.cpu().numpy().view(np.uint32), imps.cpu().numpy(),
+                                           offs.cpu().numpy().astype(np.uint64), VOCAB)
     del terms, imps, offs
     index = engine.DeviceIndex.from_csr_device(toff, docids, vals, VOCAB, P)
     queries = syn.make_queries(N_QUERIES, vocab_size=VOCAB, seed=7)
-    yield dict(torch=torch, dev=dev, toff=toff, docids=docids, vals=vals, P=P, index=index, queries=queries)
+    yield dict(torch=torch, dev=dev, toff=toff, docids=docids, vals=vals, P=P, index=index, queries=queries,
+               o_toff=o_toff, o_docs=o_docs, o_vals=o_vals)
     index.close()
+
+
+def test_full_size_inversion_is_bit_exact(full):
+    """configs[4]: quantize + term->doc inversion of the 8.8 M per-document lists, every posting compared."""
+    assert full["P"] > 1_000_000_000                               # ~120 distinct terms per document survive K1
+    assert np.array_equal(full["toff"].cpu().numpy().astype(np.uint64), full["o_toff"])
+    assert np.array_equal(full["docids"].cpu().numpy().view(np.uint32), full["o_docs"])
+    assert np.array_equal(full["vals"].cpu().numpy(), full["o_vals"])
 
 
 def test_csr_is_well_formed(full):
@@ -58,20 +72,43 @@ def test_csr_is_well_formed(full):
     assert int(full["vals"].min()) >= 1                          # quantize.py:45 dropped the zeros
 
 
-def test_sample_matches_oracle_exactly(full):
-    h_toff = full["toff"].cpu().numpy().astype(np.uint64)
-    h_docs = full["docids"].cpu().numpy().view(np.uint32)
-    h_vals = full["vals"].cpu().numpy()
+def _check_rows(full, got, queries, pick, k):
+    sample = [queries[i] for i in pick]
+    want = oracle.score_topk_csr(full["o_toff"], full["o_docs"], full["o_vals"], N_DOCS, sample, k)
+    for i, qi in enumerate(pick):
+        n = int(want[2][i])
+        assert int(got[2][qi]) == n, (k, qi)
+        assert np.array_equal(got[0][qi, :n], want[0][i, :n]) and np.array_equal(got[1][qi, :n], want[1][i, :n]), (k, qi)
+
+
+def test_timed_batch_rows_match_oracle_exactly(full):
+    """configs[1]: ALL 6 980 queries in one call (one tile chain per query, 540 hand-offs each — the timed path);
+    the rows of 24 random queries plus the edge cases are compared with the oracle."""
+    queries = list(full["queries"])
+    queries[11], queries[12], queries[13] = [], [VOCAB + 3], queries[0] * 2
     rng = np.random.default_rng(99)
-    pick = sorted(rng.choice(N_QUERIES, size=24, replace=False).tolist())
-    sample = [full["queries"][i] for i in pick] + [[], [VOCAB + 3], full["queries"][0] * 2]
+    pick = sorted(set(rng.choice(N_QUERIES, size=24, replace=False).tolist()) | {11, 12, 13})
     for k in (10, K):
-        want = oracle.score_topk_csr(h_toff, h_docs, h_vals, N_DOCS, sample, k)
-        got = full["index"].search(sample, k)
-        assert np.array_equal(got[2], want[2])
-        for i in range(len(sample)):
-            n = int(want[2][i])
-            assert np.array_equal(got[0][i, :n], want[0][i, :n]) and np.array_equal(got[1][i, :n], want[1][i, :n]), (k, i)
+        got = full["index"].search(queries, k)
+        assert full["index"].timings()["lanes"] == 1
+        _check_rows(full, got, queries, pick, k)
+    small = [queries[i] for i in pick[:8]]                       # the same queries as a small batch (tile lanes)
+    got = full["index"].search(small, K)
+    assert full["index"].timings()["lanes"] > 1
+    _check_rows(full, got, small, list(range(len(small))), K)
+
+
+def test_c4_batch_rows_match_oracle_exactly(full):
+    """configs[3]: a batch of 4 096 queries of ~6 terms, top-100."""
+    queries = syn.make_queries(4096, vocab_size=VOCAB, seed=11)
+    got = full["index"].search(queries, 100)
+    assert full["index"].timings()["lanes"] == 1
+    pick = sorted(np.random.default_rng(5).choice(4096, size=32, replace=False).tolist())
+    _check_rows(full, got, queries, pick, 100)
+    counts = got[2]
+    keys = (got[1].astype(np.uint64) << np.uint64(32)) | (~got[0]).astype(np.uint64)
+    for i in range(0, 4096, 5):
+        assert np.all(keys[i, 1:counts[i]] < keys[i, :counts[i] - 1])
 
 
 def test_all_queries_properties_and_shard_merge(full):

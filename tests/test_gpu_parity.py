@@ -161,7 +161,7 @@ CONFIGS = [
     (5000, 800, 100, 11, 512, 0xFFFFFFFF, 64, 80, (7, 100)),            # all sparse, tiny candidate slack
     (5000, 800, 100, 11, 512, 1, 0, 80, (100,)),                        # everything dense
     (40_000, 2000, 60, 12, 4096, 0, 300, 120, (100, 1000)),
-    (70_000, 3000, 40, 13, 0, 0, 0, 60, (10, 1000)),                    # default 32768-doc tiles, 3 tiles
+    (70_000, 3000, 40, 13, 0, 0, 0, 60, (10, 1000)),                    # default 16384-doc tiles, 5 tiles
 ]
 
 
@@ -185,6 +185,62 @@ def test_search_matches_oracle(cfg):
     flat = np.asarray([t for q in queries for t in q if 0 <= t < V], dtype=np.uint32)
     df = index.term_df(flat)
     assert np.array_equal(df, np.diff(x["toff"].astype(np.int64))[flat].astype(np.uint64))
+    index.close()
+
+
+@pytest.mark.parametrize("mode", ["seeded", "unseeded", "acc32", "per_tile"])
+def test_long_tile_chains_with_one_lane_match_oracle(mode):
+    """The configuration the bench times: MORE queries than resident CTAs, so every query is ONE chain of
+    tiles (lanes == 1) handed from CTA to CTA through global memory (157 tiles here), with repeated cuts to k.
+    Seeded and unseeded thresholds, 16- and 32-bit accumulators, and the one-launch-per-tile form."""
+    from improving_learned_index_b200 import _native
+    n_docs, V = 40_000, 2000
+    x = quantized_csr(n_docs, V, 60, 71)
+    flags = {"unseeded": _native.INDEX_NO_SEEDS, "per_tile": _native.INDEX_PER_TILE}.get(mode, 0)
+    index = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], tile_docs=256, flags=flags)
+    assert index.info()["n_tiles"] == 157
+    queries = syn.make_queries(3000, vocab_size=V, seed=72)
+    queries[0] = []
+    queries[1] = [V + 9]
+    queries[2] = queries[3] * 2
+    hot = int(np.argmax(np.diff(x["toff"].astype(np.int64))))
+    queries[4] = [hot]                                   # floods every tile until the threshold is exact
+    if mode == "acc32":
+        queries[5] = np.random.default_rng(3).integers(0, V, size=300).tolist()
+    for k in ((1, 100, 1000) if mode == "seeded" else (100, 1000)):
+        got = index.search(queries, k)
+        t = index.timings()
+        assert t["lanes"] == 1 and t["acc32"] == (1 if mode == "acc32" else 0), t
+        assert t["score_launches"] == (157 if mode == "per_tile" else 1)
+        want = oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], n_docs, queries, k)
+        assert_same_results(got, want, f"{mode} k={k}")
+    index.close()
+
+
+def test_duplicate_postings_force_wide_accumulators():
+    """A posting list may name a document several times (hand-made CSR, a model listing a term twice: the
+    reference appends both). 200 query terms x 5 repeats x impact 255 = 255 000 overflows a u16 accumulator and
+    exceeds the 255-per-term bound of the flood histogram: such an index must score with 32-bit accumulators."""
+    n_docs, V, reps = 3000, 40, 5
+    rng = np.random.default_rng(5)
+    docs, vals, toff = [], [], [0]
+    for t in range(V):
+        d = np.sort(rng.choice(n_docs, size=1500, replace=False)).astype(np.uint32)
+        v = rng.integers(200, 256, size=d.size).astype(np.uint8)
+        if t < 8:                                        # document 7 repeated in the hot lists, impact 255
+            d = np.concatenate([np.full(reps, 7, dtype=np.uint32), d[d != 7]])
+            v = np.concatenate([np.full(reps, 255, dtype=np.uint8), v[:d.size - reps]])
+        docs.append(d)
+        vals.append(v)
+        toff.append(toff[-1] + d.size)
+    toff, docs, vals = np.asarray(toff, dtype=np.uint64), np.concatenate(docs), np.concatenate(vals)
+    index = engine.DeviceIndex.from_csr(toff, docs, vals, tile_docs=1024)
+    queries = [list(range(8)) * 25, [0, 1, 2], list(range(V)) * 6, [3] * 257]
+    for k in (1, 10, 2000):
+        got = index.search(queries, k)
+        assert index.timings()["acc32"] == 1
+        assert_same_results(got, oracle.score_topk_csr(toff, docs, vals, n_docs, queries, k), f"k={k}")
+    assert got[1][0, 0] >= 8 * 25 * reps * 255 and got[0][0, 0] == 7
     index.close()
 
 
