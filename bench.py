@@ -406,6 +406,8 @@ def run_b200(args):
         if world == 1 and args.cpu_sample > 0:
             out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(
                 args, toff, docids, vals, queries, (h_docs, h_scores, h_counts), torch)
+        if world == 1 and args.py_ref_seconds > 0 and args.workload == "c2":
+            out["cpu_baseline_python"] = python_reference_leg(args, toff, docids, vals, torch, dev, L, stream)
     if world > 1 and args.verify_sharded:
         # every rank's merged result vs ONE index over all documents built on rank 0's GPU (itself checked against
         # the oracle in the 1-GPU run): the sharded path must be bit-identical
@@ -472,6 +474,44 @@ def cpu_baseline_and_parity(args, toff, docids, vals, queries, timed_result, tor
     if not ok:
         raise SystemExit("PARITY FAILURE at full size: GPU results of the timed batch differ from the oracle")
     return base, parity
+
+
+def python_reference_leg(args, toff, docids, vals, torch, dev, L, stream):
+    """The reference's own unmodified Python reader, timed on index files written from this run's CSR
+    (di_serialize: byte format of create.py:44-51) — see tools/py_reference_timing.py. Rank 0, N = 1 only."""
+    import shutil
+    import tempfile
+    if not (REPO / "baseline" / "_ref" / "src").is_dir():
+        return {"unavailable": "baseline/_ref/src missing: __graft_entry__.build() stages it where /root/reference exists"}
+    P, V = docids.numel(), args.vocab
+    need = 5 * P + 16 * V + (1 << 20)
+    root = next((d for d in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(d) and shutil.disk_usage(d).free > need + (2 << 30)), None)
+    if root is None:
+        return {"unavailable": "no scratch space for the %.1f GB .dat file" % (need / 1e9)}
+    tmp = Path(tempfile.mkdtemp(prefix="di_ref_index_", dir=root))
+    try:
+        from improving_learned_index_b200 import _native, synthetic
+        d_dat = torch.empty(5 * P, dtype=torch.uint8, device=dev)
+        d_idx = torch.empty(2 * V, dtype=torch.int64, device=dev)
+        _native.check(L.di_serialize_dev(toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), V, P, d_dat.data_ptr(),
+                                         d_idx.data_ptr(), stream))
+        torch.cuda.synchronize()
+        d_dat.cpu().numpy().tofile(tmp / "inverted_index.dat")
+        d_idx.cpu().numpy().tofile(tmp / "inverted_index.idx")
+        del d_dat, d_idx
+        (tmp / "vocab.txt").write_text(''.join(synthetic.term_name(t) + '\n' for t in range(V)))
+        env = dict(os.environ)
+        env.pop("OMP_NUM_THREADS", None)
+        r = subprocess.run([sys.executable, str(REPO / "tools" / "py_reference_timing.py"), "--index-dir", str(tmp),
+                            "--queries", str(args.queries), "--vocab", str(V), "--seconds", str(args.py_ref_seconds)],
+                           capture_output=True, text=True, timeout=60 + 12 * args.py_ref_seconds, env=env)
+        if r.returncode != 0:
+            return {"unavailable": "py_reference_timing.py failed: " + r.stderr.strip().splitlines()[-1][:200]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:          # a reported baseline must never take the GPU measurement down with it
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def host_threads():
@@ -557,6 +597,8 @@ def main():
                     help="N > 1: compare the merged result of every query with a single index built on rank 0")
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
     ap.add_argument("--ref-queries-per-step", type=int, default=32)
+    ap.add_argument("--py-ref-seconds", type=float, default=10.0,
+                    help="time budget per leg of the unmodified Python reference (single process and Pool); 0 = skip")
     args = ap.parse_args()
     if args.draws == 0:
         args.draws = 208 if args.unique_terms else 120
