@@ -269,10 +269,20 @@ def run_b200(args):
     B = args.batch or Q                       # queries per search call (configs[3] uses batches of 4096)
     batches = [(q0, min(q0 + B, Q)) for q0 in range(0, Q, B)]
 
+    fused = searcher.peer_exchange_available()    # N > 1: exchange + merge as one kernel over peer memory, no collective
+
+    def search_batch(q0, q1):
+        """-> ((first, last) query of this rank's result rows, keys, counts)"""
+        if fused:
+            (lo, hi), keys, counts = searcher.search_partitioned(d_flat, d_offs[q0:q1 + 1], q1 - q0, max_len, k)
+            return (q0 + lo, q0 + hi), keys, counts
+        keys, counts = searcher.search_tensors(d_flat, d_offs[q0:q1 + 1], q1 - q0, max_len, k)
+        return ((q0, q1) if rank == 0 else (q0, q0)), keys, counts   # all-gather form: rank 0 reports the rows
+
     def step_device():
         out = None
         for q0, q1 in batches:
-            out = searcher.search_tensors(d_flat, d_offs[q0:q1 + 1], q1 - q0, max_len, k)
+            out = search_batch(q0, q1)
         return out
 
     h_docs = torch.empty((Q, k), dtype=torch.int32).pin_memory()
@@ -286,16 +296,16 @@ def run_b200(args):
         for q0, q1 in batches:
             if world == 1:      # H2D + kernels + D2H inside the C-ABI call
                 index.search_flat(h_flat, h_offs[q0:q1 + 1], k, h_docs[q0:q1], h_scores[q0:q1], h_counts[q0:q1])
-            else:
+            else:               # every rank: queries H2D, search + exchange, its own slice of the results D2H
                 d_flat.copy_(h_flat, non_blocking=True)
                 d_offs.copy_(h_offs, non_blocking=True)
-                m_keys, m_counts = searcher.search_tensors(d_flat, d_offs[q0:q1 + 1], q1 - q0, max_len, k)
-                if rank == 0:
-                    n = q1 - q0
+                (r0, r1), m_keys, m_counts = search_batch(q0, q1)
+                n = r1 - r0
+                if n:
                     engine.unpack_keys_device(m_keys, n * k, dd, ds, stream)
-                    h_docs[q0:q1].copy_(dd[:n], non_blocking=True)
-                    h_scores[q0:q1].copy_(ds[:n], non_blocking=True)
-                    h_counts[q0:q1].copy_(m_counts, non_blocking=True)
+                    h_docs[r0:r1].copy_(dd[:n], non_blocking=True)
+                    h_scores[r0:r1].copy_(ds[:n], non_blocking=True)
+                    h_counts[r0:r1].copy_(m_counts[:n], non_blocking=True)
                 torch.cuda.synchronize()
 
     def barrier():
@@ -323,7 +333,7 @@ def run_b200(args):
             score_ms.append(t["score_ms"])
             final_ms.append(t["finalize_ms"])
             launches = t                     # kernels this rank's library launched in this step
-            n_launches = t["score_launches"] + t["other_launches"] + (3 * len(batches) if world > 1 else 0)
+            n_launches = t["score_launches"] + t["other_launches"] + ((2 if fused else 3) * len(batches) if world > 1 else 0)
         barrier()
         # ---- timed: end to end through the host-buffer call
         step_e2e()
@@ -401,7 +411,9 @@ def run_b200(args):
             "build": build_info,
             "postings_per_query": round(total_postings / Q),
             "build_parity": build_parity,
-            "round2_queries_last_step": searcher.round2_queries,
+            "exchange": ("fused peer-memory pull (CUDA IPC + stream barrier + di_merge_pull_dev), queries partitioned over ranks"
+                         if fused else ("NCCL all-gather + K5" if world > 1 else None)),
+            "second_pass_queries_rank0_last_step": int(searcher.round2_queries),
         }
         if world == 1 and args.cpu_sample > 0:
             out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(

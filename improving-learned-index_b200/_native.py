@@ -83,8 +83,13 @@ SIGNATURES = {
     "di_unpack_keys_dev": (ctypes.c_int, [_vp, ctypes.c_uint64, _vp, _vp, _vp]),
     "di_merge_topk_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                          _vp, _vp, _vp, _vp]),
-    "di_merge_rows_p2p_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
-                                             ctypes.c_uint32, _vp, _vp, _vp, _vp]),
+    "di_merge_pull_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                         ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp, _vp]),
+    "di_shared_alloc": (ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(_vp), ctypes.c_char_p]),
+    "di_shared_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "di_shared_close": (ctypes.c_int, [_vp]),
+    "di_shared_free": (ctypes.c_int, [_vp]),
+    "di_peer_barrier_dev": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp]),
     "di_get_timings": (ctypes.c_int, [_vp, ctypes.POINTER(Timings)]),
     "di_collection_parse": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_vp)]),
     "di_collection_free": (None, [_vp]),

@@ -664,7 +664,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
             a.done = ix->ws_done.as<uint32_t>() + 2;  // [0..1] hold the 64-bit work counter
             unsigned long long *counter = ix->ws_done.as<unsigned long long>();
             DI_CUDA(cudaMemsetAsync(ix->ws_done.p, 0, 8 + nv * 4, st));
-            const uint64_t n_items = (uint64_t)tiles_per_lane * nv;
+            const uint64_t n_items = (uint64_t)((tiles_per_lane + kTilesPerItem - 1) / kTilesPerItem) * nv;
             const unsigned grid = (unsigned)std::min<uint64_t>(n_items, (uint64_t)resident_ctas);
             if (acc32)
                 score_persistent_kernel<true><<<grid, kScoreThreads, acc_bytes, st>>>(a, counter);
@@ -792,32 +792,83 @@ extern "C" int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_co
     return DI_OK;
 }
 
-extern "C" int di_merge_rows_p2p_dev(const uint64_t *const *d_rows, const uint32_t *const *d_counts, uint32_t n_shards,
-                                     const uint32_t *d_query_ids, uint32_t n_queries, uint32_t row_stride, uint32_t k_in,
-                                     uint32_t top_k, uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_incomplete,
-                                     void *stream)
+extern "C" int di_merge_pull_dev(const uint64_t *const *d_rows, const uint32_t *const *d_counts, uint32_t n_shards,
+                                 uint32_t q_first, uint32_t n_queries, uint32_t row_stride, uint32_t k_in, uint32_t top_k,
+                                 uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_n_second_pass, void *stream)
 {
     if (n_queries == 0 || n_shards == 0) return DI_OK;
     if (!d_rows || !d_counts) return set_error(DI_ERR_ARG, "NULL shard pointer table");
-    if (n_shards > kMaxP2PShards) return set_error(DI_ERR_ARG, "at most %u shards, got %u", kMaxP2PShards, n_shards);
+    if (n_shards > kMaxPeerShards) return set_error(DI_ERR_ARG, "at most %u shards, got %u", kMaxPeerShards, n_shards);
     if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
-    if (k_in == 0 || k_in > row_stride) return set_error(DI_ERR_ARG, "k_in must be in [1, row_stride = %u], got %u", row_stride, k_in);
-    cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t cap = pow2_ceil(std::max(n_shards * k_in, top_k));
-    StreamBuf cand(st), cnt(st);  // like di_merge_topk_dev
-    DI_TRY(cand.alloc((size_t)n_queries * cap * 8));
-    DI_TRY(cnt.alloc((size_t)n_queries * 4));
-    merge_gather_p2p_kernel<<<n_queries, 256, 0, st>>>(d_rows, d_counts, n_shards, d_query_ids, row_stride, k_in,
-                                                      cand.as<uint64_t>(), cnt.as<uint32_t>(), cap);
-    DI_KERNEL_CHECK();
-    DI_TRY(launch_finalize(cand.as<uint64_t>(), cnt.as<uint32_t>(), cap, top_k, /*max_n=*/n_shards * k_in, n_queries,
-                           d_keys_out, d_counts_out, st));
-    if (d_incomplete) {
-        merge_check_p2p_kernel<<<grid_for(n_queries, 256), 256, 0, st>>>(d_rows, d_counts, n_shards, d_query_ids, n_queries,
-                                                                        row_stride, k_in, top_k, d_keys_out, d_counts_out,
-                                                                        d_incomplete);
-        DI_KERNEL_CHECK();
+    if (k_in == 0 || row_stride == 0) return set_error(DI_ERR_ARG, "k_in and row_stride must be positive");
+    // the second pass of a query holds every shard's full row in shared memory
+    const uint64_t worst = (uint64_t)n_shards * std::min(row_stride, top_k) + pow2_ceil(top_k);
+    const uint32_t smem_keys = pow2_ceil((uint32_t)std::min<uint64_t>(worst, 1u << 20));
+    int dev = 0, smem_max = 0;
+    DI_CUDA(cudaGetDevice(&dev));
+    DI_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (row_stride > top_k || (uint64_t)smem_keys * 8 + 4096 > (uint64_t)smem_max)
+        return set_error(DI_ERR_ARG, "%u shards x rows of %u keys do not fit the merge kernel's shared memory; "
+                         "gather the rows and use di_merge_topk_dev", n_shards, row_stride);
+    static std::atomic<uint64_t> attr_done{0};
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+        DI_CUDA(cudaFuncSetAttribute(merge_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 4096));
+        attr_done.fetch_or(bit, std::memory_order_release);
     }
+    merge_pull_kernel<<<n_queries, kMergeThreads, (size_t)smem_keys * 8, (cudaStream_t)stream>>>(
+        d_rows, d_counts, n_shards, q_first, row_stride, k_in, top_k, smem_keys, d_keys_out, d_counts_out, d_n_second_pass);
+    DI_KERNEL_CHECK();
+    return DI_OK;
+}
+
+// ---- peer-visible memory + cross-GPU barrier (one process per GPU; CUDA IPC over NVLink / NVSwitch)
+extern "C" int di_shared_alloc(uint64_t bytes, void **d_ptr, uint8_t handle_out[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    if (!d_ptr || !handle_out) return set_error(DI_ERR_ARG, "NULL argument");
+    DI_TRY(ensure_device());
+    void *p = nullptr;
+    DI_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    DI_CUDA(cudaMemset(p, 0, bytes ? bytes : 16));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return set_error(DI_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, 64);
+    *d_ptr = p;
+    return DI_OK;
+}
+
+extern "C" int di_shared_open(const uint8_t handle[64], void **d_ptr)
+{
+    if (!d_ptr || !handle) return set_error(DI_ERR_ARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    DI_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DI_OK;
+}
+
+extern "C" int di_shared_close(void *d_ptr)
+{
+    if (d_ptr) DI_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return DI_OK;
+}
+
+extern "C" int di_shared_free(void *d_ptr)
+{
+    if (d_ptr) DI_CUDA(cudaFree(d_ptr));
+    return DI_OK;
+}
+
+extern "C" int di_peer_barrier_dev(uint32_t *const *d_flags, uint32_t n_ranks, uint32_t my_rank, uint32_t epoch, void *stream)
+{
+    if (!d_flags || n_ranks == 0 || n_ranks > kMaxPeerShards || my_rank >= n_ranks)
+        return set_error(DI_ERR_ARG, "bad barrier arguments (%u ranks, rank %u)", n_ranks, my_rank);
+    peer_barrier_kernel<<<1, kMaxPeerShards, 0, (cudaStream_t)stream>>>(d_flags, n_ranks, my_rank, epoch);
+    DI_KERNEL_CHECK();
     return DI_OK;
 }
 

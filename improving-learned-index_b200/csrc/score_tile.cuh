@@ -39,6 +39,10 @@ constexpr int kMaxSeg = 32;        // query terms handled per round inside a wor
 #endif
 constexpr int kSparseUnroll = DI_SPARSE_UNROLL;  // independent 128-bit posting loads in flight per thread
 constexpr int kHistBins = 1024;    // score histogram of the tile-local pre-selection
+#ifndef DI_TILES_PER_ITEM
+#define DI_TILES_PER_ITEM 2
+#endif
+constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers (1 or 2)
 
 constexpr int kRecInlineTerms = 12;
 struct __align__(64) QueryRec {   // one cache-line-friendly record per query of the batch
@@ -408,18 +412,51 @@ __device__ __forceinline__ void zero_words16(uint4 *s, uint32_t n16)
     for (uint32_t i = threadIdx.x; i < n16; i += kScoreThreads) s[i] = make_uint4(0, 0, 0, 0);
 }
 
-// One (query, tile) work item; `slot` indexes the batch's launch-ordered query records.
+// Segment lists of one (query, tile, round): filled by warp 0, one query term per lane, ballot-compacted.
+// (Kept small on purpose: six CTAs of 32 KB accumulators + this fit one SM only while the static part stays <= 5 KB.)
+struct SegLists {
+    uint32_t off[kMaxSeg];        // payload offsets (16 B units): dense segments from the front, sparse ones from the back
+    uint16_t seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
+    uint32_t spref[kMaxSeg + 1];  // exclusive prefix of the sparse segments' unit counts
+    uint32_t nd, ns;
+    __device__ __forceinline__ uint32_t soff(uint32_t j) const { return off[kMaxSeg - 1 - j]; }
+};
+
+__device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t lane)
+{
+    const bool is_dense = (d.n_flag & kDenseFlag) != 0, is_sparse = !is_dense && d.n_flag != 0;
+    const uint32_t bd = __ballot_sync(0xffffffffu, is_dense), bs = __ballot_sync(0xffffffffu, is_sparse);
+    const uint32_t su = is_sparse ? (d.n_flag & 0xFFFFu) : 0u;
+    uint32_t incl = su;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += up;
+    }
+    if (is_dense) L.off[__popc(bd & lanemask_lt())] = d.off16;
+    if (is_sparse) {
+        const uint32_t j = __popc(bs & lanemask_lt());
+        L.off[kMaxSeg - 1 - j] = d.off16;
+        L.seven[j] = (uint16_t)(d.n_flag >> 16);
+        L.spref[j] = incl - su;
+    }
+    if (lane == 31) L.spref[__popc(bs)] = incl;  // total units
+    if (lane == 0) { L.nd = __popc(bd); L.ns = __popc(bs); }
+}
+
+// One work item = one query against n_sub (1 or 2) ADJACENT tiles starting at tile0; `slot` indexes the batch's
+// launch-ordered query records. Two tiles per item halve the per-item fixed costs (claim, record read, hand-off)
+// and put the descriptor loads of both tiles in flight together. Returns whether the query's state was read
+// (i.e. whether the hand-off from the previous item was observed).
 template <bool ACC32>
-__device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, uint32_t slot, uint32_t lane, uint32_t step)
+__device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, uint32_t n_sub, uint32_t slot, uint32_t lane,
+                                           uint32_t step)
 {
     static_assert(kMaxSeg == 32, "the segment lookup is one warp wide");
     extern __shared__ uint4 s_acc4[];  // tile accumulators
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_acc4);
-    __shared__ uint32_t s_doff[kMaxSeg];       // dense segments of this round: payload offset (16 B units)
-    __shared__ uint32_t s_soff[kMaxSeg];       // sparse segments: payload offset
-    __shared__ uint32_t s_seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
-    __shared__ uint32_t s_spref[kMaxSeg + 1];  // exclusive prefix of the sparse segments' unit counts
-    __shared__ uint32_t s_nd, s_ns, s_emit, s_ready, s_nhits;
+    __shared__ SegLists s_seg[2];      // one per tile of the item
+    __shared__ uint32_t s_emit, s_ready, s_nhits;
     __shared__ __align__(16) uint32_t s_hist[kHistBins];  // score histogram / hit-group list / radix-select scratch
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tmp[2];
@@ -432,226 +469,235 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile, u
     const uint32_t sq = lane * p.n_queries + q;  // this (lane, query)'s slot in the per-query state arrays
     const uint64_t qb = rec->begin, qe = rec->begin + rec->n;
     const uint32_t T = p.tile_docs, units = T >> kDenseUnitShift;
-    // The query's running state (threshold, candidate list) is handed from tile to tile through
-    // global memory; tile t may start once tile t-1 of the same query has published (done[q] >= t).
+    // The query's running state (threshold, candidate list) is handed from item to item through
+    // global memory; step s may start once step s-1 of the same query has published (done[q] >= s).
     // Items are dispatched in tile-major order, so this is almost always already true: probe now,
-    // and only wait (before the fused pass) in the rare case it is not.
+    // and only wait (before the first fused pass) in the rare case it is not.
     if (tid == 0) s_ready = p.done == nullptr || step == 0 || ld_flag_u32(p.done + sq) >= step;
-    const SegDesc *__restrict__ desc = p.desc + (uint64_t)tile * p.n_terms;
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
+
+    // ---- first-round segment lookup of BOTH tiles: warp 0, the two descriptor loads of a lane in flight together
+    if (tid < kMaxSeg) {
+        SegDesc d0{0u, 0u}, d1{0u, 0u};
+        if (qb + tid < qe) {
+            const uint32_t t = tid < kRecInlineTerms ? rec->terms[tid] : p.q_terms[qb + tid];
+            if (t < p.n_terms) {  // DI_OOV_TERM and anything out of range: no postings
+                d0 = p.desc[(uint64_t)tile0 * p.n_terms + t];
+                if (n_sub > 1) d1 = p.desc[(uint64_t)(tile0 + 1) * p.n_terms + t];
+            }
+        }
+        fill_seg_lists(s_seg[0], d0, tid);
+        if (n_sub > 1) fill_seg_lists(s_seg[1], d1, tid);
+    }
 
     DI_PROF_DECL;
     uint64_t theta = 0;
-    uint32_t cnt0 = 0, f0 = 0, nf = 0;  // s_doff[f0 .. f0 + nf): dense segments left for the fused pass
-    bool first = true, touched = false, have_state = false;
-    for (uint64_t r0 = qb; first || r0 < qe; r0 += kMaxSeg) {
-        if (!first) __syncthreads();  // the previous round's readers of the segment lists are done
-        // ---- look up this round's (term, tile) segments: warp 0, one term per lane, ballot-compacted
-        if (tid < kMaxSeg) {
-            SegDesc d{0u, 0u};
-            if (r0 + tid < qe) {
-                const uint32_t t = (first && tid < kRecInlineTerms) ? rec->terms[tid] : p.q_terms[r0 + tid];
-                if (t < p.n_terms) d = desc[t];  // DI_OOV_TERM and anything out of range: no postings
+    uint32_t cnt0 = 0;
+    bool have_state = false, dirty = false;  // dirty: threshold or count changed
+    for (uint32_t sub = 0; sub < n_sub; ++sub) {
+        const uint32_t tile = tile0 + sub;
+        SegLists &L = s_seg[sub];
+        const SegDesc *__restrict__ desc = p.desc + (uint64_t)tile * p.n_terms;
+        uint32_t f0 = 0, nf = 0;  // L.doff[f0 .. f0 + nf): dense segments left for the fused pass
+        bool first = true, touched = false, skip = false;
+        for (uint64_t r0 = qb; first || r0 < qe; r0 += kMaxSeg) {
+            if (!first) {
+                __syncthreads();  // the previous round's readers of the segment lists are done
+                if (tid < kMaxSeg) {
+                    SegDesc d{0u, 0u};
+                    if (r0 + tid < qe) {
+                        const uint32_t t = p.q_terms[r0 + tid];
+                        if (t < p.n_terms) d = desc[t];
+                    }
+                    fill_seg_lists(L, d, tid);
+                }
             }
-            const bool is_dense = (d.n_flag & kDenseFlag) != 0, is_sparse = !is_dense && d.n_flag != 0;
-            const uint32_t bd = __ballot_sync(0xffffffffu, is_dense), bs = __ballot_sync(0xffffffffu, is_sparse);
-            const uint32_t su = is_sparse ? (d.n_flag & 0xFFFFu) : 0u;
-            uint32_t incl = su;
+            if (ACC32 && first) zero_words16(s_acc4, T / 4);  // overlaps the descriptor loads of warp 0
+            __syncthreads();
+            const uint32_t nd = L.nd, ns = L.ns;
+            const bool last = r0 + kMaxSeg >= qe;
+            if (first && last && nd + ns == 0) { skip = true; break; }  // query has no posting in this tile
+            if (!have_state && s_ready) {  // state already published: fetch it now (L2), it is needed only by the fused pass
+                theta = ld_cg_u64(p.theta + sq);
+                cnt0 = ld_cg_u32(p.cnt + sq);
+                have_state = true;
+            }
+            touched = touched || (nd + ns) != 0;
+            DI_PROF_MARK(0);  // segment lookup
+
+            // ---- phase 1: sparse segments. word = impact << 16 | byte offset of the accumulator word;
+            //      units [0, even) of a segment hold even documents, the rest odd ones.
+            if (ns) {
+                const uint32_t total = L.spref[ns];
+                // the current segment's bounds live in registers and are re-read only when a unit crosses into the
+                // next segment (segments are hundreds of units long for the terms queries actually use)
+                uint32_t seg = 0, seg_lo = 0, seg_hi = L.spref[1], seg_even = L.seven[0], seg_off = L.soff(0);
+                for (uint32_t u0 = tid; u0 < total; u0 += kSparseUnroll * kScoreThreads) {
+                    uint4 v[kSparseUnroll];
+                    bool odd[kSparseUnroll];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= (unsigned)o) incl += up;
+                    for (int j = 0; j < kSparseUnroll; ++j) {
+                        const uint32_t u = u0 + j * kScoreThreads;
+                        odd[j] = false;
+                        if (u < total) {
+                            if (u >= seg_hi) {
+                                do { ++seg; seg_hi = L.spref[seg + 1]; } while (u >= seg_hi);
+                                seg_lo = L.spref[seg];
+                                seg_even = L.seven[seg];
+                                seg_off = L.soff(seg);
+                            }
+                            const uint32_t lu = u - seg_lo;
+                            odd[j] = lu >= seg_even;
+                            v[j] = ldg_stream_v4(payload4 + seg_off + lu);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kSparseUnroll; ++j) {
+                        if (u0 + j * kScoreThreads < total) {
+                            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                            if (!ACC32) {
+                                char *base = reinterpret_cast<char *>(s_acc);
+                                if (!odd[j]) {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] >> 16);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i)
+                                        atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] & 0xFFFF0000u);
+                                }
+                            } else {
+                                const uint32_t par = odd[j] ? 1u : 0u;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[((w[i] & 0xFFFFu) >> 1) | par], w[i] >> 16);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();  // every atomic has landed before a thread reads its own accumulator words
             }
-            if (is_dense) s_doff[__popc(bd & lanemask_lt())] = d.off16;
-            if (is_sparse) {
-                const uint32_t j = __popc(bs & lanemask_lt());
-                s_soff[j] = d.off16;
-                s_seven[j] = d.n_flag >> 16;
-                s_spref[j] = incl - su;
+            DI_PROF_MARK(2);  // sparse
+
+            // ---- dense segments that do not go through the fused pass: plain read-modify-write
+            nf = (!ACC32 && last) ? min(nd, 4u) : 0u;
+            f0 = nd - nf;
+            if (!ACC32) {
+                for (uint32_t j0 = 0; j0 < f0; j0 += 4)
+                    dense_dispatch16<false>(f0 - j0 < 4 ? (int)(f0 - j0) : 4, s_acc4, payload4, L.off + j0, units, 0u);
+            } else if (nd) {
+                dense_pass32(s_acc4, payload4, L.off, (int)nd, units);
             }
-            if (tid == 31) s_spref[__popc(bs)] = incl;  // total units
-            if (tid == 0) { s_nd = __popc(bd); s_ns = __popc(bs); }
+            DI_PROF_MARK(1);  // dense (read-modify-write)
+            first = false;
         }
-        if (ACC32 && first) zero_words16(s_acc4, T / 4);  // overlaps the descriptor loads of warp 0
-        __syncthreads();
-        const uint32_t nd = s_nd, ns = s_ns;
-        const bool last = r0 + kMaxSeg >= qe;
-        if (first && last && nd + ns == 0) return false;  // query has no posting in this tile
-        if (first && s_ready) {  // state already published: fetch it now (L2), it is needed only by the fused pass
+        if (skip || !touched) continue;  // nothing was added: the accumulators are still zero
+
+        // ---- the query's state. Between done[q] == step and the publish after this item, this CTA is
+        //      the only reader and writer of the query's list.
+        if (!have_state) {
+            if (tid == 0) {
+                uint32_t spins = 0;
+                while (ld_flag_u32(p.done + sq) < step) {
+                    __nanosleep(128);
+                    if (++spins > (1u << 23)) __trap();  // > 1 s: a protocol bug must fail loudly, never hang the GPU
+                }
+            }
+            __syncthreads();
             theta = ld_cg_u64(p.theta + sq);
             cnt0 = ld_cg_u32(p.cnt + sq);
             have_state = true;
         }
-        touched = touched || (nd + ns) != 0;
-        DI_PROF_MARK(0);  // segment lookup
+        uint32_t ths = (uint32_t)(theta >> 32);
+        if (ths == 0) ths = 1;  // score 0 = document not touched: never a result (inverted_index.py:58-62)
+        uint64_t *__restrict__ cand = p.cand + (uint64_t)sq * p.cap;
+        const uint32_t doc_base = p.doc_lo + (tile << p.tile_shift);
+        // A document that only TIES the threshold score needs docid <= the threshold's docid. Tiles are
+        // visited in docid order, so the threshold's document lies in an earlier tile and every such tie in
+        // this tile loses: compare against score + 1 and keep the (many) ties out of the slow path.
+        if (theta != 0 && key_docid(theta) < doc_base) ++ths;
+        if (!ACC32 && ths > 0x10000u) ths = 0x10000u;  // a caller-given bound no 16-bit sum can reach: nothing hits
+        if (tid == 0) { s_emit = 0; s_nhits = 0; }
+        uint64_t theta_pre = 0;
+        __syncthreads();
+        DI_PROF_MARK(3);  // state wait
 
-        // ---- phase 1: sparse segments. word = impact << 16 | byte offset of the accumulator word;
-        //      units [0, even) of a segment hold even documents, the rest odd ones.
-        if (ns) {
-            const uint32_t total = s_spref[ns];
-            // the current segment's bounds live in registers and are re-read only when a unit crosses into the
-            // next segment (segments are hundreds of units long for the terms queries actually use)
-            uint32_t seg = 0, seg_lo = 0, seg_hi = s_spref[1], seg_even = s_seven[0], seg_off = s_soff[0];
-            for (uint32_t u0 = tid; u0 < total; u0 += kSparseUnroll * kScoreThreads) {
-                uint4 v[kSparseUnroll];
-                bool odd[kSparseUnroll];
-#pragma unroll
-                for (int j = 0; j < kSparseUnroll; ++j) {
-                    const uint32_t u = u0 + j * kScoreThreads;
-                    odd[j] = false;
-                    if (u < total) {
-                        if (u >= seg_hi) {
-                            do { ++seg; seg_hi = s_spref[seg + 1]; } while (u >= seg_hi);
-                            seg_lo = s_spref[seg];
-                            seg_even = s_seven[seg];
-                            seg_off = s_soff[seg];
-                        }
-                        const uint32_t lu = u - seg_lo;
-                        odd[j] = lu >= seg_even;
-                        v[j] = ldg_stream_v4(payload4 + seg_off + lu);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < kSparseUnroll; ++j) {
-                    if (u0 + j * kScoreThreads < total) {
-                        const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                        if (!ACC32) {
-                            char *base = reinterpret_cast<char *>(s_acc);
-                            if (!odd[j]) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] >> 16);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    atomicAdd(reinterpret_cast<uint32_t *>(base + (w[i] & 0xFFFFu)), w[i] & 0xFFFF0000u);
-                            }
-                        } else {
-                            const uint32_t par = odd[j] ? 1u : 0u;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[((w[i] & 0xFFFFu) >> 1) | par], w[i] >> 16);
-                        }
-                    }
-                }
-            }
-            __syncthreads();  // every atomic has landed before a thread reads its own accumulator words
-        }
-        DI_PROF_MARK(2);  // sparse
-
-        // ---- dense segments that do not go through the fused pass: plain read-modify-write
-        nf = (!ACC32 && last) ? min(nd, 4u) : 0u;
-        f0 = nd - nf;
+        // ---- phase 2: fused dense + threshold pass (16-bit), or the plain scan (32-bit).
+        //      s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
         if (!ACC32) {
-            for (uint32_t j0 = 0; j0 < f0; j0 += 4)
-                dense_dispatch16<false>(f0 - j0 < 4 ? (int)(f0 - j0) : 4, s_acc4, payload4, s_doff + j0, units, 0u);
-        } else if (nd) {
-            dense_pass32(s_acc4, payload4, s_doff, (int)nd, units);
-        }
-        DI_PROF_MARK(1);  // dense (read-modify-write)
-        first = false;
-    }
-    if (!touched) return false;
-
-    // ---- the query's state. Between done[q] == tile and the publish after this item, this CTA is
-    //      the only reader and writer of the query's list.
-    if (!have_state) {
-        if (tid == 0) {
-            uint32_t spins = 0;
-            while (ld_flag_u32(p.done + sq) < step) {
-                __nanosleep(128);
-                if (++spins > (1u << 23)) __trap();  // > 1 s: a protocol bug must fail loudly, never hang the GPU
-            }
+            const uint32_t tm = ths - 1u;
+            const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, L.off + f0, units, tm | (tm << 16));
+            record_hits16(mask, units, s_hist, &s_nhits);
+        } else {
+            scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
         }
         __syncthreads();
-        theta = ld_cg_u64(p.theta + sq);
-        cnt0 = ld_cg_u32(p.cnt + sq);
-    }
-    uint32_t ths = (uint32_t)(theta >> 32);
-    if (ths == 0) ths = 1;  // score 0 = document not touched: never a result (inverted_index.py:58-62)
-    uint64_t *__restrict__ cand = p.cand + (uint64_t)sq * p.cap;
-    const uint32_t doc_base = p.doc_lo + (tile << p.tile_shift);
-    // A document that only TIES the threshold score needs docid <= the threshold's docid. Tiles are
-    // visited in docid order, so the threshold's document lies in an earlier tile and every such tie in
-    // this tile loses: compare against score + 1 and keep the (many) ties out of the slow path.
-    if (theta != 0 && key_docid(theta) < doc_base) ++ths;
-    if (!ACC32 && ths > 0x10000u) ths = 0x10000u;  // a caller-given bound no 16-bit sum can reach: nothing hits
-    if (tid == 0) { s_emit = 0; s_nhits = 0; }
-    uint64_t theta_pre = 0;
-    __syncthreads();
-    DI_PROF_MARK(3);  // state wait
-
-    // ---- phase 2: fused dense + threshold pass (16-bit), or the plain scan (32-bit).
-    //      s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
-    if (!ACC32) {
-        const uint32_t tm = ths - 1u;
-        const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, s_doff + f0, units, tm | (tm << 16));
-        record_hits16(mask, units, s_hist, &s_nhits);
-    } else {
-        scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
-    }
-    __syncthreads();
-    if (s_nhits > (uint32_t)kHistBins) {
-        // Flooded: more groups than slots hold a document at or above the threshold (the first tiles of a
-        // frequent-term query whose bound is still loose). In the 16-bit form every hit group still holds its
-        // sums (the others are zero, i.e. below any threshold), so the accumulators can simply be re-scanned.
-        if ((uint32_t)theta == 0u) {
-            // No exact k-th key yet (nothing, or only a seed bound): pre-select inside the tile with a score
-            // histogram. Keeping every document of the bins that hold the tile's k best is exact (at least k
-            // of them score >= the cut), and the cut is a valid bound for the tiles that follow.
-            int shift = 0;
-            const uint32_t max_score = 255u * (uint32_t)min((uint64_t)(qe - qb), (uint64_t)65535);
-            while ((max_score >> shift) >= (uint32_t)kHistBins) ++shift;
-            for (uint32_t i = tid; i < (uint32_t)kHistBins; i += kScoreThreads) s_hist[i] = 0;
-            __syncthreads();
-            for (uint32_t g = tid; g < T / group_docs<ACC32>(); g += kScoreThreads) {
-                const uint4 x = s_acc4[g];
+        if (s_nhits > (uint32_t)kHistBins) {
+            // Flooded: more groups than slots hold a document at or above the threshold (the first tiles of a
+            // frequent-term query whose bound is still loose). In the 16-bit form every hit group still holds its
+            // sums (the others are zero, i.e. below any threshold), so the accumulators can simply be re-scanned.
+            if ((uint32_t)theta == 0u) {
+                // No exact k-th key yet (nothing, or only a seed bound): pre-select inside the tile with a score
+                // histogram. Keeping every document of the bins that hold the tile's k best is exact (at least k
+                // of them score >= the cut), and the cut is a valid bound for the tiles that follow.
+                int shift = 0;
+                const uint32_t max_score = 255u * (uint32_t)min((uint64_t)(qe - qb), (uint64_t)65535);
+                while ((max_score >> shift) >= (uint32_t)kHistBins) ++shift;
+                for (uint32_t i = tid; i < (uint32_t)kHistBins; i += kScoreThreads) s_hist[i] = 0;
+                __syncthreads();
+                for (uint32_t g = tid; g < T / group_docs<ACC32>(); g += kScoreThreads) {
+                    const uint4 x = s_acc4[g];
 #pragma unroll
-                for (int i = 0; i < group_docs<ACC32>(); ++i) {
-                    const uint32_t sc = group_score<ACC32>(x, i);
-                    // scores above the query-length bound exist only when a posting list names a document twice:
-                    // the top bin is kept whole, so clamping stays exact
-                    if (sc >= ths) atomicAdd(&s_hist[min(sc >> shift, (uint32_t)kHistBins - 1u)], 1u);
+                    for (int i = 0; i < group_docs<ACC32>(); ++i) {
+                        const uint32_t sc = group_score<ACC32>(x, i);
+                        // scores above the query-length bound exist only when a posting list names a document twice:
+                        // the top bin is kept whole, so clamping stays exact
+                        if (sc >= ths) atomicAdd(&s_hist[min(sc >> shift, (uint32_t)kHistBins - 1u)], 1u);
+                    }
+                }
+                __syncthreads();
+                const uint32_t bin = block_find_bin_from_top(s_hist, kHistBins, p.k, s_tmp);  // 0: fewer than k documents
+                if ((bin << shift) > ths) {
+                    ths = bin << shift;
+                    theta_pre = (uint64_t)ths << 32;
                 }
             }
+            __syncthreads();  // everybody has read s_nhits
+            if (tid == 0) s_nhits = 0;
             __syncthreads();
-            const uint32_t bin = block_find_bin_from_top(s_hist, kHistBins, p.k, s_tmp);  // 0: fewer than k documents
-            if ((bin << shift) > ths) {
-                ths = bin << shift;
-                theta_pre = (uint64_t)ths << 32;
-            }
+            scan_groups<ACC32, true>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
+            __syncthreads();
         }
-        __syncthreads();  // everybody has read s_nhits
-        if (tid == 0) s_nhits = 0;
+        expand_hits<ACC32>(s_acc4, s_hist, min(s_nhits, (uint32_t)kHistBins), ths, doc_base, theta, cand, cnt0, &s_emit);
         __syncthreads();
-        scan_groups<ACC32, true>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
-        __syncthreads();
-    }
-    expand_hits<ACC32>(s_acc4, s_hist, min(s_nhits, (uint32_t)kHistBins), ths, doc_base, theta, cand, cnt0, &s_emit);
-    __syncthreads();
-    DI_PROF_MARK(4);  // fused dense + threshold pass, emission
-    uint32_t n = cnt0 + s_emit;  // <= c0 + tile_docs <= cap
-    if (n > p.c0) {
-        // too many live candidates: keep exactly the k best and raise the threshold to the k-th
-        uint64_t kth;
-        if (n <= (T * (ACC32 ? 4u : 2u)) / 8u) {
-            // the accumulators are idle now: their shared memory stages the whole list (the usual case)
-            kth = block_cut_to_k_staged(cand, n, p.k, reinterpret_cast<uint64_t *>(s_acc4), s_hist, s_tmp,
-                                        &s_emit);
-            if (!ACC32) zero_words16(s_acc4, (n + 1u) / 2u);  // restore the invariant (ordered by the next item's barrier)
-            n = p.k;
-        } else {
-            kth = block_select_kth<true>(cand, n, p.k, s_hist, s_tmp);
-            n = block_compact_ge<true>(cand, n, kth, s_scan);
+        DI_PROF_MARK(4);  // fused dense + threshold pass, emission
+        uint32_t n = cnt0 + s_emit;  // <= c0 + tile_docs <= cap
+        dirty = dirty || n != cnt0 || theta_pre > theta;
+        if (n > p.c0) {
+            // too many live candidates: keep exactly the k best and raise the threshold to the k-th
+            if (n <= (T * (ACC32 ? 4u : 2u)) / 8u) {
+                // the accumulators are idle now: their shared memory stages the whole list (the usual case)
+                theta = block_cut_to_k_staged(cand, n, p.k, reinterpret_cast<uint64_t *>(s_acc4), s_hist, s_tmp,
+                                              &s_emit);
+                if (!ACC32) zero_words16(s_acc4, (n + 1u) / 2u);  // restore the invariant (ordered by the next barrier)
+                n = p.k;
+            } else {
+                theta = block_select_kth<true>(cand, n, p.k, s_hist, s_tmp);
+                n = block_compact_ge<true>(cand, n, theta, s_scan);
+            }  // theta >= theta_pre: k of the emitted keys are at or above that bound
+        } else if (theta_pre > theta) {
+            theta = theta_pre;
         }
-        if (tid == 0) p.theta[sq] = kth;  // >= theta_pre: k of the emitted keys are at or above that bound
-    } else if (theta_pre > theta) {
-        if (tid == 0) p.theta[sq] = theta_pre;
-    }
-    if (tid == 0) p.cnt[sq] = n;
-    DI_PROF_MARK(5);  // cut to k
+        cnt0 = n;
+        __syncthreads();  // s_emit / s_hist / the accumulators are free again (second tile, or the next item)
+        DI_PROF_MARK(5);  // cut to k
 #ifdef DI_PROFILE_PHASES
-    if (tid == 0 && p.prof) atomicAdd(p.prof + (size_t)tile * 8 + 7, 1ull);  // items that reached the fused pass
+        if (tid == 0 && p.prof) atomicAdd(p.prof + (size_t)tile * 8 + 7, 1ull);  // items that reached the fused pass
 #endif
-    return true;  // the query's state was read after done[q] >= tile was observed
+    }
+    if (tid == 0 && dirty) {
+        p.theta[sq] = theta;
+        p.cnt[sq] = cnt0;
+    }
+    return have_state;
 }
 
 // ---- launch form A: one launch per tile, grid = queries (kept for profiling single tiles) -----
@@ -659,20 +705,17 @@ template <bool ACC32>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS) score_tile_kernel(SearchArgs p, uint32_t tile)
 {
     extern __shared__ uint4 s_acc4[];
-    if (!ACC32) {
-        zero_words16(s_acc4, p.tile_docs / 8);
-        __syncthreads();
-    }
-    score_item<ACC32>(p, tile, blockIdx.x, 0, tile);  // p.done == nullptr: the launch boundary orders the tiles
+    if (!ACC32) zero_words16(s_acc4, p.tile_docs / 8);  // the item's first barrier orders it
+    score_item<ACC32>(p, tile, 1, blockIdx.x, 0, tile);  // p.done == nullptr: the launch boundary orders the tiles
 }
 
 // ---- launch form B: ONE persistent launch for all tiles of the batch ---------------------------
 // grid = resident CTAs; each CTA claims work items from a global counter in tile-major order
-// (item = tile * n_queries + slot), so at any moment the whole GPU works on one or two tiles (their
-// postings stay L2-resident) and there is no per-tile launch tail. The NEXT item is claimed while the current
-// one is processed (the atomic's round trip to L2 is off the critical path). After an item, done[q] = tile + 1
-// is published with release semantics; the next tile of the same query acquires it. Waits only ever point at
-// items with a smaller index, and claims are handed out in index order, so the protocol cannot deadlock.
+// (item = step * n_queries + slot, step = a pair of adjacent tiles), so at any moment the whole GPU works on a few
+// tiles (their postings stay L2-resident) and there is no per-tile launch tail. The NEXT item is claimed while the
+// current one is processed (the atomic's round trip to L2 is off the critical path). After an item,
+// done[q] = step + 1 is published with release semantics; the next step of the same query acquires it. Waits only
+// ever point at items with a smaller index, and claims are handed out in index order, so the protocol cannot deadlock.
 template <bool ACC32>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS)
 score_persistent_kernel(SearchArgs p, unsigned long long *counter)
@@ -680,7 +723,8 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
     extern __shared__ uint4 s_acc4[];
     __shared__ unsigned long long s_item;
     const uint32_t n_virtual = p.lanes * p.n_queries;  // (lane, query) chains
-    const unsigned long long n_items = (unsigned long long)p.tiles_per_lane * n_virtual;
+    const uint32_t steps_per_lane = (p.tiles_per_lane + kTilesPerItem - 1) / kTilesPerItem;
+    const unsigned long long n_items = (unsigned long long)steps_per_lane * n_virtual;
     const bool narrow = n_items <= 0xFFFFFFFFull;  // 32-bit item arithmetic (a 64-bit divide is ~100 instructions)
     unsigned long long next = 0;
     if (threadIdx.x == 0) next = atomicAdd(counter, 1ull);
@@ -694,7 +738,7 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
         __syncthreads();
         const unsigned long long item = s_item;
         if (item >= n_items) break;
-        // step-major: all chains advance together, so the GPU works on `lanes` tiles at a time
+        // step-major: all chains advance together, so the GPU works on `lanes` tile pairs at a time
         uint32_t step, v;
         if (narrow) {
             step = (uint32_t)item / n_virtual;
@@ -704,13 +748,14 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
             v = (uint32_t)(item % n_virtual);
         }
         const uint32_t lane = p.lanes == 1 ? 0u : v / p.n_queries, slot = v - lane * p.n_queries;
-        const uint32_t tile = lane * p.tiles_per_lane + step;
-        if (tile >= p.n_tiles) continue;  // the last lane may be shorter; nobody waits on these steps
-        const bool synced = score_item<ACC32>(p, tile, slot, lane, step);
+        const uint32_t tile0 = lane * p.tiles_per_lane + step * kTilesPerItem;
+        const uint32_t lane_end = min((lane + 1) * p.tiles_per_lane, p.n_tiles);
+        if (tile0 >= lane_end) continue;  // the last lane may be shorter; nobody waits on these steps
+        const bool synced = score_item<ACC32>(p, tile0, min((uint32_t)kTilesPerItem, lane_end - tile0), slot, lane, step);
         // Hand-off: CTA barrier, then ONE thread publishes with a release store (MEMBAR.GPU + store). The
         // barrier orders every thread's candidate / threshold writes before the release (the pattern
-        // cooperative-groups grid sync relies on). done[q] must grow one tile at a time: an item that had
-        // nothing to do in this tile still waits for the previous tile before announcing the next.
+        // cooperative-groups grid sync relies on). done[q] must grow one step at a time: an item that had
+        // nothing to do in its tiles still waits for the previous step before announcing the next.
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t *flag = p.done + lane * p.n_queries + p.recs[slot].q;

@@ -15,6 +15,36 @@ namespace di {
 constexpr uint32_t kSortSmemKeys = 4096;
 
 // ---------------------------------------------------------------------------- K4: final select + sort
+// n keys resident in shared memory (s_keys has room for smem_keys >= n entries, a power of two): cut them to the k
+// best, sort descending (score desc, docid asc) and write them to out[0 .. n_out). Returns n_out; *kth receives the
+// k-th key when k keys were written, else 0.
+__device__ __forceinline__ uint32_t block_topk_sorted_smem(uint64_t *s_keys, uint32_t n, uint32_t k, uint32_t smem_keys,
+                                                           uint64_t *out, uint32_t *s_hist, uint32_t *s_scan, uint32_t *s_tmp,
+                                                           uint64_t *kth_out)
+{
+    uint64_t *keys = s_keys;
+    if (n > k) {
+        const uint64_t kth = block_select_kth(s_keys, n, k, s_hist, s_tmp);
+        uint32_t k_pow2 = 1;
+        while (k_pow2 < k) k_pow2 <<= 1;
+        if (n + k_pow2 <= smem_keys) {  // room behind the list: pack the k survivors there (any order, sorted next)
+            keys = s_keys + n;
+            n = block_compact_ge_unordered(s_keys, n, kth, keys, s_tmp);
+        } else {
+            n = block_compact_ge(s_keys, n, kth, s_scan);
+        }
+    }
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (uint32_t i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(keys, np2);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = keys[i];
+    if (kth_out) *kth_out = n == k ? keys[k - 1] : 0ull;
+    __syncthreads();  // s_keys may be refilled by the caller
+    return n;
+}
+
 // One CTA per query: cut the candidate list to the k best and sort them descending by key
 // (score desc, docid asc). Sorting happens in shared memory when the list fits.
 __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *cand_all, const uint32_t *cnt, uint32_t cap,
@@ -32,24 +62,7 @@ __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *
     if (n <= smem_keys) {  // usual case: everything happens in shared memory after one coalesced read
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = cand[i];
         __syncthreads();
-        uint64_t *keys = s_keys;
-        if (n > k) {
-            const uint64_t kth = block_select_kth(s_keys, n, k, s_hist, s_tmp);
-            uint32_t k_pow2 = 1;
-            while (k_pow2 < k) k_pow2 <<= 1;
-            if (n + k_pow2 <= smem_keys) {  // room behind the list: pack the k survivors there (any order, sorted next)
-                keys = s_keys + n;
-                n = block_compact_ge_unordered(s_keys, n, kth, keys, s_tmp);
-            } else {
-                n = block_compact_ge(s_keys, n, kth, s_scan);
-            }
-        }
-        uint32_t np2 = 1;
-        while (np2 < n) np2 <<= 1;
-        for (uint32_t i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
-        __syncthreads();
-        bitonic_sort_desc(keys, np2);
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = keys[i];
+        n = block_topk_sorted_smem(s_keys, n, k, smem_keys, out, s_hist, s_scan, s_tmp, nullptr);
         if (threadIdx.x == 0) out_counts[q] = n;
         return;
     }
@@ -123,59 +136,90 @@ __global__ void merge_check_kernel(const uint64_t *__restrict__ keys_in, const u
     }
 }
 
-// ---------------------------------------------------------------------------- K5 over peer memory
-// The gather half of the merge WITHOUT a collective: rows[s] / counts[s] point at shard s's sorted key rows
-// ([.][row_stride]) and counts where that shard's search wrote them — on a peer GPU, mapped into this process
-// (NVLink loads). One CTA per query reads the first min(count, k_in) keys of every shard's row straight into
-// the merge list; finalize_topk_kernel then selects + sorts as in the all-gather form. query_ids (nullable)
-// restricts the merge to a subset of the queries (the unproven ones, second pass with k_in = row_stride).
-constexpr uint32_t kMaxP2PShards = 64;
+// ---------------------------------------------------------------------------- K5 over peer memory (fused)
+// The exchange step of the sharded search as ONE kernel and NO collective: rows[s] / counts[s] point at shard s's
+// sorted key rows ([.][row_stride]) and counts where that shard's own search wrote them — on a peer GPU, mapped into
+// this process (CUDA IPC; the loads travel over NVLink / NVSwitch). The queries are PARTITIONED over the ranks: this
+// rank merges only its own slice [q_first, q_first + gridDim.x), so gathered bytes and merge work per GPU shrink with
+// the number of GPUs. One CTA per query:
+//   1. pull the first min(count, k_in) keys of every shard's row straight into shared memory (k_in ~ 1.25 k / G);
+//   2. select the k best and sort them (same total order as one GPU: bit-identical result);
+//   3. PROVE the result: a shard that holds more than k_in keys hides only keys below its k_in-th, so the merge is
+//      exact iff that key <= the merged k-th;
+//   4. a query that fails the proof pulls the full rows (they are already there, nothing is searched twice) and
+//      selects again — inside the same CTA: no host round trip, no second launch, no compaction of query ids.
+constexpr uint32_t kMaxPeerShards = 64;
+constexpr int kMergeThreads = 256;
 
-__global__ void __launch_bounds__(256) merge_gather_p2p_kernel(const uint64_t *const *__restrict__ rows,
-                                                               const uint32_t *const *__restrict__ counts, uint32_t n_shards,
-                                                               const uint32_t *__restrict__ query_ids, uint32_t row_stride,
-                                                               uint32_t k_in, uint64_t *__restrict__ cand,
-                                                               uint32_t *__restrict__ cnt, uint32_t cap)
+__global__ void __launch_bounds__(kMergeThreads) merge_pull_kernel(const uint64_t *const *__restrict__ rows,
+                                                                 const uint32_t *const *__restrict__ counts,
+                                                                 uint32_t n_shards, uint32_t q_first, uint32_t row_stride,
+                                                                 uint32_t k_in, uint32_t k, uint32_t smem_keys,
+                                                                 uint64_t *__restrict__ out_keys,
+                                                                 uint32_t *__restrict__ out_counts,
+                                                                 uint32_t *__restrict__ n_second_pass)
 {
-    __shared__ uint32_t s_pref[kMaxP2PShards + 1];
-    __shared__ const uint64_t *s_row[kMaxP2PShards];
-    const uint32_t i = blockIdx.x, q = query_ids ? query_ids[i] : i;
+    extern __shared__ uint64_t s_keys[];  // smem_keys entries >= n_shards * min(row_stride, k)
+    __shared__ __align__(16) uint32_t s_hist[kSelectSmemWords];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tmp[2];
+    __shared__ uint32_t s_cnt[kMaxPeerShards], s_pref[kMaxPeerShards + 1], s_bad;
+    __shared__ const uint64_t *s_row[kMaxPeerShards];
+    const uint32_t i = blockIdx.x, q = q_first + i;
     if (threadIdx.x < n_shards) {  // one remote 4-byte read per shard, all in flight together
         const uint32_t c = counts[threadIdx.x][q];
-        s_pref[threadIdx.x + 1] = c < k_in ? c : k_in;
+        s_cnt[threadIdx.x] = c < row_stride ? c : row_stride;
         s_row[threadIdx.x] = rows[threadIdx.x] + (uint64_t)q * row_stride;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_pref[0] = 0;
-        for (uint32_t s = 0; s < n_shards; ++s) s_pref[s + 1] += s_pref[s];
+    uint64_t *out = out_keys + (uint64_t)i * k;
+    uint32_t n_out = 0;
+    for (uint32_t lim = k_in < row_stride ? k_in : row_stride;; lim = row_stride) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (uint32_t s = 0; s < n_shards; ++s) {
+                s_pref[s] = run;
+                run += s_cnt[s] < lim ? s_cnt[s] : lim;
+            }
+            s_pref[n_shards] = run;
+            s_bad = 0;
+        }
+        __syncthreads();
+        const uint32_t total = s_pref[n_shards];
+        uint32_t s = 0;
+        for (uint32_t j = threadIdx.x; j < total; j += kMergeThreads) {  // flattened over the shards: loads from different peers overlap
+            while (j >= s_pref[s + 1]) ++s;
+            s_keys[j] = s_row[s][j - s_pref[s]];
+        }
+        __syncthreads();
+        uint64_t kth;
+        n_out = block_topk_sorted_smem(s_keys, total, k, smem_keys, out, s_hist, s_scan, s_tmp, &kth);
+        if (lim == row_stride) break;  // full rows: nothing is hidden
+        if (threadIdx.x < n_shards && s_cnt[threadIdx.x] > lim && s_row[threadIdx.x][lim - 1] > kth) s_bad = 1;
+        __syncthreads();
+        if (!s_bad) break;
+        if (threadIdx.x == 0 && n_second_pass) atomicAdd(n_second_pass, 1u);
     }
-    __syncthreads();
-    const uint32_t total = s_pref[n_shards];
-    uint32_t s = 0;
-    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {  // flattened over the shards: loads of different peers overlap
-        while (j >= s_pref[s + 1]) ++s;
-        cand[(uint64_t)i * cap + j] = s_row[s][j - s_pref[s]];
-    }
-    if (threadIdx.x == 0) cnt[i] = total;
+    if (threadIdx.x == 0) out_counts[i] = n_out;
 }
 
-// proof of completeness for the peer-memory form (see merge_check_kernel): keys_out / counts_out / incomplete are
-// indexed like the launch (row i = query query_ids[i]).
-__global__ void merge_check_p2p_kernel(const uint64_t *const *__restrict__ rows, const uint32_t *const *__restrict__ counts,
-                                       uint32_t n_shards, const uint32_t *__restrict__ query_ids, uint32_t n_queries,
-                                       uint32_t row_stride, uint32_t k_in, uint32_t k_out,
-                                       const uint64_t *__restrict__ keys_out, const uint32_t *__restrict__ counts_out,
-                                       uint32_t *__restrict__ incomplete)
+// Cross-GPU barrier on the launching stream, without a collective library: flags[r] points at rank r's flag array
+// ([n_ranks] words, peer-mapped). Thread s tells rank s "rank `me` reached `epoch`" with a system-scope release
+// (everything this GPU wrote before — the search results — is visible to a peer that observes the flag), then waits
+// until rank s has said the same to us. One CTA; epochs only grow, so the flags are never reset.
+__global__ void peer_barrier_kernel(uint32_t *const *__restrict__ flags, uint32_t n_ranks, uint32_t me, uint32_t epoch)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_queries; i += gridDim.x * blockDim.x) {
-        const uint32_t q = query_ids ? query_ids[i] : i;
-        const uint32_t n = counts_out[i];
-        const uint64_t kth = n == k_out ? keys_out[(uint64_t)i * k_out + k_out - 1] : 0ull;  // 0: fewer than k found
-        uint32_t bad = 0;
-        for (uint32_t s = 0; s < n_shards; ++s)  // a shard holding more than k_in keys hides those below the k_in-th
-            if (counts[s][q] > k_in && rows[s][(uint64_t)q * row_stride + k_in - 1] > kth) bad = 1;
-        incomplete[i] = bad;
+    const uint32_t s = threadIdx.x;
+    if (s >= n_ranks) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags[s] + me), "r"(epoch) : "memory");
+    const uint32_t *mine = flags[me] + s;
+    uint32_t v, spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        __nanosleep(200);
+        if (++spins > (1u << 24)) __trap();  // seconds: a rank that never arrives must fail loudly, not hang the box
     }
 }
 

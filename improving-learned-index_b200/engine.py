@@ -195,10 +195,14 @@ def merge_topk_device(d_keys_in, d_counts_in, n_shards: int, n_queries: int, top
                                       N.ptr(d_keys_out), N.ptr(d_counts_out), N.ptr(d_incomplete), stream))
 
 
-def merge_rows_p2p_device(d_row_ptrs, d_count_ptrs, n_shards: int, n_queries: int, row_stride: int, k_in: int, top_k: int,
-                          d_keys_out, d_counts_out, stream: int = 0, d_query_ids=None, d_incomplete=None):
-    """K5 over peer memory (experimental, DI_B200_P2P=1): d_row_ptrs / d_count_ptrs are device tables of
-    n_shards pointers to the shards' own result rows (peer memory); no all-gather."""
-    N.check(N.lib().di_merge_rows_p2p_dev(N.ptr(d_row_ptrs), N.ptr(d_count_ptrs), n_shards, N.ptr(d_query_ids), n_queries,
-                                          row_stride, k_in, top_k, N.ptr(d_keys_out), N.ptr(d_counts_out),
-                                          N.ptr(d_incomplete), stream))
+def merge_pull_device(d_row_ptrs, d_count_ptrs, n_shards: int, q_first: int, n_queries: int, row_stride: int, k_in: int,
+                      top_k: int, d_keys_out, d_counts_out, stream: int = 0, d_n_second_pass=None):
+    """K5 fused with its exchange: d_row_ptrs / d_count_ptrs are device tables of n_shards pointers to the shards' own
+    sorted rows (peer memory); merges queries [q_first, q_first + n_queries) — pull, select, prove, second pass —
+    in one kernel."""
+    N.check(N.lib().di_merge_pull_dev(N.ptr(d_row_ptrs), N.ptr(d_count_ptrs), n_shards, q_first, n_queries, row_stride, k_in,
+                                      top_k, N.ptr(d_keys_out), N.ptr(d_counts_out), N.ptr(d_n_second_pass), stream))
+
+
+def peer_barrier_device(d_flag_ptrs, n_ranks: int, my_rank: int, epoch: int, stream: int = 0):
+    N.check(N.lib().di_peer_barrier_dev(N.ptr(d_flag_ptrs), n_ranks, my_rank, epoch, stream))

@@ -17,9 +17,13 @@ the proof (with docid-ordered ties the boundary tie group of a short query sits 
 so one shard holds most of the top-k) the full rows — already computed — are gathered and merged; nothing
 is searched twice.
 
-Experimental (DI_B200_P2P=1, not yet validated on hardware in round 1): the shards' rows live in torch symmetric
-memory and K5 reads the peers' rows directly over NVLink (`di_merge_rows_p2p_dev`) after one cross-GPU barrier —
-no all-gather, no staging copy, and the second pass reads the unproven queries' full rows in place.
+On GPUs the exchange is ONE fused kernel over peer memory and no collective at all (`search_partitioned`): every
+rank's search writes its sorted rows into a CUDA-IPC buffer that all peers have mapped (`PeerExchange`), a one-CTA
+flag barrier orders the searches (`di_peer_barrier_dev`), and `di_merge_pull_dev` lets rank r merge ITS slice of the
+queries by pulling the first k_in keys of every shard's row over NVLink straight into shared memory, proving the
+result, and pulling the full rows of the queries that fail the proof — inside the same kernel, without a host
+round trip. Merge work, pulled bytes and the device-to-host copy of the results are all divided by the number of GPUs.
+The all-gather form below stays as the transport-agnostic fallback (gloo in the CPU tests, or when IPC is unavailable).
 
 The collective and the two compute steps are injected, so the plumbing (ranges, tensor layout of
 the gather, count handling, the two-round protocol) is testable on CPU with world_size 2 while the
@@ -58,6 +62,66 @@ def unpack_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return (k >> np.uint64(32)).astype(np.int32), ~(k & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 
 
+class PeerExchange:
+    """This rank's peer-visible result buffers and the tables of every rank's: two sets of (rows [q_cap, k] u64,
+    counts [q_cap] u32) that alternate between calls — the barrier of call t + 1 is what protects set t from being
+    overwritten while a peer still reads it — and one flag array for the stream barrier. Memory comes from the
+    library (cudaMalloc + CUDA IPC handle); torch.distributed only carries the 64-byte handles once."""
+
+    def __init__(self, device, rank: int, world: int, q_cap: int, k: int, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _native as N
+        self.N, self.torch = N, torch
+        self.rank, self.world, self.q_cap, self.k = rank, world, q_cap, k
+        self.calls = self.epoch = 0
+        L = N.lib()
+        sizes = [q_cap * k * 8, q_cap * 4, q_cap * k * 8, q_cap * 4, max(world, 64) * 4]     # rows0 counts0 rows1 counts1 flags
+        self.own, handles = [], []
+        for nbytes in sizes:
+            ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            N.check(L.di_shared_alloc(nbytes, ctypes.byref(ptr), h))
+            self.own.append(ptr.value)
+            handles.append(h.raw)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles, group=group)
+        self.opened, table = [], []
+        for r in range(world):
+            if r == rank:
+                table.append(list(self.own))
+                continue
+            ptrs = []
+            for h in everyone[r]:
+                ptr = ctypes.c_void_p()
+                N.check(L.di_shared_open(h, ctypes.byref(ptr)))
+                ptrs.append(ptr.value)
+                self.opened.append(ptr.value)
+            table.append(ptrs)
+        as_table = lambda j: torch.tensor([table[r][j] for r in range(world)], dtype=torch.int64, device=device)
+        self.sets = [(self.own[0], self.own[1], as_table(0), as_table(1)), (self.own[2], self.own[3], as_table(2), as_table(3))]
+        self.flag_table = as_table(4)
+        dist.barrier(group=group)               # nobody starts a barrier kernel before every rank has mapped the flags
+
+    def next_set(self):
+        s = self.sets[self.calls % 2]
+        self.calls += 1
+        return s
+
+    def barrier(self, stream: int):
+        self.epoch += 1
+        self.N.check(self.N.lib().di_peer_barrier_dev(self.flag_table.data_ptr(), self.world, self.rank, self.epoch, stream))
+
+    def close(self):
+        L = self.N.lib()
+        self.torch.cuda.synchronize()
+        for p in self.opened:
+            L.di_shared_close(p)
+        for p in self.own:
+            L.di_shared_free(p)
+        self.opened, self.own = [], []
+
+
 class ShardedSearcher:
     """search(): local best keys on this rank's shard -> all_gather of the first columns -> merge + proof
     (-> all_gather of the full rows of the unproven queries -> merge).
@@ -71,7 +135,7 @@ class ShardedSearcher:
     incomplete [Q] int32) writes the global top-k and flags the queries whose merge is not proven exact.
     """
 
-    def __init__(self, local_search: Callable, merge: Callable, device, group=None, rows_per_shard=None, p2p_merge=None):
+    def __init__(self, local_search: Callable, merge: Callable, device, group=None, rows_per_shard=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -83,8 +147,8 @@ class ShardedSearcher:
         self._buffers = {}
         self.rows_per_shard = rows_per_shard   # optional override of shard_k: k -> keys per shard in round 1
         self.round2_queries = 0          # how many queries of the last search needed their full rows gathered
-        self.p2p_merge = p2p_merge       # experimental: merge straight from the peers' symmetric-memory rows
-        self._p2p = None
+        self._peer = None                # PeerExchange of the fused path (CUDA, world > 1), created on first use
+        self._second = None
 
     @classmethod
     def for_device_index(cls, index: "engine.DeviceIndex", device, group=None) -> "ShardedSearcher":
@@ -97,13 +161,7 @@ class ShardedSearcher:
         def merge(g_keys, g_counts, n_shards, n_q, k_in, k, out_keys, out_counts, incomplete):
             engine.merge_topk_device(g_keys, g_counts, n_shards, n_q, k, out_keys, out_counts,
                                      torch.cuda.current_stream().cuda_stream, k_in=k_in, d_incomplete=incomplete)
-        p2p_merge = None
-        if os.environ.get("DI_B200_P2P") == "1":
-            def p2p_merge(row_ptrs, count_ptrs, n_shards, query_ids, n_q, row_stride, k_in, k, out_keys, out_counts, incomplete):
-                engine.merge_rows_p2p_device(row_ptrs, count_ptrs, n_shards, n_q, row_stride, k_in, k, out_keys, out_counts,
-                                             torch.cuda.current_stream().cuda_stream, d_query_ids=query_ids,
-                                             d_incomplete=incomplete)
-        return cls(local_search, merge, device, group, p2p_merge=p2p_merge)
+        return cls(local_search, merge, device, group)
 
     def _buf(self, name, shape, dtype):
         key = (name, tuple(shape))
@@ -136,52 +194,56 @@ class ShardedSearcher:
                    k_in, k, out_keys, out_counts, incomplete)
         return out_keys, out_counts, incomplete if prove else None
 
-    def _search_tensors_p2p(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
-        """Peer-memory form of search_tensors (world > 1, CUDA): rows are written into symmetric memory, one
-        cross-GPU barrier, then K5 reads the peers' rows over NVLink. Two buffer sets alternate, so the barrier of
-        the next call is what protects a set from being overwritten while a peer still reads it."""
-        import torch.distributed._symmetric_memory as symm
+    # ---- fused exchange over peer memory (CUDA only) --------------------------------------------------
+    def peer_exchange_available(self) -> bool:
+        return self.world > 1 and getattr(self.device, "type", "cpu") == "cuda" and os.environ.get("DI_B200_NO_PEER") != "1"
+
+    def search_partitioned(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
+        """Fused form: returns ((q_lo, q_hi), keys [q_hi - q_lo, k] int64, counts [q_hi - q_lo] int32) — the GLOBAL
+        top-k of THIS rank's slice of the queries (`shard_range(n_queries, world, rank)`); the slices of all ranks
+        tile the batch. No collective and no host synchronisation in the call. The returned tensors are owned by
+        the searcher and overwritten by the next call."""
         torch = self.torch
-        if self._p2p is None or self._p2p["q"] < n_queries or self._p2p["k"] != k:   # collective: same sizes on every rank
-            q_cap = n_queries + n_queries // 4 + 1
-            group = self.group if self.group is not None else self.dist.group.WORLD
-            sets = []
-            for _ in range(2):
-                rows = symm.empty(q_cap * k, dtype=torch.int64, device=self.device)
-                cnts = symm.empty(q_cap, dtype=torch.int32, device=self.device)
-                sets.append((rows, cnts, symm.rendezvous(rows, group), symm.rendezvous(cnts, group)))
-            self._p2p = {"q": q_cap, "k": k, "sets": sets, "calls": 0}
-        rows, cnts, h_rows, h_cnts = self._p2p["sets"][self._p2p["calls"] % 2]
-        self._p2p["calls"] += 1
-        keys, counts = rows[:n_queries * k].view(n_queries, k), cnts[:n_queries]
-        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)
-        h_rows.barrier(channel=0)            # every shard's rows and counts are written
+        stream = torch.cuda.current_stream().cuda_stream
+        if self._peer is None or self._peer.q_cap < n_queries or self._peer.k != k:    # collective: same sizes on every rank
+            if self._peer is not None:
+                self._peer.close()
+            self._peer = PeerExchange(self.device, self.rank, self.world, n_queries + n_queries // 4 + 1, k, self.group)
+            self._second = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ex = self._peer
+        rows, counts, row_table, cnt_table = ex.next_set()
+        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, rows, counts)    # this shard's sorted rows
+        ex.barrier(stream)                                   # every shard's rows are written and visible
         k_in = min(k, self.rows_per_shard(k)) if self.rows_per_shard else shard_k(k, self.world)
-        out_keys = self._flat("p_out_keys", n_queries * k, torch.int64).view(n_queries, k)
-        out_counts = self._flat("p_out_counts", n_queries, torch.int32)
-        incomplete = self._flat("p_incomplete", n_queries, torch.int32) if k_in < k else None
-        self.p2p_merge(h_rows.buffer_ptrs_dev, h_cnts.buffer_ptrs_dev, self.world, None, n_queries, k, k_in, k,
-                       out_keys, out_counts, incomplete)
-        if incomplete is not None:
-            redo = torch.nonzero(incomplete).flatten()
-            if redo.numel():
-                n_redo = int(redo.numel())
-                self.round2_queries = n_redo
-                k2 = self._flat("p_k2", n_redo * k, torch.int64).view(n_redo, k)
-                c2 = self._flat("p_c2", n_redo, torch.int32)
-                self.p2p_merge(h_rows.buffer_ptrs_dev, h_cnts.buffer_ptrs_dev, self.world, redo.to(torch.int32), n_redo, k, k, k,
-                               k2, c2, None)
-                out_keys[redo] = k2
-                out_counts[redo] = c2
-        return out_keys, out_counts
+        q_lo, q_hi = shard_range(n_queries, self.world, self.rank)
+        n_own = q_hi - q_lo
+        out_keys = self._flat("own_keys", max(n_own, 1) * k, torch.int64)[:n_own * k].view(n_own, k)
+        out_counts = self._flat("own_counts", max(n_own, 1), torch.int32)[:n_own]
+        self._second.zero_()
+        engine.merge_pull_device(row_table, cnt_table, self.world, q_lo, n_own, k, k_in, k, out_keys, out_counts,
+                                 stream, d_n_second_pass=self._second)
+        self.round2_queries = self._second       # device counter of this rank's slice (read it after a synchronize)
+        return (q_lo, q_hi), out_keys, out_counts
 
     def search_tensors(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
         """Device-level entry: returns (keys [Q,k] int64, counts [Q] int32) tensors holding the GLOBAL top-k.
         The returned tensors are owned by the searcher and overwritten by the next call."""
         torch = self.torch
         self.round2_queries = 0
-        if self.p2p_merge is not None and self.world > 1:
-            return self._search_tensors_p2p(d_q_terms, d_q_offsets, n_queries, max_len, k)
+        if self.peer_exchange_available():
+            # fused path + one all-gather of the finished slices (callers that can work on a slice use search_partitioned)
+            (q_lo, q_hi), own_keys, own_counts = self.search_partitioned(d_q_terms, d_q_offsets, n_queries, max_len, k)
+            per = -(-n_queries // self.world)
+            pad_keys = self._flat("pad_keys", per * k, torch.int64).view(per, k)
+            pad_counts = self._flat("pad_counts", per, torch.int32)
+            pad_counts.zero_()
+            pad_keys[:q_hi - q_lo].copy_(own_keys)
+            pad_counts[:q_hi - q_lo].copy_(own_counts)
+            all_keys = self._flat("all_keys", self.world * per * k, torch.int64)
+            all_counts = self._flat("all_counts", self.world * per, torch.int32)
+            self.dist.all_gather_into_tensor(all_keys.view(self.world * per, k), pad_keys, group=self.group)
+            self.dist.all_gather_into_tensor(all_counts, pad_counts, group=self.group)
+            return all_keys.view(self.world * per, k)[:n_queries], all_counts[:n_queries]
         keys = self._flat("keys", n_queries * k, torch.int64).view(n_queries, k)
         counts = self._flat("counts", n_queries, torch.int32)
         self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)   # this shard's sorted top-k

@@ -192,20 +192,31 @@ int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_counts_in,
                       uint32_t n_shards, uint32_t n_queries, uint32_t k_in, uint32_t top_k,
                       uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_incomplete, void *stream);
 
-/* K5 over peer memory (no collective): d_rows[s] / d_counts[s] are DEVICE-resident tables of n_shards pointers to
- * every shard's sorted key rows ([.][row_stride]) and counts where that shard's own di_search_dev wrote them
- * — peer GPU memory mapped into this process (e.g. torch symmetric memory `buffer_ptrs_dev`); the caller orders
- * the shards' searches before this call with a cross-GPU barrier. One kernel reads the first min(count, k_in)
- * keys of each row over NVLink while it builds the merge list, then selects + sorts like di_merge_topk_dev.
- * d_query_ids (NULL = all queries 0..n_queries-1) merges only the listed queries; output rows, counts and
- * flags are indexed by position in that list. d_incomplete as in di_merge_topk_dev (never set when
- * k_in == row_stride). EXPERIMENTAL in round 1: compiled and exported, exercised only by
- * tests/test_gpu_p2p.py and sharded.py when DI_B200_P2P=1.
- */
-int di_merge_rows_p2p_dev(const uint64_t *const *d_rows, const uint32_t *const *d_counts, uint32_t n_shards,
-                          const uint32_t *d_query_ids, uint32_t n_queries, uint32_t row_stride, uint32_t k_in,
-                          uint32_t top_k, uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_incomplete,
-                          void *stream);
+/* K5 over peer memory: the exchange step as ONE fused kernel, no collective. d_rows / d_counts are DEVICE-resident tables
+ * of n_shards pointers to every shard's sorted key rows ([.][row_stride]) and counts, where that shard's own
+ * di_search_dev wrote them — peer GPU memory mapped into this process (di_shared_alloc / di_shared_open below); the
+ * caller orders the shards' searches before this call with di_peer_barrier_dev. The queries are partitioned over the
+ * ranks: this call merges queries [q_first, q_first + n_queries) only; output rows / counts are indexed from 0.
+ * Per query, one CTA pulls the first min(count, k_in) keys of each shard's row over NVLink into shared memory, selects
+ * and sorts the top_k, proves the result complete (a shard holding more than k_in keys hides only keys below its
+ * k_in-th) and, for a query that fails the proof, pulls the full rows and selects again — all inside the kernel.
+ * *d_n_second_pass (optional counter, caller-zeroed) counts those queries. row_stride <= top_k. */
+int di_merge_pull_dev(const uint64_t *const *d_rows, const uint32_t *const *d_counts, uint32_t n_shards,
+                      uint32_t q_first, uint32_t n_queries, uint32_t row_stride, uint32_t k_in, uint32_t top_k,
+                      uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_n_second_pass, void *stream);
+
+/* Peer-visible device memory for the rows above (one process per GPU): di_shared_alloc = cudaMalloc (zero-filled) +
+ * a 64-byte CUDA IPC handle that the caller sends to the other ranks (any transport); di_shared_open maps a peer's
+ * allocation into this process (peer access over NVLink is enabled on first use). */
+int di_shared_alloc(uint64_t bytes, void **d_ptr, uint8_t handle_out[64]);
+int di_shared_open(const uint8_t handle[64], void **d_ptr);
+int di_shared_close(void *d_ptr);
+int di_shared_free(void *d_ptr);
+/* Cross-GPU barrier ON THE STREAM (a one-CTA kernel, no host involvement): d_flags is a device table of n_ranks
+ * pointers, entry r = rank r's flag array of n_ranks u32 (di_shared_alloc'ed, zero at start). Every rank calls it
+ * with the same, strictly increasing epoch (1, 2, ...). Work enqueued before it on every rank's stream is complete
+ * and visible to all ranks' work enqueued after it. */
+int di_peer_barrier_dev(uint32_t *const *d_flags, uint32_t n_ranks, uint32_t my_rank, uint32_t epoch, void *stream);
 
 /* ------------------------------------------------------------------ measurement hooks
  * Device time (CUDA events on the launching stream) of the di_search / di_search_dev calls made since the
