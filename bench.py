@@ -216,7 +216,7 @@ def run_b200(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         _native.check(L.di_invert_dev(terms.data_ptr(), imps.data_ptr(), offs.data_ptr(), doc_hi - doc_lo, V, P,
-                                      toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), stream))
+                                      toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), None, stream))
         ev1.record()
         torch.cuda.synchronize()
         invert_runs.append(ev0.elapsed_time(ev1))
@@ -236,17 +236,22 @@ def run_b200(args):
         del o_toff, o_docs, o_vals
         if not same:
             raise SystemExit("PARITY FAILURE: GPU inversion differs from the oracle at full size")
-    del terms, imps, offs
     docids += doc_lo                                  # docids stay global across shards
     torch.cuda.synchronize()
     t1 = time.time()
-    index = engine.DeviceIndex.from_csr_device(toff, docids, vals, V, P, doc_lo=doc_lo, doc_hi=max(doc_hi, doc_lo + 1),
-                                               tile_docs=args.tile_docs, dense_ratio=args.dense_ratio,
-                                               cand_slack=args.cand_slack)
+    if args.index_from == "docmajor":                 # one segmented two-pass sort, no term-major detour
+        index = engine.DeviceIndex.from_docmajor_device(terms, imps, offs, doc_hi - doc_lo, V, P, doc_lo=doc_lo,
+                                                        tile_docs=args.tile_docs, dense_ratio=args.dense_ratio,
+                                                        cand_slack=args.cand_slack)
+    else:                                             # from the inverted CSR (the reference's index format)
+        index = engine.DeviceIndex.from_csr_device(toff, docids, vals, V, P, doc_lo=doc_lo, doc_hi=max(doc_hi, doc_lo + 1),
+                                                   tile_docs=args.tile_docs, dense_ratio=args.dense_ratio,
+                                                   cand_slack=args.cand_slack)
     t_tile = time.time() - t1
+    del terms, imps, offs
     info = index.info()
     build_info = {"generate_s": round(t_gen, 2), "invert_ms": round(invert_ms, 1), "invert_ms_first_call": round(invert_runs[0], 1),
-                  "tile_layout_s": round(t_tile, 3), "invert_postings_per_s": round(P / (invert_ms * 1e-3)),
+                  "tile_layout_s": round(t_tile, 3), "index_from": args.index_from, "invert_postings_per_s": round(P / (invert_ms * 1e-3)),
                   "invert_gbs_at_17B": round(17 * P / (invert_ms * 1e-3) / 1e9, 1)}
     n_idx = torch.tensor([info["n_postings"]], dtype=torch.int64, device=dev)
     if world > 1:
@@ -433,7 +438,7 @@ def run_b200(args):
             docs_a = torch.empty(P_all, dtype=torch.int32, device=dev)
             vals_a = torch.empty(P_all, dtype=torch.uint8, device=dev)
             _native.check(L.di_invert_dev(t_all.data_ptr(), v_all.data_ptr(), o_all.data_ptr(), N, V, P_all,
-                                          toff_a.data_ptr(), docs_a.data_ptr(), vals_a.data_ptr(), stream))
+                                          toff_a.data_ptr(), docs_a.data_ptr(), vals_a.data_ptr(), None, stream))
             del t_all, v_all, o_all
             whole = engine.DeviceIndex.from_csr_device(toff_a, docs_a, vals_a, V, P_all, doc_lo=0, doc_hi=N)
             w_keys = torch.zeros((Q, k), dtype=torch.int64, device=dev)
@@ -600,6 +605,8 @@ def main():
     ap.add_argument("--draws", type=int, default=0, help="Zipf draws per document (0 = 208 with --unique-terms, else 120)")
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--top-k", type=int, default=0)
+    ap.add_argument("--index-from", default="docmajor", choices=["docmajor", "csr"],
+                    help="build the device index straight from the doc-major collection, or from the inverted CSR")
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--dense-ratio", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0, help="queries per search call (0 = all queries at once)")

@@ -66,7 +66,9 @@ SIGNATURES = {
     "di_find_max_f64_dev": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp]),
     "di_quantize_f64_dev": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_double, _vp, _vp]),
     "di_invert": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint32, _vp, _vp, _vp]),
-    "di_invert_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, _vp, _vp, _vp, _vp]),
+    "di_invert_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp]),
+    "di_index_create_docmajor_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
+                                                    ctypes.c_uint32, ctypes.POINTER(IndexParams), ctypes.POINTER(_vp)]),
     "di_serialize": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp]),
     "di_serialize_dev": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint64, _vp, _vp, _vp]),
     "di_index_create_csr": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,

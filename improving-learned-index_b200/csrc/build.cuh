@@ -53,8 +53,8 @@ __device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t *a, uint64_t 
 }
 
 __global__ void invert_keys_kernel(const uint32_t *__restrict__ term_ids, const uint8_t *__restrict__ impacts,
-                                   const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, uint64_t n_post,
-                                   uint32_t n_terms, uint64_t *__restrict__ keys, int *__restrict__ err)
+                                   const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, uint32_t n_terms,
+                                   uint64_t *__restrict__ keys, uint32_t *__restrict__ status)
 {
     // one warp per document (lists are ~100 postings): the docid comes for free and the accesses stay
     // coalesced, instead of a 23-step binary search over doc_offsets per posting
@@ -63,23 +63,27 @@ __global__ void invert_keys_kernel(const uint32_t *__restrict__ term_ids, const 
     for (uint64_t doc = warp; doc < n_docs; doc += n_warps) {
         const uint64_t lo = doc_offsets[doc], hi = doc_offsets[doc + 1];
         for (uint64_t i = lo + lane_id(); i < hi; i += 32) {
-            const uint32_t t = term_ids[i];
-            if (t >= n_terms) *err = 1;
+            uint32_t t = term_ids[i];
+            if (t >= n_terms) {  // not a term of the vocabulary: sorts behind every list and is left out; the caller is told
+                t = n_terms;
+                if (status) *status = 1u;
+            }
             keys[i] = ((uint64_t)t << kInvTermShift) | ((uint64_t)(255u - impacts[i]) << 32) | (uint64_t)(uint32_t)doc;
         }
     }
-    (void)n_post;
 }
 
-__global__ void invert_extract_kernel(const uint64_t *__restrict__ keys, uint64_t n_post, uint32_t n_terms,
+__global__ void invert_extract_kernel(const uint64_t *__restrict__ ka, const uint64_t *__restrict__ kb,
+                                      const uint32_t *__restrict__ cur, uint64_t n_post, uint32_t n_terms,
                                       uint64_t *__restrict__ term_offsets, uint32_t *__restrict__ docids,
                                       uint8_t *__restrict__ impacts)
 {
+    const uint64_t *__restrict__ keys = rs_result(ka, kb, cur);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[i];
         docids[i] = (uint32_t)k;
         impacts[i] = (uint8_t)(255u - ((uint32_t)(k >> 32) & 255u));
-        const int64_t t = (int64_t)(k >> kInvTermShift);
+        const int64_t t = (int64_t)(k >> kInvTermShift);  // <= n_terms (n_terms = postings of unknown terms, left out)
         const int64_t tprev = i ? (int64_t)(keys[i - 1] >> kInvTermShift) : -1;
         for (int64_t tt = tprev + 1; tt <= t; ++tt) term_offsets[tt] = i;  // also covers empty terms
         if (i == n_post - 1)
@@ -107,43 +111,40 @@ __global__ void serialize_idx_kernel(const uint64_t *__restrict__ term_offsets, 
     }
 }
 
+// Asynchronous on `st`: scratch comes from the stream-ordered pool (no driver allocation after the first call) and
+// nothing waits for the GPU. *d_status (optional) is set to 1 when a term id >= n_terms was met; those postings are
+// left out and term_offsets[n_terms] is the number of postings kept.
 inline int invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
                       uint64_t n_docs, uint32_t n_terms, uint64_t n_post, uint64_t *d_term_offsets,
-                      uint32_t *d_out_docids, uint8_t *d_out_impacts, cudaStream_t st)
+                      uint32_t *d_out_docids, uint8_t *d_out_impacts, uint32_t *d_status, cudaStream_t st)
 {
-    if (n_terms > kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24", n_terms);
+    if (n_terms >= kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24 - 1", n_terms);
     if (n_docs >= (1ull << 32)) return set_error(DI_ERR_ARG, "n_docs exceeds 2^32-1");
+    if (d_status) DI_CUDA(cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
     if (n_post == 0) {
         DI_CUDA(cudaMemsetAsync(d_term_offsets, 0, ((size_t)n_terms + 1) * sizeof(uint64_t), st));
         return DI_OK;
     }
-    DevBuf ka, kb, err;
-    RadixSortScratch ws;
+    StreamBuf ka(st), kb(st);
+    RadixSortScratch ws(st);
     DI_TRY(ka.alloc(n_post * sizeof(uint64_t)));
     DI_TRY(kb.alloc(n_post * sizeof(uint64_t)));
-    DI_TRY(err.alloc(sizeof(int)));
-    DI_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
-    invert_keys_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(d_term_ids, d_impacts, d_doc_offsets, n_docs, n_post,
-                                                              n_terms, ka.as<uint64_t>(), err.as<int>());
+    invert_keys_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(d_term_ids, d_impacts, d_doc_offsets, n_docs, n_terms,
+                                                              ka.as<uint64_t>(), d_status);
     DI_KERNEL_CHECK();
-    int h_err = 0;
-    DI_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DI_CUDA(cudaStreamSynchronize(st));
-    if (h_err) return set_error(DI_ERR_RANGE, "term id >= n_terms (%u) in the collection", n_terms);
     int term_bits = 1;
-    while ((1ull << term_bits) < n_terms) ++term_bits;
-    uint64_t *sorted = nullptr;
-    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, 32, kInvTermShift + term_bits, ws, st, &sorted));
-    invert_extract_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(sorted, n_post, n_terms, d_term_offsets, d_out_docids,
-                                                                 d_out_impacts);
+    while ((1ull << term_bits) < (uint64_t)n_terms + 1) ++term_bits;  // the value n_terms marks unknown terms
+    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, 32, kInvTermShift + term_bits, nullptr, 1, ws, st));
+    invert_extract_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(ka.as<uint64_t>(), kb.as<uint64_t>(), ws.cur(), n_post,
+                                                                 n_terms, d_term_offsets, d_out_docids, d_out_impacts);
     DI_KERNEL_CHECK();
-    DI_CUDA(cudaStreamSynchronize(st));  // scratch is freed on return
     return DI_OK;
 }
 
 // ============================================================================ tiled shard layout
-// tile key = [tile:16 | term:24 | parity:1 | local docid >> 1 : 15 | impact:8]; hidden postings get
-// ~0 and sort last. Sorting puts a segment's even documents first, then its odd documents, each
+// tile key = [tile:16 | term:24 | parity:1 | local docid >> 1 : 15 | impact:8]; hidden postings carry a term
+// field >= n_terms (~0 from term-major input: they sort behind everything; n_terms from doc-major input: they sort
+// behind the visible postings of their tile) and are skipped by every consumer. Sorting puts a segment's even documents first, then its odd documents, each
 // by ascending docid: the scorer adds a u8 impact into a u16 accumulator that shares a 32-bit
 // shared-memory word with its neighbour, and knowing the parity per 16-byte unit makes the
 // addend a single instruction (DESIGN.md "sparse segments").
@@ -345,6 +346,50 @@ __global__ void tile_keys_kernel(const uint64_t *__restrict__ term_offsets, uint
     }
 }
 
+// Doc-major input (a collection as the indexer wrote it, create.py:33-35 order): one warp per document. The input is
+// already ordered by tile and, inside a tile, by document — a stable sort of every tile on (term, parity) is all
+// that is left to do. Postings with impact 0 are hidden (create.py writes them, inverted_index.py:50-51 never reads
+// past the first one of an impact-sorted list, so none is ever visible); so are term ids outside the vocabulary.
+__global__ void tile_keys_docmajor_kernel(const uint32_t *__restrict__ term_ids, const uint8_t *__restrict__ impacts,
+                                          const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, uint32_t n_terms,
+                                          int tile_shift, uint64_t *__restrict__ keys, TileStats *__restrict__ stats)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long vis = 0;
+    for (uint64_t doc = warp; doc < n_docs; doc += n_warps) {
+        const uint64_t lo = doc_offsets[doc], hi = doc_offsets[doc + 1];
+        const uint64_t tile = doc >> tile_shift;
+        const uint32_t field = local_to_field((uint32_t)doc & ((1u << tile_shift) - 1u));
+        for (uint64_t i = lo + lane_id(); i < hi; i += 32) {
+            uint32_t t = term_ids[i];
+            const uint32_t v = impacts[i];
+            if (t >= n_terms) { t = n_terms; stats->bad_docid = 2; }   // reported as an out-of-vocabulary term id
+            else if (v == 0) t = n_terms;
+            else ++vis;
+            keys[i] = (tile << kTkTileShift) | ((uint64_t)t << kTkTermShift) | ((uint64_t)field << kTkLocalShift) | v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(0xffffffffu, vis, o);
+    if (lane_id() == 0 && vis) atomicAdd(&stats->n_visible, vis);
+}
+
+// key index at which every tile starts (n_tiles + 1 entries)
+__global__ void tile_first_keys_kernel(const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, int tile_shift,
+                                       uint32_t n_tiles, uint64_t *__restrict__ first_key)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= n_tiles; t += gridDim.x * blockDim.x)
+        first_key[t] = doc_offsets[min((uint64_t)t << tile_shift, n_docs)];
+}
+
+__global__ void seed_slots_from_df_kernel(const unsigned long long *__restrict__ df, uint32_t n_terms,
+                                          uint32_t *__restrict__ slot_of_term, uint32_t *__restrict__ counter)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_terms; t += gridDim.x * blockDim.x)
+        slot_of_term[t] = df[t] >= kSeedMinDf ? atomicAdd(counter, 1u) : kNoSeedSlot;
+}
+
 __device__ __forceinline__ uint64_t seg_index(uint64_t key, uint32_t n_terms)
 {
     const uint64_t tile = key >> kTkTileShift;
@@ -355,19 +400,22 @@ __device__ __forceinline__ uint64_t seg_index(uint64_t key, uint32_t n_terms)
 // `seg_dup[s]` is set when a segment holds the same document twice (possible in hand-made CSR or
 // a model that lists a term twice): such a segment cannot be stored densely (one byte per doc).
 // `seg_odd[s]` (pre-set to 0xFFFFFFFF) receives the index of the segment's first odd document.
-__global__ void seg_bounds_kernel(const uint64_t *__restrict__ keys, uint64_t n_vis, uint32_t n_terms,
+__global__ void seg_bounds_kernel(const uint64_t *__restrict__ ka, const uint64_t *__restrict__ kb,
+                                  const uint32_t *__restrict__ cur, uint64_t n_keys, uint32_t n_terms,
                                   uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ seg_end,
                                   uint32_t *__restrict__ seg_odd, uint32_t *__restrict__ seg_dup)
 {
     constexpr int kParityBit = kTkLocalShift + 15;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t *__restrict__ keys = rs_result(ka, kb, cur);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_keys; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (((keys[i] >> kTkTermShift) & 0xFFFFFFu) >= n_terms) continue;  // hidden
         const uint64_t id = keys[i] >> kTkTermShift;
         const bool starts = i == 0 || (keys[i - 1] >> kTkTermShift) != id;
         if (i && (keys[i - 1] >> kTkLocalShift) == (keys[i] >> kTkLocalShift)) seg_dup[seg_index(keys[i], n_terms)] = 1u;
         if (((keys[i] >> kParityBit) & 1u) && (starts || !((keys[i - 1] >> kParityBit) & 1u)))
             seg_odd[seg_index(keys[i], n_terms)] = (uint32_t)i;
         if (starts) seg_begin[seg_index(keys[i], n_terms)] = (uint32_t)i;
-        if (i == n_vis - 1 || (keys[i + 1] >> kTkTermShift) != id) seg_end[seg_index(keys[i], n_terms)] = (uint32_t)(i + 1);
+        if (i == n_keys - 1 || (keys[i + 1] >> kTkTermShift) != id) seg_end[seg_index(keys[i], n_terms)] = (uint32_t)(i + 1);
     }
 }
 
@@ -423,12 +471,23 @@ __global__ void seg_desc_kernel(const uint32_t *__restrict__ off16, const uint32
 // dense segment: one impact byte per document of the tile, in the unit order dense_pass16 reads.
 // sparse posting word = impact << 16 | byte offset of the accumulator word ((local >> 1) * 4); the
 // parity of the document is implied by the unit the word sits in.
-__global__ void fill_payload_kernel(const uint64_t *__restrict__ keys, uint64_t n_vis, uint32_t n_terms,
+// seed_slot / seed_hist (both nullable): while every posting passes through, the impact histograms of the frequent
+// terms are counted too (doc-major build; the term-major build counts them from its impact-sorted lists instead)
+__global__ void fill_payload_kernel(const uint64_t *__restrict__ ka, const uint64_t *__restrict__ kb,
+                                    const uint32_t *__restrict__ cur, uint64_t n_keys, uint32_t n_terms,
                                     const SegDesc *__restrict__ desc, const uint32_t *__restrict__ seg_begin,
-                                    const uint32_t *__restrict__ seg_odd, uint32_t tile_docs, uint8_t *__restrict__ payload)
+                                    const uint32_t *__restrict__ seg_odd, uint32_t tile_docs, uint8_t *__restrict__ payload,
+                                    const uint32_t *__restrict__ seed_slot, uint32_t *__restrict__ seed_hist)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t *__restrict__ keys = rs_result(ka, kb, cur);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_keys; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i];
+        const uint32_t term = (uint32_t)(key >> kTkTermShift) & 0xFFFFFFu;
+        if (term >= n_terms) continue;  // hidden
+        if (seed_slot) {
+            const uint32_t slot = seed_slot[term];
+            if (slot != kNoSeedSlot) atomicAdd(&seed_hist[(size_t)slot * 256 + ((uint32_t)key & 0xFFu)], 1u);
+        }
         const uint64_t s = seg_index(key, n_terms);
         const SegDesc d = desc[s];
         const uint32_t field = (uint32_t)(key >> kTkLocalShift) & 0xFFFFu;

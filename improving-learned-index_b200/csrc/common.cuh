@@ -128,6 +128,32 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const uint4 *ptr)
     return r;
 }
 
+// Dense segments of the hottest terms are read by most work items of a tile, and the six CTAs of an SM work on the
+// same few tiles: letting these loads allocate in what is left of L1 beside the accumulators pays (measured,
+// profiles/README.md). DI_DENSE_NO_L1 / DI_SPARSE_L1 are the A/B switches.
+__device__ __forceinline__ uint4 ldg_cached_v4(const uint4 *ptr)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_dense_v4(const uint4 *ptr)
+{
+#ifdef DI_DENSE_NO_L1
+    return ldg_stream_v4(ptr);
+#else
+    return ldg_cached_v4(ptr);
+#endif
+}
+__device__ __forceinline__ uint4 ldg_sparse_v4(const uint4 *ptr)
+{
+#ifdef DI_SPARSE_L1
+    return ldg_cached_v4(ptr);
+#else
+    return ldg_stream_v4(ptr);
+#endif
+}
+
 __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *ptr)
 {
     uint64_t r;

@@ -145,10 +145,10 @@ extern "C" int di_quantize_f64(const double *scores, int64_t n, double max_val, 
 // ============================================================================ K2
 extern "C" int di_invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
                              uint64_t n_docs, uint32_t n_terms, uint64_t n_postings, uint64_t *d_term_offsets,
-                             uint32_t *d_out_docids, uint8_t *d_out_impacts, void *stream)
+                             uint32_t *d_out_docids, uint8_t *d_out_impacts, uint32_t *d_status, void *stream)
 {
     return invert_dev(d_term_ids, d_impacts, d_doc_offsets, n_docs, n_terms, n_postings, d_term_offsets, d_out_docids,
-                      d_out_impacts, (cudaStream_t)stream);
+                      d_out_impacts, d_status, (cudaStream_t)stream);
 }
 
 extern "C" int di_invert(const uint32_t *term_ids, const uint8_t *impacts, const uint64_t *doc_offsets, uint64_t n_docs,
@@ -157,7 +157,8 @@ extern "C" int di_invert(const uint32_t *term_ids, const uint8_t *impacts, const
     if (!doc_offsets || !term_offsets) return set_error(DI_ERR_ARG, "NULL argument");
     DI_TRY(ensure_device());
     const uint64_t P = doc_offsets[n_docs];
-    DevBuf d_t, d_v, d_o, d_to, d_od, d_ov;
+    DevBuf d_t, d_v, d_o, d_to, d_od, d_ov, d_status;
+    DI_TRY(d_status.alloc(sizeof(uint32_t)));
     DI_TRY(d_t.alloc(P * sizeof(uint32_t)));
     DI_TRY(d_v.alloc(P));
     DI_TRY(d_o.alloc((n_docs + 1) * sizeof(uint64_t)));
@@ -170,7 +171,10 @@ extern "C" int di_invert(const uint32_t *term_ids, const uint8_t *impacts, const
     }
     DI_CUDA(cudaMemcpy(d_o.p, doc_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     DI_TRY(invert_dev(d_t.as<uint32_t>(), d_v.as<uint8_t>(), d_o.as<uint64_t>(), n_docs, n_terms, P, d_to.as<uint64_t>(),
-                      d_od.as<uint32_t>(), d_ov.as<uint8_t>(), nullptr));
+                      d_od.as<uint32_t>(), d_ov.as<uint8_t>(), d_status.as<uint32_t>(), nullptr));
+    uint32_t status = 0;
+    DI_CUDA(cudaMemcpy(&status, d_status.p, sizeof status, cudaMemcpyDeviceToHost));
+    if (status) return set_error(DI_ERR_RANGE, "term id >= n_terms (%u) in the collection", n_terms);
     DI_CUDA(cudaMemcpy(term_offsets, d_to.p, ((size_t)n_terms + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (P) {
         DI_CUDA(cudaMemcpy(out_docids, d_od.p, P * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -219,19 +223,97 @@ extern "C" int di_serialize(const uint64_t *term_offsets, const uint32_t *docids
 }
 
 // ============================================================================ index create
+// Second half of both tiled builds: keys sorted by (tile, term, parity, local) inside rs_result(ka, kb, cur)[0 .. n_keys)
+// (hidden keys anywhere, recognised by their term field) -> segment table + payload. count_seeds: also count the
+// impact histograms of the frequent terms from the keys (the term-major build has them already).
+static int finish_tiled(di_index *ix, const uint64_t *ka, const uint64_t *kb, const uint32_t *cur, uint64_t n_keys,
+                        TileStats *d_stats, bool count_seeds, cudaStream_t st)
+{
+    const uint32_t V = ix->n_terms;
+    const uint64_t n_segs = (uint64_t)ix->n_tiles * V;
+    if (n_segs * sizeof(SegDesc) > (48ull << 30))
+        return set_error(DI_ERR_NOMEM, "segment table of %llu entries is too large; use larger tiles",
+                         (unsigned long long)n_segs);
+    TileStats stats{};
+    DevBuf d_begin, d_end, d_odd, d_size, d_nflag, d_scan, d_cnt;
+    DI_TRY(d_begin.alloc(n_segs * 4));
+    DI_TRY(d_end.alloc(n_segs * 4));
+    DI_TRY(d_odd.alloc(n_segs * 4));
+    DI_CUDA(cudaMemsetAsync(d_odd.p, 0xFF, n_segs * 4, st));
+    DI_TRY(d_size.alloc((n_segs + 1) * 4));
+    DI_TRY(d_nflag.alloc(n_segs * 4));
+    DI_TRY(d_scan.alloc(scan_scratch_words(n_segs + 1) * 4));
+    DI_CUDA(cudaMalloc(&ix->d_df, (size_t)V * sizeof(unsigned long long)));
+    DI_CUDA(cudaMemsetAsync(ix->d_df, 0, (size_t)V * sizeof(unsigned long long), st));
+    DI_CUDA(cudaMemsetAsync(d_begin.p, 0, n_segs * 4, st));
+    DI_CUDA(cudaMemsetAsync(d_end.p, 0, n_segs * 4, st));
+    DI_CUDA(cudaMemsetAsync(d_size.p, 0, (n_segs + 1) * 4, st));
+    seg_bounds_kernel<<<grid_for(n_keys, 256), 256, 0, st>>>(ka, kb, cur, n_keys, V, d_begin.as<uint32_t>(),
+                                                           d_end.as<uint32_t>(), d_odd.as<uint32_t>(), d_size.as<uint32_t>());
+    DI_KERNEL_CHECK();
+    seg_size_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_begin.as<uint32_t>(), d_end.as<uint32_t>(),
+                                                          d_odd.as<uint32_t>(), n_segs, V,
+                                                          ix->tile_docs, ix->dense_ratio, d_size.as<uint32_t>(),
+                                                          d_nflag.as<uint32_t>(), ix->d_df, d_stats);
+    DI_KERNEL_CHECK();
+    // exclusive scan over n_segs + 1 entries: the last output is the total payload size
+    DI_TRY(exclusive_scan_u32(d_size.as<uint32_t>(), d_size.as<uint32_t>(), n_segs + 1, d_scan.as<uint32_t>(), st));
+    uint32_t total16 = 0;
+    DI_CUDA(cudaMemcpyAsync(&total16, d_size.as<uint32_t>() + n_segs, 4, cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaMemcpyAsync(&stats, d_stats, sizeof stats, cudaMemcpyDeviceToHost, st));
+    const uint64_t max_slots = std::min<uint64_t>(V, n_keys / kSeedMinDf);
+    const bool seeds = count_seeds && max_slots && !(ix->flags & DI_INDEX_NO_SEEDS);
+    if (seeds) {  // which terms are frequent is known now (df): slots, then the histograms ride along with the payload fill
+        DI_TRY(d_cnt.alloc(4));
+        DI_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4, st));
+        DI_CUDA(cudaMalloc(&ix->d_seed_slot, (size_t)V * 4));
+        DI_CUDA(cudaMalloc(&ix->d_seed_cum, max_slots * 256 * 4));
+        DI_CUDA(cudaMemsetAsync(ix->d_seed_cum, 0, max_slots * 256 * 4, st));
+        seed_slots_from_df_kernel<<<grid_for(V, 256), 256, 0, st>>>(ix->d_df, V, ix->d_seed_slot, d_cnt.as<uint32_t>());
+        DI_KERNEL_CHECK();
+    }
+    DI_CUDA(cudaStreamSynchronize(st));
+    ix->has_dup_postings = stats.n_dup_segments != 0;
+    ix->n_dense_segments = stats.n_dense_segments;
+    ix->n_sparse_segments = stats.n_sparse_segments;
+    ix->n_dense_postings = stats.n_dense_postings;
+    ix->payload_bytes = (uint64_t)total16 * 16;
+    ix->table_bytes = n_segs * sizeof(SegDesc);
+    DI_CUDA(cudaMalloc(&ix->d_desc, ix->table_bytes));
+    DI_CUDA(cudaMalloc(&ix->d_payload, ix->payload_bytes ? ix->payload_bytes : 16));
+    DI_CUDA(cudaMemsetAsync(ix->d_payload, 0, ix->payload_bytes ? ix->payload_bytes : 16, st));
+    seg_desc_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_size.as<uint32_t>(), d_nflag.as<uint32_t>(), n_segs, ix->d_desc);
+    DI_KERNEL_CHECK();
+    fill_payload_kernel<<<grid_for(n_keys, 256), 256, 0, st>>>(ka, kb, cur, n_keys, V, ix->d_desc, d_begin.as<uint32_t>(),
+                                                               d_odd.as<uint32_t>(), ix->tile_docs, ix->d_payload,
+                                                               seeds ? ix->d_seed_slot : nullptr, seeds ? ix->d_seed_cum : nullptr);
+    DI_KERNEL_CHECK();
+    if (seeds) {
+        seed_cum_kernel<<<(unsigned)((max_slots * 32 + 255) / 256), 256, 0, st>>>(ix->d_seed_cum, (uint32_t)max_slots);
+        DI_KERNEL_CHECK();
+    }
+    DI_CUDA(cudaStreamSynchronize(st));
+    if (ix->has_dup_postings && ix->d_seed_cum) {  // a posting list that names a document twice: k postings != k documents
+        cudaFree(ix->d_seed_cum);
+        cudaFree(ix->d_seed_slot);
+        ix->d_seed_cum = ix->d_seed_slot = nullptr;
+    }
+    return DI_OK;
+}
+
+// From term-major CSR (the reference's index format): postings are re-keyed and sorted by (tile, term, parity, local).
 static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
                        uint64_t n_post, cudaStream_t st)
 {
     const uint32_t V = ix->n_terms;
-    if (V > kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24", V);
-    if (n_post >= (1ull << 32)) return set_error(DI_ERR_ARG, "more than 2^32-1 postings in one shard");
+    if (V >= kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24 - 1", V);
+    if (n_post >= (1ull << 32) - 1) return set_error(DI_ERR_ARG, "more than 2^32-2 postings in one shard");
 
     DevBuf d_stats, d_fz, ka, kb;
-    RadixSortScratch ws;
+    RadixSortScratch ws(st);
     DI_TRY(d_stats.alloc(sizeof(TileStats)));
     DI_CUDA(cudaMemsetAsync(d_stats.p, 0, sizeof(TileStats), st));
     TileStats stats{};
-    uint64_t *sorted = nullptr;
     if (n_post) {
         DI_TRY(d_fz.alloc((size_t)V * sizeof(unsigned long long)));
         DI_TRY(ka.alloc(n_post * sizeof(uint64_t)));
@@ -272,66 +354,59 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
         }
         d_fz.release();
         // hidden postings carry ~0 and sort to the end; the (tile, term, local) order is total
-        DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, kTkLocalShift, 64, ws, st, &sorted));
+        DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, kTkLocalShift, 64, nullptr, 1, ws, st));
     }
     const uint64_t n_vis = stats.n_visible;
     ix->n_postings = n_vis;
     ix->max_docid_plus1 = stats.max_docid_plus1;
     ix->n_tiles = n_vis ? ((stats.max_docid_plus1 - ix->doc_lo) + ix->tile_docs - 1) / ix->tile_docs : 0;
     if (ix->n_tiles == 0) return DI_OK;
+    return finish_tiled(ix, ka.as<uint64_t>(), kb.as<uint64_t>(), ws.cur(), n_vis, d_stats.as<TileStats>(), false, st);
+}
 
-    const uint64_t n_segs = (uint64_t)ix->n_tiles * V;
-    if (n_segs * sizeof(SegDesc) > (48ull << 30))
-        return set_error(DI_ERR_NOMEM, "segment table of %llu entries is too large; use larger tiles",
-                         (unsigned long long)n_segs);
-    DevBuf d_begin, d_end, d_odd, d_size, d_nflag, d_scan;
-    DI_TRY(d_begin.alloc(n_segs * 4));
-    DI_TRY(d_end.alloc(n_segs * 4));
-    DI_TRY(d_odd.alloc(n_segs * 4));
-    DI_CUDA(cudaMemsetAsync(d_odd.p, 0xFF, n_segs * 4, st));
-    DI_TRY(d_size.alloc((n_segs + 1) * 4));
-    DI_TRY(d_nflag.alloc(n_segs * 4));
-    DI_TRY(d_scan.alloc(scan_scratch_words(n_segs + 1) * 4));
-    DI_CUDA(cudaMalloc(&ix->d_df, (size_t)V * sizeof(unsigned long long)));
-    DI_CUDA(cudaMemsetAsync(ix->d_df, 0, (size_t)V * sizeof(unsigned long long), st));
-    DI_CUDA(cudaMemsetAsync(d_begin.p, 0, n_segs * 4, st));
-    DI_CUDA(cudaMemsetAsync(d_end.p, 0, n_segs * 4, st));
-    DI_CUDA(cudaMemsetAsync(d_size.p, 0, (n_segs + 1) * 4, st));
-    seg_bounds_kernel<<<grid_for(n_vis, 256), 256, 0, st>>>(sorted, n_vis, V, d_begin.as<uint32_t>(), d_end.as<uint32_t>(),
-                                                          d_odd.as<uint32_t>(), d_size.as<uint32_t>());
+// From a doc-major collection (what the indexer produces, create.py:31-35): the input is already grouped by tile and
+// ordered by document inside a tile, so ONE segmented stable sort of every tile on (term, parity) — two 8-bit
+// passes for a BERT-sized vocabulary, working set of a tile ~ L2 — replaces the inversion (3 passes) plus the
+// re-tiling sort (6 passes) of the term-major route. The resulting index is identical.
+static int build_tiled_docmajor(di_index *ix, const uint32_t *d_term_ids, const uint8_t *d_impacts,
+                                const uint64_t *d_doc_offsets, uint64_t n_docs, uint64_t n_post, cudaStream_t st)
+{
+    const uint32_t V = ix->n_terms;
+    if (V >= kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24 - 1", V);
+    if (n_post >= (1ull << 32) - 1) return set_error(DI_ERR_ARG, "more than 2^32-2 postings in one shard");
+    const uint64_t n_tiles = (n_docs + ix->tile_docs - 1) / ix->tile_docs;
+    if (n_tiles >= 0xFFFFu)
+        return set_error(DI_ERR_RANGE, "shard spans more than 65535 tiles of %u docs; raise tile_docs or shard further", ix->tile_docs);
+    DevBuf d_stats, ka, kb, d_first;
+    RadixSortScratch ws(st);
+    DI_TRY(d_stats.alloc(sizeof(TileStats)));
+    DI_CUDA(cudaMemsetAsync(d_stats.p, 0, sizeof(TileStats), st));
+    ix->n_tiles = 0;
+    if (n_post == 0 || n_docs == 0) return DI_OK;
+    DI_TRY(ka.alloc(n_post * sizeof(uint64_t)));
+    DI_TRY(kb.alloc(n_post * sizeof(uint64_t)));
+    DI_TRY(d_first.alloc((n_tiles + 1) * sizeof(uint64_t)));
+    tile_keys_docmajor_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(d_term_ids, d_impacts, d_doc_offsets, n_docs, V,
+                                                                     (int)ix->tile_shift, ka.as<uint64_t>(),
+                                                                     d_stats.as<TileStats>());
     DI_KERNEL_CHECK();
-    seg_size_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_begin.as<uint32_t>(), d_end.as<uint32_t>(),
-                                                          d_odd.as<uint32_t>(), n_segs, V,
-                                                          ix->tile_docs, ix->dense_ratio, d_size.as<uint32_t>(),
-                                                          d_nflag.as<uint32_t>(), ix->d_df, d_stats.as<TileStats>());
+    tile_first_keys_kernel<<<grid_for(n_tiles + 1, 256), 256, 0, st>>>(d_doc_offsets, n_docs, (int)ix->tile_shift,
+                                                                       (uint32_t)n_tiles, d_first.as<uint64_t>());
     DI_KERNEL_CHECK();
-    // exclusive scan over n_segs + 1 entries: the last output is the total payload size
-    DI_TRY(exclusive_scan_u32(d_size.as<uint32_t>(), d_size.as<uint32_t>(), n_segs + 1, d_scan.as<uint32_t>(), st));
-    uint32_t total16 = 0;
-    DI_CUDA(cudaMemcpyAsync(&total16, d_size.as<uint32_t>() + n_segs, 4, cudaMemcpyDeviceToHost, st));
+    int term_bits = 1;
+    while ((1ull << term_bits) < (uint64_t)V + 1) ++term_bits;  // the value V marks hidden postings
+    // bit 23 = parity of the document, bits 24.. = term: inside a tile the input is in document order already
+    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, kTkTermShift - 1, kTkTermShift + term_bits,
+                          d_first.as<uint64_t>(), (uint32_t)n_tiles, ws, st));
+    TileStats stats{};
     DI_CUDA(cudaMemcpyAsync(&stats, d_stats.p, sizeof stats, cudaMemcpyDeviceToHost, st));
     DI_CUDA(cudaStreamSynchronize(st));
-    ix->has_dup_postings = stats.n_dup_segments != 0;
-    if (stats.n_dup_segments && ix->d_seed_cum) {  // a posting list that names a document twice: k postings != k documents
-        cudaFree(ix->d_seed_cum);
-        cudaFree(ix->d_seed_slot);
-        ix->d_seed_cum = ix->d_seed_slot = nullptr;
-    }
-    ix->n_dense_segments = stats.n_dense_segments;
-    ix->n_sparse_segments = stats.n_sparse_segments;
-    ix->n_dense_postings = stats.n_dense_postings;
-    ix->payload_bytes = (uint64_t)total16 * 16;
-    ix->table_bytes = n_segs * sizeof(SegDesc);
-    DI_CUDA(cudaMalloc(&ix->d_desc, ix->table_bytes));
-    DI_CUDA(cudaMalloc(&ix->d_payload, ix->payload_bytes ? ix->payload_bytes : 16));
-    DI_CUDA(cudaMemsetAsync(ix->d_payload, 0, ix->payload_bytes ? ix->payload_bytes : 16, st));
-    seg_desc_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_size.as<uint32_t>(), d_nflag.as<uint32_t>(), n_segs, ix->d_desc);
-    DI_KERNEL_CHECK();
-    fill_payload_kernel<<<grid_for(n_vis, 256), 256, 0, st>>>(sorted, n_vis, V, ix->d_desc, d_begin.as<uint32_t>(),
-                                                              d_odd.as<uint32_t>(), ix->tile_docs, ix->d_payload);
-    DI_KERNEL_CHECK();
-    DI_CUDA(cudaStreamSynchronize(st));
-    return DI_OK;
+    if (stats.bad_docid) return set_error(DI_ERR_RANGE, "term id >= n_terms (%u) in the collection", V);
+    ix->n_postings = stats.n_visible;
+    ix->max_docid_plus1 = ix->doc_lo + (uint32_t)n_docs;
+    if (stats.n_visible == 0) return DI_OK;
+    ix->n_tiles = (uint32_t)n_tiles;
+    return finish_tiled(ix, ka.as<uint64_t>(), kb.as<uint64_t>(), ws.cur(), n_post, d_stats.as<TileStats>(), true, st);
 }
 
 static int new_index(uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const di_index_params *params, di_index **out)
@@ -373,6 +448,23 @@ extern "C" int di_index_create_csr_dev(const uint64_t *d_term_offsets, const uin
     di_index *ix = nullptr;
     DI_TRY(new_index(n_terms, doc_lo, doc_hi, params, &ix));
     int rc = build_tiled(ix, d_term_offsets, d_docids, d_impacts, n_postings, ix->stream);
+    if (rc != DI_OK) {
+        delete ix;
+        *out = nullptr;
+        return rc;
+    }
+    *out = ix;
+    return DI_OK;
+}
+
+extern "C" int di_index_create_docmajor_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
+                                            uint64_t n_docs, uint32_t n_terms, uint64_t n_postings, uint32_t doc_lo,
+                                            const di_index_params *params, di_index_t **out)
+{
+    if (n_docs == 0 || (uint64_t)doc_lo + n_docs > 0xFFFFFFFFull) return set_error(DI_ERR_ARG, "bad document range");
+    di_index *ix = nullptr;
+    DI_TRY(new_index(n_terms, doc_lo, doc_lo + (uint32_t)n_docs, params, &ix));
+    int rc = build_tiled_docmajor(ix, d_term_ids, d_impacts, d_doc_offsets, n_docs, n_postings, ix->stream);
     if (rc != DI_OK) {
         delete ix;
         *out = nullptr;

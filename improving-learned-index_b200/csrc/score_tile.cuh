@@ -35,14 +35,18 @@ namespace di {
 constexpr int kScoreThreads = DI_SCORE_THREADS;
 constexpr int kMaxSeg = 32;        // query terms handled per round inside a work item
 #ifndef DI_SPARSE_UNROLL
-#define DI_SPARSE_UNROLL 4
+#define DI_SPARSE_UNROLL 2
 #endif
 constexpr int kSparseUnroll = DI_SPARSE_UNROLL;  // independent 128-bit posting loads in flight per thread
-constexpr int kHistBins = 1024;    // score histogram of the tile-local pre-selection
+#ifndef DI_HIST_BINS
+#define DI_HIST_BINS 1024
+#endif
+constexpr int kHistBins = DI_HIST_BINS;  // score histogram of the tile-local pre-selection = slots of the hit-group list (multiple of 256)
 #ifndef DI_TILES_PER_ITEM
 #define DI_TILES_PER_ITEM 2
 #endif
-constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers (1 or 2)
+constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers (1 .. 4)
+static_assert(kTilesPerItem >= 1 && kTilesPerItem <= 4, "the item's segment lists must fit beside six 32 KB accumulators");
 
 constexpr int kRecInlineTerms = 12;
 struct __align__(64) QueryRec {   // one cache-line-friendly record per query of the batch
@@ -190,7 +194,7 @@ __device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *co
             const uint32_t g = g0 + s * kScoreThreads;
 #pragma unroll
             for (int u = 0; u < NB; ++u)
-                v[s][u] = (FULL || g < units) ? ldg_stream_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
+                v[s][u] = (FULL || g < units) ? ldg_dense_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int s = 0; s < U; ++s) {
@@ -455,7 +459,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
     static_assert(kMaxSeg == 32, "the segment lookup is one warp wide");
     extern __shared__ uint4 s_acc4[];  // tile accumulators
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_acc4);
-    __shared__ SegLists s_seg[2];      // one per tile of the item
+    __shared__ SegLists s_seg[kTilesPerItem];  // one per tile of the item
     __shared__ uint32_t s_emit, s_ready, s_nhits;
     __shared__ __align__(16) uint32_t s_hist[kHistBins];  // score histogram / hit-group list / radix-select scratch
     __shared__ uint32_t s_scan[33];
@@ -476,18 +480,22 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
     if (tid == 0) s_ready = p.done == nullptr || step == 0 || ld_flag_u32(p.done + sq) >= step;
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
 
-    // ---- first-round segment lookup of BOTH tiles: warp 0, the two descriptor loads of a lane in flight together
+    // ---- first-round segment lookup of ALL the item's tiles: warp 0, a lane's descriptor loads in flight together
     if (tid < kMaxSeg) {
-        SegDesc d0{0u, 0u}, d1{0u, 0u};
+        SegDesc d[kTilesPerItem];
+#pragma unroll
+        for (int j = 0; j < kTilesPerItem; ++j) d[j] = SegDesc{0u, 0u};
         if (qb + tid < qe) {
             const uint32_t t = tid < kRecInlineTerms ? rec->terms[tid] : p.q_terms[qb + tid];
             if (t < p.n_terms) {  // DI_OOV_TERM and anything out of range: no postings
-                d0 = p.desc[(uint64_t)tile0 * p.n_terms + t];
-                if (n_sub > 1) d1 = p.desc[(uint64_t)(tile0 + 1) * p.n_terms + t];
+#pragma unroll
+                for (int j = 0; j < kTilesPerItem; ++j)
+                    if ((uint32_t)j < n_sub) d[j] = p.desc[(uint64_t)(tile0 + j) * p.n_terms + t];
             }
         }
-        fill_seg_lists(s_seg[0], d0, tid);
-        if (n_sub > 1) fill_seg_lists(s_seg[1], d1, tid);
+#pragma unroll
+        for (int j = 0; j < kTilesPerItem; ++j)
+            if ((uint32_t)j < n_sub) fill_seg_lists(s_seg[j], d[j], tid);
     }
 
     DI_PROF_DECL;
@@ -548,7 +556,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                             }
                             const uint32_t lu = u - seg_lo;
                             odd[j] = lu >= seg_even;
-                            v[j] = ldg_stream_v4(payload4 + seg_off + lu);
+                            v[j] = ldg_sparse_v4(payload4 + seg_off + lu);
                         }
                     }
 #pragma unroll
@@ -687,7 +695,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
             theta = theta_pre;
         }
         cnt0 = n;
-        __syncthreads();  // s_emit / s_hist / the accumulators are free again (second tile, or the next item)
+        if (sub + 1 < n_sub) __syncthreads();  // s_emit / s_hist / the accumulators are free again for the second tile
         DI_PROF_MARK(5);  // cut to k
 #ifdef DI_PROFILE_PHASES
         if (tid == 0 && p.prof) atomicAdd(p.prof + (size_t)tile * 8 + 7, 1ull);  // items that reached the fused pass
@@ -711,9 +719,8 @@ __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS
 
 // ---- launch form B: ONE persistent launch for all tiles of the batch ---------------------------
 // grid = resident CTAs; each CTA claims work items from a global counter in tile-major order
-// (item = step * n_queries + slot, step = a pair of adjacent tiles), so at any moment the whole GPU works on a few
-// tiles (their postings stay L2-resident) and there is no per-tile launch tail. The NEXT item is claimed while the
-// current one is processed (the atomic's round trip to L2 is off the critical path). After an item,
+// (item = step * n_queries + slot, step = kTilesPerItem adjacent tiles), so at any moment the whole GPU works on a few
+// tiles (their postings stay L2-resident) and there is no per-tile launch tail. After an item,
 // done[q] = step + 1 is published with release semantics; the next step of the same query acquires it. Waits only
 // ever point at items with a smaller index, and claims are handed out in index order, so the protocol cannot deadlock.
 template <bool ACC32>
@@ -727,13 +734,19 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
     const unsigned long long n_items = (unsigned long long)steps_per_lane * n_virtual;
     const bool narrow = n_items <= 0xFFFFFFFFull;  // 32-bit item arithmetic (a 64-bit divide is ~100 instructions)
     unsigned long long next = 0;
+#ifdef DI_CLAIM_AHEAD
     if (threadIdx.x == 0) next = atomicAdd(counter, 1ull);
+#endif
     if (!ACC32) zero_words16(s_acc4, p.tile_docs / 8);  // accumulator invariant: zero at every item start
     for (;;) {
         __syncthreads();  // everybody is done with the previous item's shared memory
         if (threadIdx.x == 0) {
+#ifdef DI_CLAIM_AHEAD   // measured slower (profiles/README.md): the value lives across the whole item and spills
             s_item = next;
             if (next < n_items) next = atomicAdd(counter, 1ull);
+#else
+            s_item = atomicAdd(counter, 1ull);
+#endif
         }
         __syncthreads();
         const unsigned long long item = s_item;

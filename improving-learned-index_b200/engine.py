@@ -109,6 +109,18 @@ class DeviceIndex:
         return cls(h.value)
 
     @classmethod
+    def from_docmajor_device(cls, d_term_ids, d_impacts, d_doc_offsets, n_docs: int, n_terms: int, n_postings: int,
+                             doc_lo: int = 0, tile_docs: int = 0, dense_ratio: int = 0, cand_slack: int = 0,
+                             flags: int = 0) -> "DeviceIndex":
+        """Straight from a doc-major collection in device memory (u32 term ids, u8 impacts, u64 doc offsets of
+        documents doc_lo .. doc_lo + n_docs): no term-major detour, one segmented two-pass sort. Identical index."""
+        h = ctypes.c_void_p()
+        p = cls._params(tile_docs, dense_ratio, cand_slack, flags)
+        N.check(N.lib().di_index_create_docmajor_dev(N.ptr(d_term_ids), N.ptr(d_impacts), N.ptr(d_doc_offsets), n_docs,
+                                                     n_terms, n_postings, doc_lo, ctypes.byref(p), ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
     def from_files(cls, dat, idx_pairs, doc_lo: int = 0, doc_hi: int = N.ALL_DOCS, tile_docs: int = 0,
                    dense_ratio: int = 0, cand_slack: int = 0, flags: int = 0) -> "DeviceIndex":
         """From the reference's file images: inverted_index.dat bytes and inverted_index.idx as u64 pairs."""

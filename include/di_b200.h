@@ -9,8 +9,9 @@
  *
  * Conventions
  *   - plain C types; every buffer is caller-owned; `*_dev` variants take DEVICE pointers and a
- *     cudaStream_t (passed as void*) and are asynchronous on that stream; the others take HOST
- *     pointers and return when the result is in the output buffers.
+ *     cudaStream_t (passed as void*) and are asynchronous on that stream (the di_index_create_* constructors
+ *     are the exception: they return a finished index); the others take HOST pointers and return when the
+ *     result is in the output buffers.
  *   - return value: 0 = DI_OK, otherwise an error code; di_last_error() gives the message of
  *     the last failure on the calling thread.
  *   - no global mutable state besides the handles; a handle must not be used from two threads
@@ -92,9 +93,13 @@ int di_collection_write_quantized(const di_collection_t *collection, const int32
 int di_invert(const uint32_t *term_ids, const uint8_t *impacts, const uint64_t *doc_offsets,
               uint64_t n_docs, uint32_t n_terms,
               uint64_t *term_offsets, uint32_t *out_docids, uint8_t *out_impacts);
+/* Device form: truly asynchronous on `stream` — scratch comes from the stream-ordered memory pool and nothing waits
+ * for the GPU. *d_status (device u32, may be NULL) becomes 1 when a term id >= n_terms was met (di_invert returns
+ * DI_ERR_RANGE for that); such postings are left out and d_term_offsets[n_terms] is the number kept. */
 int di_invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
                   uint64_t n_docs, uint32_t n_terms, uint64_t n_postings,
-                  uint64_t *d_term_offsets, uint32_t *d_out_docids, uint8_t *d_out_impacts, void *stream);
+                  uint64_t *d_term_offsets, uint32_t *d_out_docids, uint8_t *d_out_impacts, uint32_t *d_status,
+                  void *stream);
 int di_serialize(const uint64_t *term_offsets, const uint32_t *docids, const uint8_t *impacts,
                  uint32_t n_terms, uint8_t *dat, uint64_t *idx);
 int di_serialize_dev(const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
@@ -141,6 +146,13 @@ int di_index_create_csr(const uint64_t *term_offsets, const uint32_t *docids, co
 int di_index_create_csr_dev(const uint64_t *d_term_offsets, const uint32_t *d_docids, const uint8_t *d_impacts,
                             uint32_t n_terms, uint64_t n_postings, uint32_t doc_lo, uint32_t doc_hi,
                             const di_index_params *params, di_index_t **out);
+/* straight from a DOC-MAJOR collection in device memory (the input of di_invert_dev: what create.py:31-35 iterates over),
+ * for documents [doc_lo, doc_lo + n_docs): skips the term-major detour when no index files are wanted — one segmented
+ * two-pass sort instead of inversion + re-tiling; the index is identical to the one built from the inverted CSR.
+ * Postings with impact 0 are invisible (the reader never gets past them, inverted_index.py:50-51). */
+int di_index_create_docmajor_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, const uint64_t *d_doc_offsets,
+                                 uint64_t n_docs, uint32_t n_terms, uint64_t n_postings, uint32_t doc_lo,
+                                 const di_index_params *params, di_index_t **out);
 /* from the reference's file images: inverted_index.dat bytes + inverted_index.idx as (start,end) u64 pairs */
 int di_index_create_files(const uint8_t *dat, uint64_t dat_bytes, const uint64_t *idx_pairs,
                           uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi,

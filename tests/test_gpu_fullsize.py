@@ -35,7 +35,7 @@ def full():
     vals = torch.empty(P, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     _native.check(L.di_invert_dev(terms.data_ptr(), imps.data_ptr(), offs.data_ptr(), N_DOCS, VOCAB, P,
-                                  toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), st))
+                                  toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), None, st))
     torch.cuda.synchronize()
     # the oracle's own inversion of the same doc-major arrays (create.py:31-46 restated, ~20 s single-threaded): the
     # reference for configs[4] and the CSR every scoring comparison below runs the oracle on

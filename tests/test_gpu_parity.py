@@ -119,6 +119,61 @@ def test_invert_random_matches_oracle():
     assert toff.tolist() == [0] * 5 and docs.size == 0
 
 
+def test_invert_is_stable_over_many_sort_blocks_and_flags_bad_term_ids():
+    """K2's one-sweep sort: many 8192-key blocks per digit run (look-back chains), skewed digits (one hot term),
+    a digit pass that is uniform (tiny vocabulary -> skipped on the device), term ids outside the vocabulary."""
+    rng = np.random.default_rng(7)
+    for n_docs, V, per_doc in ((60_000, 3, 3), (30_000, 700, 40), (9_000, 70_000, 25)):
+        terms = np.concatenate([np.sort(rng.choice(V, size=min(per_doc, V), replace=False)) for _ in range(n_docs)]).astype(np.uint32)
+        if V == 700:
+            terms[rng.random(terms.size) < 0.5] = 5                      # half of all postings in one list (duplicates allowed)
+        offs = np.arange(n_docs + 1, dtype=np.uint64) * min(per_doc, V)
+        imps = rng.integers(0, 256, size=terms.size).astype(np.uint8)
+        toff, docs, vals = engine.invert(terms, imps, offs, V)
+        o_toff, o_docs, o_vals = oracle.invert(terms, imps, offs, V)
+        assert np.array_equal(toff, o_toff) and np.array_equal(docs, o_docs) and np.array_equal(vals, o_vals), V
+    with pytest.raises(RuntimeError):                                    # term id == n_terms: DI_ERR_RANGE
+        engine.invert([0, 3], [1, 1], [0, 2], 3)
+
+
+@pytest.mark.parametrize("n_docs,V,draws,tile_docs,dense_ratio", [(5000, 800, 100, 512, 0), (40_000, 2000, 60, 4096, 0),
+                                                                    (40_000, 2000, 60, 256, 0xFFFFFFFF), (70_000, 3000, 40, 0, 0),
+                                                                    (3000, 40, 30, 1024, 1)])
+def test_index_from_docmajor_equals_index_from_csr(n_docs, V, draws, tile_docs, dense_ratio):
+    """di_index_create_docmajor_dev (one segmented two-pass sort straight from the collection) must give the very
+    index the term-major route gives: same statistics, same results as the oracle; shards by document range too."""
+    torch = pytest.importorskip("torch")
+    x = quantized_csr(n_docs, V, draws, 17)
+    dev = torch.device("cuda:0")
+    imps = x["imps"].copy()
+    imps[::97] = 0                                                       # zero impacts are written by create.py and never read back
+    o_toff, o_docs, o_vals = oracle.invert(x["terms"], imps, x["offs"], V)
+    d_terms = torch.from_numpy(x["terms"].astype(np.int64)).to(dev).to(torch.int32)
+    d_imps = torch.from_numpy(imps).to(dev)
+    d_offs = torch.from_numpy(x["offs"].astype(np.int64)).to(dev)
+    ref = engine.DeviceIndex.from_csr(o_toff, o_docs, o_vals, tile_docs=tile_docs, dense_ratio=dense_ratio)
+    got = engine.DeviceIndex.from_docmajor_device(d_terms, d_imps, d_offs, n_docs, V, x["terms"].size,
+                                                  tile_docs=tile_docs, dense_ratio=dense_ratio)
+    a, b = ref.info(), got.info()
+    for key in ("n_postings", "payload_bytes", "table_bytes", "n_dense_segments", "n_sparse_segments", "n_dense_postings", "tile_docs"):
+        assert a[key] == b[key], key
+    queries = syn.make_queries(300, vocab_size=V, seed=18)
+    queries[0], queries[1] = [], [V + 1]
+    for k in (10, 1000):
+        want = oracle.score_topk_csr(o_toff, o_docs, o_vals, n_docs, queries, k)
+        assert_same_results(got.search(queries, k), want, f"docmajor k={k}")
+        assert_same_results(ref.search(queries, k), want, f"csr k={k}")
+    flat = np.asarray([t for q in queries for t in q if 0 <= t < V], dtype=np.uint32)
+    assert np.array_equal(got.term_df(flat), ref.term_df(flat))
+    # a shard = a slice of the documents with its own doc_lo; docids stay global
+    lo, hi = n_docs // 3, n_docs // 3 + n_docs // 2
+    p0, p1 = int(x["offs"][lo]), int(x["offs"][hi])
+    shard = engine.DeviceIndex.from_docmajor_device(d_terms[p0:p1], d_imps[p0:p1], (d_offs[lo:hi + 1] - p0).contiguous(),
+                                                    hi - lo, V, p1 - p0, doc_lo=lo, tile_docs=tile_docs, dense_ratio=dense_ratio)
+    twin = engine.DeviceIndex.from_csr(o_toff, o_docs, o_vals, doc_lo=lo, doc_hi=hi, tile_docs=tile_docs, dense_ratio=dense_ratio)
+    assert_same_results(shard.search(queries, 100), twin.search(queries, 100), "shard")
+
+
 # ------------------------------------------------------------------ reader semantics + scoring on golden indexes
 @pytest.mark.parametrize("name", ["kat", "zeros"])
 def test_index_golden_small(golden, tmp_path, name):

@@ -45,7 +45,7 @@ def main():
     docids = torch.empty(P, dtype=torch.int32, device=dev)
     vals = torch.empty(P, dtype=torch.uint8, device=dev)
     _native.check(L.di_invert_dev(terms.data_ptr(), imps.data_ptr(), offs.data_ptr(), hi - lo, V, P, toff.data_ptr(),
-                                  docids.data_ptr(), vals.data_ptr(), st))
+                                  docids.data_ptr(), vals.data_ptr(), None, st))
     docids += lo
     index = engine.DeviceIndex.from_csr_device(toff, docids, vals, V, P, doc_lo=lo, doc_hi=hi)
     queries = synthetic.make_queries(args.queries, vocab_size=V, seed=7)
