@@ -18,7 +18,7 @@ import os
 # DI_B200_LIB lets a tuning run point at an alternative build of the SAME sources (e.g. other block size)
 LIB_PATH = Path(os.environ.get("DI_B200_LIB", PKG_DIR / "libdi_b200.so"))
 SOURCES = [PKG_DIR / "csrc" / n for n in
-           ("di_b200.cu", "collection.cu", "common.cuh", "scan_sort.cuh", "build.cuh", "select.cuh", "score_tile.cuh", "search.cuh")] + [REPO_DIR / "include" / "di_b200.h"]
+           ("di_b200.cu", "collection.cu", "run_io.cu", "common.cuh", "scan_sort.cuh", "build.cuh", "select.cuh", "score_tile.cuh", "search.cuh")] + [REPO_DIR / "include" / "di_b200.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -92,6 +92,8 @@ SIGNATURES = {
     "di_shared_close": (ctypes.c_int, [_vp]),
     "di_shared_free": (ctypes.c_int, [_vp]),
     "di_peer_barrier_dev": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    "di_write_run_file": (ctypes.c_int, [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
+    "di_eval_ranks_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]),
     "di_get_timings": (ctypes.c_int, [_vp, ctypes.POINTER(Timings)]),
     "di_collection_parse": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_vp)]),
     "di_collection_free": (None, [_vp]),
@@ -117,7 +119,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     newest = max(p.stat().st_mtime for p in SOURCES)
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
         cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB_PATH), str(PKG_DIR / "csrc" / "di_b200.cu"),
-               str(PKG_DIR / "csrc" / "collection.cu")]
+               str(PKG_DIR / "csrc" / "collection.cu"), str(PKG_DIR / "csrc" / "run_io.cu")]
         if verbose:
             print(' '.join(cmd))
         subprocess.run(cmd, check=True)

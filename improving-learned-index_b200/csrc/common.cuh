@@ -128,9 +128,9 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const uint4 *ptr)
     return r;
 }
 
-// Dense segments of the hottest terms are read by most work items of a tile, and the six CTAs of an SM work on the
-// same few tiles: letting these loads allocate in what is left of L1 beside the accumulators pays (measured,
-// profiles/README.md). DI_DENSE_NO_L1 / DI_SPARSE_L1 are the A/B switches.
+// The segments of the hottest terms are read by most work items of a tile, and the six CTAs of an SM work on the
+// same few tiles: letting the posting loads allocate in what is left of L1 beside the accumulators pays (measured,
+// profiles/README.md). DI_DENSE_NO_L1 / DI_SPARSE_NO_L1 are the A/B switches.
 __device__ __forceinline__ uint4 ldg_cached_v4(const uint4 *ptr)
 {
     uint4 r;
@@ -147,10 +147,10 @@ __device__ __forceinline__ uint4 ldg_dense_v4(const uint4 *ptr)
 }
 __device__ __forceinline__ uint4 ldg_sparse_v4(const uint4 *ptr)
 {
-#ifdef DI_SPARSE_L1
-    return ldg_cached_v4(ptr);
-#else
+#ifdef DI_SPARSE_NO_L1
     return ldg_stream_v4(ptr);
+#else
+    return ldg_cached_v4(ptr);
 #endif
 }
 

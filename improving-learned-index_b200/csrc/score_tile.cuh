@@ -39,14 +39,15 @@ constexpr int kMaxSeg = 32;        // query terms handled per round inside a wor
 #endif
 constexpr int kSparseUnroll = DI_SPARSE_UNROLL;  // independent 128-bit posting loads in flight per thread
 #ifndef DI_HIST_BINS
-#define DI_HIST_BINS 1024
+#define DI_HIST_BINS 768
 #endif
 constexpr int kHistBins = DI_HIST_BINS;  // score histogram of the tile-local pre-selection = slots of the hit-group list (multiple of 256)
 #ifndef DI_TILES_PER_ITEM
-#define DI_TILES_PER_ITEM 2
+#define DI_TILES_PER_ITEM 4
 #endif
 constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers (1 .. 4)
-static_assert(kTilesPerItem >= 1 && kTilesPerItem <= 4, "the item's segment lists must fit beside six 32 KB accumulators");
+static_assert(kTilesPerItem >= 1 && kTilesPerItem * 332 + DI_HIST_BINS * 4 <= 4800,
+              "segment lists + hit list must leave room for six CTAs of 32 KB accumulators per SM (static smem <= 5 KB)");
 
 constexpr int kRecInlineTerms = 12;
 struct __align__(64) QueryRec {   // one cache-line-friendly record per query of the batch
@@ -733,8 +734,8 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
     const uint32_t steps_per_lane = (p.tiles_per_lane + kTilesPerItem - 1) / kTilesPerItem;
     const unsigned long long n_items = (unsigned long long)steps_per_lane * n_virtual;
     const bool narrow = n_items <= 0xFFFFFFFFull;  // 32-bit item arithmetic (a 64-bit divide is ~100 instructions)
-    unsigned long long next = 0;
 #ifdef DI_CLAIM_AHEAD
+    unsigned long long next = 0;
     if (threadIdx.x == 0) next = atomicAdd(counter, 1ull);
 #endif
     if (!ACC32) zero_words16(s_acc4, p.tile_docs / 8);  // accumulator invariant: zero at every item start

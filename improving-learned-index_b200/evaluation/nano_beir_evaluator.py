@@ -5,9 +5,14 @@ src/deep_impact/evaluation/nano_beir_evaluator.py (SparseSearch :70-137, BaseEva
 ``SparseSearch`` keeps the reference's constructor, attributes and ``search`` signature and
 return shape; the inversion of the model's (term, impact) lists and the query scoring run on
 the GPU. The model is the same duck type: ``get_impact_scores_batch(list[str])`` and
-``process_query(str)``. Impacts must be integers in [0, 255] (the 8-bit index the reference's
-own quantize step produces, defaults.py:26) unless ``quantize_max`` is given, in which case
-they are first quantized with the reference rule int(v * 255 / quantize_max).
+``process_query(str)``. The GPU index is the 8-bit index the reference's own quantize step produces
+(defaults.py:26): impacts must be integers in [0, 255], or ``quantize_max`` says how to get there —
+a number: the reference rule int(v * 255 / quantize_max) (quantize.py:13-14,37); ``"auto"``: the same
+rule with the collection's own maximum (find_max_value, quantize.py:17-24) whenever the model emits
+non-integer impacts (what a real DeepImpact model does, models/original.py:309). ``NanoBEIREvaluator``
+uses ``"auto"``. Scores are then sums of 8-bit impacts — the scale of the reference's on-disk index
+path — not the float sums the reference's in-memory SparseSearch returns: documents whose float
+scores differ by less than the quantization step may swap places (documented deviation).
 Ties are ordered by corpus position (the reference: first-touch order, PYTHONHASHSEED-dependent).
 """
 from __future__ import annotations
@@ -79,8 +84,14 @@ class SparseSearch:
                         raw_scores.append(float(score))
                 doc_offsets.append(len(term_ids))
         scores = np.asarray(raw_scores, dtype=np.float64)
-        if self.quantize_max is not None:
-            values = engine.quantize(scores, self.quantize_max).astype(np.int64)
+        quantize_max = self.quantize_max
+        if isinstance(quantize_max, str):
+            if quantize_max != "auto":
+                raise ValueError("quantize_max must be a number, None or 'auto'")
+            integral = scores.size == 0 or (np.array_equal(np.floor(scores), scores) and scores.max() <= 255)
+            quantize_max = None if integral else engine.find_max(scores)
+        if quantize_max is not None:
+            values = engine.quantize(scores, quantize_max).astype(np.int64)
         else:
             values = scores.astype(np.int64)
             if scores.size and not np.array_equal(values, scores):
@@ -135,9 +146,10 @@ class NanoBEIREvaluator(BaseEvaluator):
 
     K_VALUES = [10, 100, 1000]
 
-    def __init__(self, batch_size=16, verbose=False, datasets: Optional[Dict[str, Dataset]] = None):
+    def __init__(self, batch_size=16, verbose=False, datasets: Optional[Dict[str, Dataset]] = None, quantize_max="auto"):
         super().__init__(batch_size, verbose)
         self._datasets = datasets
+        self.quantize_max = quantize_max   # how float model impacts reach the 8-bit index (see SparseSearch)
 
     def dataset_names(self) -> Iterable[str]:
         return list(self._datasets) if self._datasets is not None else list(MAPPING_DATASET_NAME_TO_ID)
@@ -162,7 +174,7 @@ class NanoBEIREvaluator(BaseEvaluator):
 
     def evaluate_dataset(self, model, dataset_name):
         dataset = self._load_dataset(dataset_name)
-        searcher = SparseSearch(model, batch_size=self.batch_size, verbose=self.verbose)
+        searcher = SparseSearch(model, batch_size=self.batch_size, verbose=self.verbose, quantize_max=self.quantize_max)
         results = searcher.search(dataset.queries, dataset.corpus, k=1000)
         return EvaluateRetrieval().evaluate(dataset.relevant_docs, results, self.K_VALUES)
 

@@ -230,6 +230,23 @@ int di_shared_free(void *d_ptr);
  * and visible to all ranks' work enqueued after it. */
 int di_peer_barrier_dev(uint32_t *const *d_flags, uint32_t n_ranks, uint32_t my_rank, uint32_t epoch, void *stream);
 
+/* ------------------------------------------------------------------ after the search: run file and metrics
+ * di_write_run_file replaces RunFile.writelines (src/utils/datasets.py:312-317) for a whole batch: appends the rows
+ * "qid<TAB>pid<TAB>rank<TAB>score\n" (rank from 1) of n_queries result lists to `path`, formatted and written by all
+ * host threads straight from the result arrays (host pointers: rows of row_stride entries, counts[i] valid). Query i's
+ * id is the bytes qid_blob[qid_offsets[i] .. qid_offsets[i+1]). The bytes are those the reference writer appends.
+ *
+ * di_eval_ranks_dev replaces the run-file pass of Metrics.evaluate (src/deep_impact/evaluation/metrics.py:31-43) while
+ * the result keys are still on the device: query i's relevant documents are the SORTED docids
+ * d_qrel_docs[d_qrel_offsets[i] .. d_qrel_offsets[i+1]); d_best_rank[i] = rank (from 1) of its first relevant hit (0 =
+ * none retrieved), d_hits[i * n_depths + j] = relevant hits with rank <= d_depths[j] (n_depths <= 8). The float
+ * arithmetic of metrics.py:36-43 stays with the caller, so the reported numbers are bit-identical. */
+int di_write_run_file(const char *path, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
+                      const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride);
+int di_eval_ranks_dev(const uint64_t *d_keys, const uint32_t *d_counts, uint32_t n_queries, uint32_t row_stride,
+                      const uint64_t *d_qrel_offsets, const uint32_t *d_qrel_docs, const uint32_t *d_depths,
+                      uint32_t n_depths, uint32_t *d_best_rank, uint32_t *d_hits, void *stream);
+
 /* ------------------------------------------------------------------ measurement hooks
  * Device time (CUDA events on the launching stream) of the di_search / di_search_dev calls made since the
  * previous di_get_timings() (reading clears the record). */

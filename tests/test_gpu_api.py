@@ -133,3 +133,12 @@ def test_sparse_search_quantize_max_and_evaluator():
             return [[(t, float(int(v * (255 / 6.0)))) for t, v in self.docs[x]] for x in texts]
     out = ev.evaluate_all(QModel(docs))
     assert set(out) == {"toy", "avg"} and out["toy"][0]["NDCG@10"] == 1.0 and out["avg"][2]["Recall@10"] == 1.0
+    # the reference's entry point with a model that emits FLOAT impacts (models/original.py:309): the evaluator
+    # quantizes with the collection's own maximum (quantize.py:17-24,37) instead of refusing
+    out_f = ev.evaluate_all(Model(docs))
+    mx = max(v for lst in docs.values() for _, v in lst)
+    by_hand = SparseSearch(Model(docs), 32, quantize_max=mx).search(queries, corpus, k=1000)
+    auto = SparseSearch(Model(docs), 32, quantize_max="auto").search(queries, corpus, k=1000)
+    assert auto == by_hand and set(out_f) == {"toy", "avg"} and 0.0 < out_f["toy"][0]["NDCG@10"] <= 1.0
+    with pytest.raises(ValueError):
+        SparseSearch(Model(docs), 32).search(queries, corpus, k=10)          # strict default: no silent rescaling
