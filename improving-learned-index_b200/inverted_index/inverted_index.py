@@ -20,6 +20,35 @@ from ..utils.defaults import (DOC_SCORE_BLOCK_BYTES, INVERTED_INDEX_DATA, INVERT
 MAX_TOP_K = 65536
 
 
+class BatchResults(Sequence):
+    """What score_batch returns: reads like the list of per-query ``[(doc_id, score), ...]`` lists that calling the
+    reference's score() in a loop gives, but holds the results as arrays (``.docids`` / ``.scores`` [n, k] and
+    ``.counts`` [n]); the tuples of query i are only built when element i is asked for. 7 M tuples for the MS MARCO dev
+    queries at depth 1000 cost seconds of Python; the search itself takes 30 ms."""
+
+    def __init__(self, docids: np.ndarray, scores: np.ndarray, counts: np.ndarray):
+        self.docids, self.scores, self.counts = docids, scores, counts
+
+    def __len__(self) -> int:
+        return int(self.counts.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        c = int(self.counts[i])
+        return list(zip(self.docids[i, :c].tolist(), self.scores[i, :c].tolist()))
+
+    def __eq__(self, other):
+        return len(self) == len(other) and all(a == b for a, b in zip(self, other))
+
+    def __repr__(self) -> str:
+        return f"BatchResults({len(self)} queries, k={self.docids.shape[1] if self.docids.ndim == 2 else 0})"
+
+
 class InvertedIndex:
     def __init__(self, index_path: Union[str, Path], doc_lo: int = 0, doc_hi: int = 0xFFFFFFFF,
                  tile_docs: int = 0, dense_ratio: int = 0, cand_slack: int = 0):
@@ -65,15 +94,15 @@ class InvertedIndex:
         get = self.vocab.get
         return [get(t, -1) for t in query_terms]
 
-    def score_batch(self, queries: Sequence[Iterable[str]], top_k: int = 1000) -> List[List[Tuple[int, int]]]:
+    def score_batch(self, queries: Sequence[Iterable[str]], top_k: int = 1000) -> "BatchResults":
         """score() for many queries in one GPU pass; element i is what score(queries[i]) returns."""
         if top_k <= 0 or not len(queries):
-            return [[] for _ in queries]
+            return BatchResults(np.zeros((len(queries), 0), dtype=np.uint32), np.zeros((len(queries), 0), dtype=np.int32),
+                                np.zeros(len(queries), dtype=np.uint32))
         k = min(int(top_k), max(int(self._n_docs_hint), 1))
         if k > MAX_TOP_K:
             raise ValueError(f'top_k={top_k} on {self._n_docs_hint} documents exceeds the supported {MAX_TOP_K}')
-        docs, scores, counts = self.device_index.search([self._term_ids(q) for q in queries], k)
-        return [list(zip(docs[i, :c].tolist(), scores[i, :c].tolist())) for i, c in enumerate(counts.tolist())]
+        return BatchResults(*self.device_index.search([self._term_ids(q) for q in queries], k))
 
     def score(self, query_terms, top_k=1000):
         return self.score_batch([list(query_terms)], top_k)[0]

@@ -101,6 +101,23 @@ class RunFile:
         with open(self.run_file_path, 'a', encoding='utf-8') as f:
             f.writelines(rows)
 
+    def write_batch(self, qids, docids, scores, counts):
+        """writelines() for a whole batch straight from result arrays (docids / scores: [n, k] rows, counts[i] valid
+        entries of row i): the same bytes, formatted and written by all host threads inside the library
+        (di_write_run_file) instead of one Python string per row."""
+        import numpy as np
+        from .. import _native as N
+        blob = [str(q).encode('utf-8') for q in qids]
+        offs = np.zeros(len(blob) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(b) for b in blob])
+        d = np.ascontiguousarray(docids, dtype=np.uint32)
+        s = np.ascontiguousarray(scores, dtype=np.int32)
+        c = np.ascontiguousarray(counts, dtype=np.uint32)
+        if d.ndim != 2 or d.shape != s.shape or d.shape[0] != len(blob) or c.shape != (len(blob),):
+            raise ValueError("write_batch: docids/scores must be [len(qids), k] and counts [len(qids)]")
+        N.check(N.lib().di_write_run_file(str(self.run_file_path).encode(), b''.join(blob), N.ptr(offs), N.ptr(d), N.ptr(s),
+                                          N.ptr(c), len(blob), d.shape[1]))
+
     def read(self):
         with open(self.run_file_path, 'r', encoding='utf-8') as f:
             for line in f:

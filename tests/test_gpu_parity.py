@@ -534,17 +534,38 @@ def test_ranker_and_metrics_end_to_end(golden, tmp_path):
     rows = [(f"{100 + i}", ' '.join(q["terms"])) for i, q in enumerate(g["queries"]) if q["terms"]]
     qfile.write_text(''.join(f"{qid}\t{text}\n" for qid, text in rows))
     run = tmp_path / "run.tsv"
-    Ranker(index_dir, qfile, run, num_workers=3, query_processor=lambda s: s.split(), top_k=10).run()
+    Ranker(index_dir, qfile, run, num_workers=3, query_processor=lambda s: s.split(), top_k=10, batch_size=7).run()
     lines = run.read_text().split('\n')[:-1]
     by_q = {}
     for line in lines:
         qid, pid, rank, score = line.split('\t')
         by_q.setdefault(qid, []).append([int(pid), int(score)])
         assert int(rank) == len(by_q[qid])
+    assert list(by_q) == [qid for qid, _ in rows if qid in by_q]            # batches reach the file in query order
     for (qid, _), q in zip(rows, [q for q in g["queries"] if q["terms"]]):
         terms = list(dict.fromkeys(q["terms"]))          # the ranker de-duplicates (set), like process_query
         want = oracle.py_score({t: i for i, t in enumerate(g["vocab"])}, g["dat"], g["idx"], terms, 10, canonical=True)
         assert by_q.get(qid, []) == [list(p) for p in want]
+    # the same run with qrels: the report computed from the device-resident keys (di_eval_ranks_dev) must equal what
+    # Metrics.evaluate reads back out of the run file, and the file must be the same bytes
+    rng = np.random.default_rng(11)
+    qrels = tmp_path / "qrels.tsv"
+    with open(qrels, "w") as f:
+        for qid, hits in by_q.items():
+            picks = {hits[int(rng.integers(0, len(hits)))][0], hits[-1][0], 10 ** 6 + int(qid)}   # two retrieved, one never retrieved
+            if int(qid) % 4 == 0:
+                picks = {10 ** 6 + int(qid)}                                   # a query with no retrieved relevant passage
+            for pid in sorted(picks):
+                f.write(f"{qid}\t0\t{pid}\t1\n")
+        f.write("99999\t0\t5\t1\n")                                           # in the qrels, not in the query file? -> must be in it
+    qfile.write_text(qfile.read_text() + "99999\tzzz-not-in-vocab\n")
+    run2 = tmp_path / "run2.tsv"
+    depths = dict(mrr_depths=[1, 10], recall_depths=[1, 3, 5, 10])
+    report = Ranker(index_dir, qfile, run2, qrels_path=qrels, query_processor=lambda s: s.split(), top_k=10, batch_size=5).run(**depths)
+    want_report = Metrics(run2, qrels, **depths).evaluate()
+    assert report == want_report and any(v > 0 for v in report.values())
+    kept = [l for l in lines if l.split('\t')[0] in by_q]
+    assert sorted(run2.read_text().split('\n')[:-1]) == sorted(kept)
 
 
 def test_metrics_golden(golden, tmp_path):

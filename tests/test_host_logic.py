@@ -256,3 +256,32 @@ def test_maxp_aggregation_matches_reference_output(golden, tmp_path):
     (tmp_path / "mixed.tsv").write_text("a\t0\t1\t2.0\n7\t0\t1\t1.0\n")
     with pytest.raises(TypeError):            # aggregate_run.py:52 cannot order 'a' against 7 either
         aggregate_run(tmp_path / "mixed.tsv", tmp_path / "mapping.txt", tmp_path / "o2.tsv")
+
+
+def test_run_file_writer_matches_python_writelines(tmp_path, monkeypatch):
+    """di_write_run_file (all host threads, pwrite at final offsets) appends exactly the bytes RunFile.writelines does
+    (datasets.py:312-317), whatever the thread count: ragged counts, empty lists, non-ASCII ids, an existing file."""
+    from improving_learned_index_b200.utils.datasets import RunFile
+    rng = np.random.default_rng(3)
+    n, k = 700, 90
+    docids = rng.integers(0, 2 ** 32, size=(n, k), dtype=np.uint64).astype(np.uint32)
+    scores = rng.integers(-5, 70000, size=(n, k)).astype(np.int32)
+    counts = rng.integers(0, k + 1, size=n).astype(np.uint32)
+    counts[:3] = [0, k, 1]
+    qids = [f"q{i}" if i % 7 else f"ü{i}-äß" for i in range(n)]
+    want = tmp_path / "python.tsv"
+    want.write_text("existing\trow\n", encoding="utf-8")
+    ref = RunFile(want)
+    for i, q in enumerate(qids):
+        ref.writelines(q, list(zip(docids[i, :counts[i]].tolist(), scores[i, :counts[i]].tolist())))
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("DI_B200_IO_THREADS", threads)
+        got = tmp_path / f"native{threads}.tsv"
+        got.write_text("existing\trow\n", encoding="utf-8")
+        RunFile(got).write_batch(qids[:300], docids[:300], scores[:300], counts[:300])      # two appends, like two batches
+        RunFile(got).write_batch(qids[300:], docids[300:], scores[300:], counts[300:])
+        assert got.read_bytes() == want.read_bytes(), threads
+    rows = list(RunFile(want).read())
+    assert rows[1][2] == 1 and len(rows) == 1 + int(counts.sum())
+    with pytest.raises(ValueError):
+        RunFile(tmp_path / "x").write_batch(qids[:2], docids[:3], scores[:3], counts[:2])
