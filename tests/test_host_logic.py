@@ -270,14 +270,14 @@ def test_run_file_writer_matches_python_writelines(tmp_path, monkeypatch):
     counts[:3] = [0, k, 1]
     qids = [f"q{i}" if i % 7 else f"ü{i}-äß" for i in range(n)]
     want = tmp_path / "python.tsv"
-    want.write_text("existing\trow\n", encoding="utf-8")
+    want.write_text("0\t1\t1\t5\n", encoding="utf-8")
     ref = RunFile(want)
     for i, q in enumerate(qids):
         ref.writelines(q, list(zip(docids[i, :counts[i]].tolist(), scores[i, :counts[i]].tolist())))
     for threads in ("1", "3", "16"):
         monkeypatch.setenv("DI_B200_IO_THREADS", threads)
         got = tmp_path / f"native{threads}.tsv"
-        got.write_text("existing\trow\n", encoding="utf-8")
+        got.write_text("0\t1\t1\t5\n", encoding="utf-8")
         RunFile(got).write_batch(qids[:300], docids[:300], scores[:300], counts[:300])      # two appends, like two batches
         RunFile(got).write_batch(qids[300:], docids[300:], scores[300:], counts[300:])
         assert got.read_bytes() == want.read_bytes(), threads
