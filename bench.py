@@ -423,8 +423,17 @@ def run_b200(args):
         if world == 1 and args.cpu_sample > 0:
             out["cpu_baseline"], out["parity"] = cpu_baseline_and_parity(
                 args, toff, docids, vals, queries, (h_docs, h_scores, h_counts), torch)
-        if world == 1 and args.py_ref_seconds > 0 and args.workload == "c2":
-            out["cpu_baseline_python"] = python_reference_leg(args, toff, docids, vals, torch, dev, L, stream)
+        if world == 1 and args.file_legs and args.workload == "c2" and args.cpu_sample > 0:
+            legs = file_based_legs(args, toff, docids, vals, queries, (h_docs, h_scores, h_counts), torch, dev, L, stream)
+            for key in ("cpu_baseline_python", "api_e2e", "load"):
+                if key in legs:
+                    out[key] = legs[key]
+            if "load" in legs:
+                out["build"]["load"] = legs["load"]
+            if "error" in legs or "unavailable" in legs:
+                out["file_legs_note"] = legs.get("error") or legs.get("unavailable")
+            if "api_e2e" in legs:
+                out["api_e2e"]["vs_e2e"] = {key: round(v["value"] / out["e2e"]["value"], 3) for key, v in legs["api_e2e"].items()}
     if world > 1 and args.verify_sharded:
         # every rank's merged result vs ONE index over all documents built on rank 0's GPU (itself checked against
         # the oracle in the 1-GPU run): the sharded path must be bit-identical
@@ -493,21 +502,27 @@ def cpu_baseline_and_parity(args, toff, docids, vals, queries, timed_result, tor
     return base, parity
 
 
-def python_reference_leg(args, toff, docids, vals, torch, dev, L, stream):
-    """The reference's own unmodified Python reader, timed on index files written from this run's CSR
-    (di_serialize: byte format of create.py:44-51) — see tools/py_reference_timing.py. Rank 0, N = 1 only."""
+def file_based_legs(args, toff, docids, vals, queries, timed_result, torch, dev, L, stream):
+    """Everything that needs the index as the reference's three FILES (rank 0, N = 1, configs[1] only): the files are
+    written once from this run's CSR (di_serialize: byte format of create.py:27-51) into a RAM-backed scratch directory,
+    then   (1) `cpu_baseline_python`: the reference's own unmodified Python reader, timed on them
+               (tools/py_reference_timing.py);
+           (2) `load`: InvertedIndex(dir) — the reference-shaped loader: file images -> pinned chunks -> HBM -> tiled index;
+           (3) `api_e2e`: the drop-in classes a user of the reference calls — Ranker.run (query TSV -> run file) and
+               InvertedIndex.score_batch — on all queries, wall clock, against `e2e` (the array-level C-ABI call)."""
     import shutil
     import tempfile
-    if not (REPO / "baseline" / "_ref" / "src").is_dir():
-        return {"unavailable": "baseline/_ref/src missing: __graft_entry__.build() stages it where /root/reference exists"}
-    P, V = docids.numel(), args.vocab
-    need = 5 * P + 16 * V + (1 << 20)
+    out = {}
+    P, V, Q, k = docids.numel(), args.vocab, len(queries), args.top_k
+    need = 5 * P + 16 * V + 40 * Q * k + (1 << 20)
     root = next((d for d in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(d) and shutil.disk_usage(d).free > need + (2 << 30)), None)
     if root is None:
         return {"unavailable": "no scratch space for the %.1f GB .dat file" % (need / 1e9)}
     tmp = Path(tempfile.mkdtemp(prefix="di_ref_index_", dir=root))
     try:
-        from improving_learned_index_b200 import _native, synthetic
+        from improving_learned_index_b200 import InvertedIndex, _native, synthetic
+        from improving_learned_index_b200.evaluation import Ranker
+        t0 = time.perf_counter()
         d_dat = torch.empty(5 * P, dtype=torch.uint8, device=dev)
         d_idx = torch.empty(2 * V, dtype=torch.int64, device=dev)
         _native.check(L.di_serialize_dev(toff.data_ptr(), docids.data_ptr(), vals.data_ptr(), V, P, d_dat.data_ptr(),
@@ -517,16 +532,70 @@ def python_reference_leg(args, toff, docids, vals, torch, dev, L, stream):
         d_idx.cpu().numpy().tofile(tmp / "inverted_index.idx")
         del d_dat, d_idx
         (tmp / "vocab.txt").write_text(''.join(synthetic.term_name(t) + '\n' for t in range(V)))
-        env = dict(os.environ)
-        env.pop("OMP_NUM_THREADS", None)
-        r = subprocess.run([sys.executable, str(REPO / "tools" / "py_reference_timing.py"), "--index-dir", str(tmp),
-                            "--queries", str(args.queries), "--vocab", str(V), "--seconds", str(args.py_ref_seconds)],
-                           capture_output=True, text=True, timeout=60 + 12 * args.py_ref_seconds, env=env)
-        if r.returncode != 0:
-            return {"unavailable": "py_reference_timing.py failed: " + r.stderr.strip().splitlines()[-1][:200]}
-        return json.loads(r.stdout.strip().splitlines()[-1])
+        out["index_files"] = {"dat_gb": round(5 * P / 1e9, 3), "write_s": round(time.perf_counter() - t0, 2), "dir": root}
+        # (1) the reference's own Python
+        if args.py_ref_seconds > 0:
+            if not (REPO / "baseline" / "_ref" / "src").is_dir():
+                out["cpu_baseline_python"] = {"unavailable": "baseline/_ref/src missing: __graft_entry__.build() stages it where /root/reference exists"}
+            else:
+                env = dict(os.environ)
+                env.pop("OMP_NUM_THREADS", None)
+                r = subprocess.run([sys.executable, str(REPO / "tools" / "py_reference_timing.py"), "--index-dir", str(tmp),
+                                    "--queries", str(args.queries), "--vocab", str(V), "--seconds", str(args.py_ref_seconds)],
+                                   capture_output=True, text=True, timeout=60 + 12 * args.py_ref_seconds, env=env)
+                out["cpu_baseline_python"] = (json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else
+                                              {"unavailable": "py_reference_timing.py failed: " + (r.stderr.strip().splitlines() or ["?"])[-1][:200]})
+        # (2) loader
+        t0 = time.perf_counter()
+        index = InvertedIndex(tmp)
+        torch.cuda.synchronize()
+        load_s = time.perf_counter() - t0
+        out["load"] = {"seconds": round(load_s, 3), "dat_gb_per_s": round(5 * P / 1e9 / load_s, 2),
+                       "what": "InvertedIndex(index_dir): vocab.txt + .idx + mmap'ed .dat -> pinned chunks -> HBM -> decode -> tiled index"}
+        # (3) the drop-in API
+        qfile, run = tmp / "queries.tsv", tmp / "run.tsv"
+        qfile.write_text(''.join("%d\t%s\n" % (i, ' '.join(synthetic.term_name(t) for t in q)) for i, q in enumerate(queries)))
+        ranker = Ranker(index, qfile, run, query_processor=lambda text: text.split(), top_k=k, batch_size=args.api_batch)
+        times = []
+        for _ in range(3):                                  # first pass = warm-up (workspace allocation)
+            if run.exists():
+                run.unlink()
+            t0 = time.perf_counter()
+            ranker.run()
+            times.append(time.perf_counter() - t0)
+        g_docs, g_scores, g_counts = (t.numpy() for t in timed_result)
+        same, n_rows = True, 0
+        with open(run) as f:                                # the rows of the first queries against the timed C-ABI batch
+            for line in f:
+                qid, pid, rank, score = line.split('\t')
+                qi, r = int(qid), int(rank) - 1
+                if qi >= 50:
+                    break
+                n_rows += 1
+                same = same and r < g_counts[qi] and int(pid) == int(g_docs[qi, r].view(np.uint32)) and int(score) == int(g_scores[qi, r])
+        term_lists = [[synthetic.term_name(t) for t in q] for q in queries]
+        sb = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = index.score_batch(term_lists, top_k=k)
+            sb.append(time.perf_counter() - t0)
+        same_sb = bool(np.array_equal(res.counts, g_counts.view(np.uint32)) and np.array_equal(res.docids[:64], g_docs[:64].view(np.uint32)))
+        out["api_e2e"] = {"ranker_run": {"value": round(Q / min(times[1:]), 1), "unit": "queries/s", "seconds": round(min(times[1:]), 4),
+                                         "what": "Ranker.run(): %d queries from a TSV -> term ids -> GPU search in batches of %d -> "
+                                                 "run file of %d rows (%.0f MB)" % (Q, args.api_batch, int(g_counts.sum()), run.stat().st_size / 1e6),
+                                         "rows_checked_against_timed_batch": n_rows, "rows_match": bool(same)},
+                          "score_batch": {"value": round(Q / min(sb[1:]), 1), "unit": "queries/s", "seconds": round(min(sb[1:]), 4),
+                                          "what": "InvertedIndex.score_batch(list of term-string lists, top_k): arrays behind a lazy list view",
+                                          "rows_match": same_sb}}
+        if not (same and same_sb):
+            raise SystemExit("PARITY FAILURE: the drop-in API returned other rows than the timed C-ABI batch")
+        index.device_index.close()
+        return out
+    except SystemExit:
+        raise
     except Exception as e:          # a reported baseline must never take the GPU measurement down with it
-        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        out["error"] = "%s: %s" % (type(e).__name__, str(e)[:300])
+        return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -616,6 +685,9 @@ def main():
                     help="N > 1: compare the merged result of every query with a single index built on rank 0")
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the timed CPU baseline / parity sample")
     ap.add_argument("--ref-queries-per-step", type=int, default=32)
+    ap.add_argument("--no-file-legs", dest="file_legs", action="store_false",
+                    help="skip the legs that need the index as files (Python reference, loader, drop-in API throughput)")
+    ap.add_argument("--api-batch", type=int, default=1745, help="queries per GPU call of Ranker.run in the api_e2e leg")
     ap.add_argument("--py-ref-seconds", type=float, default=10.0,
                     help="time budget per leg of the unmodified Python reference (single process and Pool); 0 = skip")
     args = ap.parse_args()

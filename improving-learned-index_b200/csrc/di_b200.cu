@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "build.cuh"
@@ -497,6 +498,57 @@ extern "C" int di_index_create_csr(const uint64_t *term_offsets, const uint32_t 
                                    params, out);
 }
 
+// Host -> device copy of a large PAGEABLE region (an mmap'ed index file): a single cudaMemcpy would fault the pages in and
+// bounce them through the driver's staging buffer on one thread. Here the region is cut into chunks; host threads
+// copy a chunk into one of a few PINNED staging buffers in parallel (that is what touches the file pages), the DMA of
+// that chunk runs asynchronously while the threads already fill the next buffer. Returns after the last DMA finished.
+static int upload_pinned(void *d_dst, const uint8_t *src, uint64_t bytes, cudaStream_t st)
+{
+    constexpr uint64_t kChunk = 32ull << 20;
+    constexpr int kBufs = 4;
+    if (bytes <= kChunk) {
+        DI_CUDA(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, st));
+        DI_CUDA(cudaStreamSynchronize(st));
+        return DI_OK;
+    }
+    uint8_t *stage[kBufs] = {};
+    cudaEvent_t done[kBufs] = {};
+    int rc = DI_OK;
+    auto cleanup = [&] {
+        for (int b = 0; b < kBufs; ++b) {
+            if (done[b]) cudaEventDestroy(done[b]);
+            if (stage[b]) cudaFreeHost(stage[b]);
+        }
+    };
+    for (int b = 0; b < kBufs && rc == DI_OK; ++b) {
+        if (cudaHostAlloc((void **)&stage[b], kChunk, cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming) != cudaSuccess)
+            rc = set_error(DI_ERR_NOMEM, "pinned staging buffers for the index upload: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    const unsigned n_threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    uint64_t chunk_i = 0;
+    for (uint64_t off = 0; off < bytes && rc == DI_OK; off += kChunk, ++chunk_i) {
+        const int b = (int)(chunk_i % kBufs);
+        const uint64_t n = std::min(kChunk, bytes - off);
+        if (chunk_i >= kBufs && cudaEventSynchronize(done[b]) != cudaSuccess) { rc = set_error(DI_ERR_CUDA, "index upload failed"); break; }
+        {
+            std::vector<std::thread> pool;
+            const uint64_t per = (n + n_threads - 1) / n_threads;
+            for (unsigned t = 0; t < n_threads; ++t) {
+                const uint64_t lo = std::min<uint64_t>(n, t * per), hi = std::min<uint64_t>(n, lo + per);
+                if (lo < hi) pool.emplace_back([=] { memcpy(stage[b] + lo, src + off + lo, hi - lo); });
+            }
+            for (std::thread &th : pool) th.join();
+        }
+        if (cudaMemcpyAsync((uint8_t *)d_dst + off, stage[b], n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaEventRecord(done[b], st) != cudaSuccess)
+            rc = set_error(DI_ERR_CUDA, "index upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == DI_OK) rc = set_error(DI_ERR_CUDA, "index upload failed");
+    cleanup();
+    return rc;
+}
+
 extern "C" int di_index_create_files(const uint8_t *dat, uint64_t dat_bytes, const uint64_t *idx_pairs, uint32_t n_terms,
                                      uint32_t doc_lo, uint32_t doc_hi, const di_index_params *params, di_index_t **out)
 {
@@ -520,7 +572,7 @@ extern "C" int di_index_create_files(const uint8_t *dat, uint64_t dat_bytes, con
     DI_TRY(d_st.alloc((size_t)(n_terms ? n_terms : 1) * sizeof(uint64_t)));
     DI_TRY(d_d.alloc(P * sizeof(uint32_t)));
     DI_TRY(d_v.alloc(P));
-    if (dat_bytes) DI_CUDA(cudaMemcpy(d_dat.p, dat, dat_bytes, cudaMemcpyHostToDevice));
+    if (dat_bytes) DI_TRY(upload_pinned(d_dat.p, dat, dat_bytes, nullptr));
     DI_CUDA(cudaMemcpy(d_to.p, offs.data(), ((size_t)n_terms + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     if (n_terms) DI_CUDA(cudaMemcpy(d_st.p, starts.data(), (size_t)n_terms * sizeof(uint64_t), cudaMemcpyHostToDevice));
     if (P) {

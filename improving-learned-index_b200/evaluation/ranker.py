@@ -47,7 +47,8 @@ class Ranker:
         if qrels_path is not None:      # evaluate only the queries in the qrels file
             self.qrels = QueryRelevanceDataset(qrels_path=qrels_path)
             self.query_iterator = self.qrels.keys()
-        self.index = InvertedIndex(index_path=index_path)
+        # (an already loaded InvertedIndex is accepted in place of its path: loading puts the whole index into HBM)
+        self.index = index_path if isinstance(index_path, InvertedIndex) else InvertedIndex(index_path=index_path)
         self.run_file = RunFile(run_file_path=output_path)
         self.num_workers = num_workers
         self.pairwise = pairwise
