@@ -1007,6 +1007,22 @@ extern "C" int di_shared_free(void *d_ptr)
     return DI_OK;
 }
 
+// page-locked host memory for result buffers: a device-to-host copy into it runs at full PCIe rate instead of being
+// bounced through the driver's staging buffer (and the pages are never faulted in again)
+extern "C" int di_host_alloc(uint64_t bytes, void **ptr)
+{
+    if (!ptr) return set_error(DI_ERR_ARG, "NULL argument");
+    DI_TRY(ensure_device());
+    DI_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return DI_OK;
+}
+
+extern "C" int di_host_free(void *ptr)
+{
+    if (ptr) DI_CUDA(cudaFreeHost(ptr));
+    return DI_OK;
+}
+
 extern "C" int di_peer_barrier_dev(uint32_t *const *d_flags, uint32_t n_ranks, uint32_t my_rank, uint32_t epoch, void *stream)
 {
     if (!d_flags || n_ranks == 0 || n_ranks > kMaxPeerShards || my_rank >= n_ranks)

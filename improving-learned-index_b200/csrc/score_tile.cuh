@@ -39,13 +39,13 @@ constexpr int kMaxSeg = 32;        // query terms handled per round inside a wor
 #endif
 constexpr int kSparseUnroll = DI_SPARSE_UNROLL;  // independent 128-bit posting loads in flight per thread
 #ifndef DI_HIST_BINS
-#define DI_HIST_BINS 768
+#define DI_HIST_BINS 512
 #endif
 constexpr int kHistBins = DI_HIST_BINS;  // score histogram of the tile-local pre-selection = slots of the hit-group list (multiple of 256)
 #ifndef DI_TILES_PER_ITEM
-#define DI_TILES_PER_ITEM 4
+#define DI_TILES_PER_ITEM 8
 #endif
-constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers (1 .. 4)
+constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers
 static_assert(kTilesPerItem >= 1 && kTilesPerItem * 332 + DI_HIST_BINS * 4 <= 4800,
               "segment lists + hit list must leave room for six CTAs of 32 KB accumulators per SM (static smem <= 5 KB)");
 

@@ -59,16 +59,34 @@ def serialize(term_offsets, docids, impacts):
     return dat, idx
 
 
+# --------------------------------------------------------------------------- host buffers
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """np.empty in page-locked host memory (di_host_alloc): the result buffers of a host-level search. The memory is
+    released when the last array viewing it is collected."""
+    import weakref
+    dtype = np.dtype(dtype)
+    n = max(int(np.prod(shape)) * dtype.itemsize, 16)
+    ptr = ctypes.c_void_p()
+    N.check(N.lib().di_host_alloc(n, ctypes.byref(ptr)))
+    buf = (ctypes.c_uint8 * n).from_address(ptr.value)
+    weakref.finalize(buf, N.lib().di_host_free, ptr)       # numpy keeps `buf` alive as the base of every view
+    return np.frombuffer(buf, dtype=np.uint8, count=int(np.prod(shape)) * dtype.itemsize).view(dtype).reshape(shape)
+
+
 # --------------------------------------------------------------------------- queries
 def flatten_queries(queries: Sequence[Iterable[int]]):
     """List of term-id lists -> (flat u32 terms, u64 offsets). Negative / None ids become OOV."""
-    offs = np.zeros(len(queries) + 1, dtype=np.uint64)
-    flat = []
-    for i, q in enumerate(queries):
-        for t in q:
-            flat.append(N.OOV if (t is None or t < 0) else int(t))
-        offs[i + 1] = len(flat)
-    return np.asarray(flat, dtype=np.uint32).reshape(-1), offs
+    from itertools import chain
+    lists = [q if isinstance(q, (list, tuple)) else list(q) for q in queries]
+    offs = np.zeros(len(lists) + 1, dtype=np.uint64)
+    if lists:
+        np.cumsum(np.fromiter(map(len, lists), dtype=np.int64, count=len(lists)), out=offs[1:].view(np.int64))
+    try:
+        flat = np.fromiter(chain.from_iterable(lists), dtype=np.int64, count=int(offs[-1]))
+    except TypeError:                      # a None among the ids
+        flat = np.asarray([-1 if t is None else int(t) for t in chain.from_iterable(lists)], dtype=np.int64)
+    flat[(flat < 0) | (flat > N.OOV)] = N.OOV
+    return flat.astype(np.uint32).reshape(-1), offs
 
 
 class DeviceIndex:
@@ -174,12 +192,27 @@ class DeviceIndex:
                                   N.ptr(out_docids), N.ptr(out_scores), N.ptr(out_counts)))
         return out_docids, out_scores, out_counts
 
-    def search(self, queries: Sequence[Iterable[int]], top_k: int):
-        """queries: list of term-id lists. Returns (docids[Q,k], scores[Q,k], counts[Q])."""
+    def search(self, queries: Sequence[Iterable[int]], top_k: int, pinned: bool = False):
+        """queries: list of term-id lists. Returns (docids[Q,k], scores[Q,k], counts[Q]). pinned=True: the arrays
+        live in page-locked memory owned by the index (full-rate device-to-host copy of large results) and are
+        RECYCLED: two sets per result shape alternate, so a result stays valid until the second next pinned call."""
         flat, offs = flatten_queries(queries)
         if flat.size == 0:
             flat = np.zeros(1, dtype=np.uint32)
-        return self.search_flat(flat, offs, top_k)
+        if not pinned:
+            return self.search_flat(flat, offs, top_k)
+        n_q = len(offs) - 1
+        sets = self.__dict__.setdefault("_pinned_sets", {})
+        if len(sets) > 8:
+            sets.clear()
+        ring = sets.setdefault((n_q, top_k), [None, None, 0])
+        slot = ring[2] % 2
+        ring[2] += 1
+        if ring[slot] is None:
+            ring[slot] = (pinned_empty((n_q, top_k), np.uint32), pinned_empty((n_q, top_k), np.int32), pinned_empty((n_q,), np.uint32))
+        out = ring[slot]
+        out[2][:] = 0
+        return self.search_flat(flat, offs, top_k, *out)
 
     def search_device(self, d_q_terms, d_q_offsets, n_queries: int, max_query_len: int, top_k: int,
                       d_out_keys, d_out_counts, stream: int = 0, d_theta_init=None):

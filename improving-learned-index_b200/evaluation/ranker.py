@@ -72,15 +72,24 @@ class Ranker:
         qids = list(self.query_iterator)
         want_metrics = (mrr_depths or recall_depths) and self.qrels is not None
         collector = _DeviceMetrics(self.qrels, mrr_depths or [], recall_depths or []) if want_metrics else None
-        pending = None
-        with ThreadPoolExecutor(max_workers=1) as writer:      # one worker: batches reach the file in order
-            for lo in range(0, len(qids), self.batch_size):
-                batch = qids[lo:lo + self.batch_size]
-                terms = [self.get_query_terms(q) for q in batch]
+        batches = [qids[lo:lo + self.batch_size] for lo in range(0, len(qids), self.batch_size)]
+
+        def prepare(batch):                                     # query text -> term strings -> term ids (pure Python)
+            return [self.index._term_ids(self.get_query_terms(q)) for q in batch]
+
+        # three stages, each on its own thread: Python prepares batch i+1 and the library writes batch i-1 to the run
+        # file while the GPU scores batch i (ctypes releases the GIL inside the library); single workers keep the order
+        with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=1) as writer:
+            ready = prep.submit(prepare, batches[0]) if batches else None
+            pending = None
+            for i, batch in enumerate(batches):
+                term_ids = ready.result()
+                if i + 1 < len(batches):
+                    ready = prep.submit(prepare, batches[i + 1])
                 if collector is not None:
-                    docs, scores, counts = collector.search(self.index, batch, terms, self.top_k)
+                    docs, scores, counts = collector.search(self.index, batch, term_ids, self.top_k)
                 else:
-                    res = self.index.score_batch(terms, top_k=self.top_k)
+                    res = self.index.score_id_batch(term_ids, top_k=self.top_k, pinned=True)
                     docs, scores, counts = res.docids, res.scores, res.counts
                 if pending is not None:
                     pending.result()
@@ -117,7 +126,7 @@ class _DeviceMetrics:
         st = torch.cuda.current_stream().cuda_stream
         n = len(qids)
         k = min(int(top_k), max(int(index._n_docs_hint), 1))
-        flat, offs = engine.flatten_queries([index._term_ids(t) for t in term_lists])
+        flat, offs = engine.flatten_queries(term_lists)          # term ids already
         if flat.size == 0:
             flat = np.zeros(1, dtype=np.uint32)
         d_flat = torch.from_numpy(flat.astype(np.int64)).to(torch.int32).to(dev)
@@ -130,17 +139,19 @@ class _DeviceMetrics:
         r_offs[1:] = np.cumsum([len(r) for r in rel])
         r_docs = np.asarray([d for r in rel for d in r] or [0], dtype=np.int64)
         depths = sorted(set(self.recall_depths)) or [1]
+        d_roffs = torch.from_numpy(r_offs).to(dev)                      # named: they must outlive the kernel launches
+        d_rdocs = torch.from_numpy(r_docs).to(torch.int32).to(dev)
         best = torch.zeros(n, dtype=torch.int32, device=dev)
         hits = torch.zeros((n, len(depths)), dtype=torch.int32, device=dev)
-        for j0 in range(0, len(depths), 8):
-            part = depths[j0:j0 + 8]
-            h = torch.zeros((n, len(part)), dtype=torch.int32, device=dev)
-            N.check(N.lib().di_eval_ranks_dev(keys.data_ptr(), counts.data_ptr(), n, k, torch.from_numpy(r_offs).to(dev).data_ptr(),
-                                              torch.from_numpy(r_docs).to(torch.int32).to(dev).data_ptr(),
-                                              torch.tensor(part, dtype=torch.int32, device=dev).data_ptr(), len(part),
-                                              best.data_ptr(), h.data_ptr(), st))
-            torch.cuda.synchronize()           # the temporaries above must outlive the kernel
-            hits[:, j0:j0 + len(part)] = h
+        parts = []
+        for j0 in range(0, len(depths), 8):                             # the kernel takes up to 8 depths per launch
+            d_part = torch.tensor(depths[j0:j0 + 8], dtype=torch.int32, device=dev)
+            h = torch.zeros((n, d_part.numel()), dtype=torch.int32, device=dev)
+            N.check(N.lib().di_eval_ranks_dev(keys.data_ptr(), counts.data_ptr(), n, k, d_roffs.data_ptr(), d_rdocs.data_ptr(),
+                                              d_part.data_ptr(), d_part.numel(), best.data_ptr(), h.data_ptr(), st))
+            parts.append((j0, d_part, h))
+        for j0, d_part, h in parts:
+            hits[:, j0:j0 + d_part.numel()] = h
         docs = torch.zeros((n, k), dtype=torch.int32, device=dev)
         scores = torch.zeros((n, k), dtype=torch.int32, device=dev)
         engine.unpack_keys_device(keys, n * k, docs, scores, st)

@@ -94,7 +94,7 @@ class InvertedIndex:
         get = self.vocab.get
         return [get(t, -1) for t in query_terms]
 
-    def score_batch(self, queries: Sequence[Iterable[str]], top_k: int = 1000) -> "BatchResults":
+    def score_batch(self, queries: Sequence[Iterable[str]], top_k: int = 1000, pinned: bool = False) -> "BatchResults":
         """score() for many queries in one GPU pass; element i is what score(queries[i]) returns."""
         if top_k <= 0 or not len(queries):
             return BatchResults(np.zeros((len(queries), 0), dtype=np.uint32), np.zeros((len(queries), 0), dtype=np.int32),
@@ -102,7 +102,16 @@ class InvertedIndex:
         k = min(int(top_k), max(int(self._n_docs_hint), 1))
         if k > MAX_TOP_K:
             raise ValueError(f'top_k={top_k} on {self._n_docs_hint} documents exceeds the supported {MAX_TOP_K}')
-        return BatchResults(*self.device_index.search([self._term_ids(q) for q in queries], k))
+        return BatchResults(*self.device_index.search([self._term_ids(q) for q in queries], k, pinned=pinned))
+
+    def score_id_batch(self, term_id_lists: Sequence[Sequence[int]], top_k: int = 1000, pinned: bool = False) -> "BatchResults":
+        """score_batch for queries already mapped to term ids (-1 = not in the vocabulary)."""
+        if top_k <= 0 or not len(term_id_lists):
+            return self.score_batch([[] for _ in term_id_lists], 0)
+        k = min(int(top_k), max(int(self._n_docs_hint), 1))
+        if k > MAX_TOP_K:
+            raise ValueError(f'top_k={top_k} on {self._n_docs_hint} documents exceeds the supported {MAX_TOP_K}')
+        return BatchResults(*self.device_index.search(term_id_lists, k, pinned=pinned))
 
     def score(self, query_terms, top_k=1000):
         return self.score_batch([list(query_terms)], top_k)[0]

@@ -230,6 +230,11 @@ int di_shared_free(void *d_ptr);
  * and visible to all ranks' work enqueued after it. */
 int di_peer_barrier_dev(uint32_t *const *d_flags, uint32_t n_ranks, uint32_t my_rank, uint32_t epoch, void *stream);
 
+/* page-locked host memory for query / result buffers of di_search (optional: any host memory works, pinned memory makes
+ * the copies run at PCIe rate) */
+int di_host_alloc(uint64_t bytes, void **ptr);
+int di_host_free(void *ptr);
+
 /* ------------------------------------------------------------------ after the search: run file and metrics
  * di_write_run_file replaces RunFile.writelines (src/utils/datasets.py:312-317) for a whole batch: appends the rows
  * "qid<TAB>pid<TAB>rank<TAB>score\n" (rank from 1) of n_queries result lists to `path`, formatted and written by all
