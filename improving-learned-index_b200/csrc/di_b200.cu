@@ -674,7 +674,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
 
     // 257 * 255 = 65535 still fits a u16 accumulator — as long as a term adds to a document at most once
     const bool acc32 = max_query_len > 257 || ix->has_dup_postings;
-    const size_t acc_bytes = (size_t)ix->tile_docs * (acc32 ? 4 : 2);
+    const size_t acc_bytes = score_smem_bytes(ix->tile_docs, acc32);  // dynamic shared memory per CTA
     if ((int)acc_bytes + 4096 > ix->smem_opt_in)
         return set_error(DI_ERR_ARG, "tile of %u docs needs %zu B of shared memory for %d-bit accumulators (limit %d); "
                          "rebuild the index with smaller tiles for queries of %u terms",

@@ -181,8 +181,22 @@ __device__ __forceinline__ void add_bytes8(uint4 &a, uint32_t lo, uint32_t hi)
 //                 group holds a candidate (then the sums are kept for expand_hits). Returns the thread's hit
 //                 mask: bit 2j (+1) = the group of its j-th unit in the lower (upper) half of the tile.
 // FULL: units is a multiple of the step (U * threads), so no load or store needs a bounds predicate.
+// DI_DENSE_TMA (experiment): segment 0 of the fused pass was copied into shared memory by the TMA unit (`stage`); the
+// pass then reads it with LDS instead of LDG.
+#ifdef DI_DENSE_TMA
+constexpr bool kDenseTma = true;
+#else
+constexpr bool kDenseTma = false;
+#endif
+// dynamic shared memory of a score CTA: the accumulators, plus one staged dense segment in the TMA experiment
+__host__ __device__ inline size_t score_smem_bytes(uint32_t tile_docs, bool acc32)
+{
+    return (size_t)tile_docs * (acc32 ? 4 : 2) + ((kDenseTma && !acc32) ? tile_docs : 0);
+}
+
 template <int NB, bool FUSE, bool FULL>
-__device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *const (&ptr)[4], uint32_t units, uint32_t tm2)
+__device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *const (&ptr)[4], uint32_t units, uint32_t tm2,
+                                                  const uint4 *stage = nullptr)
 {
     // U units per step so that about 8 independent 128-bit loads are in flight per thread whatever
     // the number of dense terms (a work item is latency-bound: few CTAs per SM, L2-resident postings)
@@ -194,8 +208,12 @@ __device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *co
         for (int s = 0; s < U; ++s) {
             const uint32_t g = g0 + s * kScoreThreads;
 #pragma unroll
-            for (int u = 0; u < NB; ++u)
-                v[s][u] = (FULL || g < units) ? ldg_dense_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < NB; ++u) {
+                if (kDenseTma && FUSE && u == 0 && stage)
+                    v[s][u] = (FULL || g < units) ? stage[g] : make_uint4(0, 0, 0, 0);
+                else
+                    v[s][u] = (FULL || g < units) ? ldg_dense_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
+            }
         }
 #pragma unroll
         for (int s = 0; s < U; ++s) {
@@ -225,25 +243,25 @@ __device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *co
 
 template <int NB, bool FUSE>
 __device__ __forceinline__ uint32_t dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
-                                                 const uint4 *p3, uint32_t units, uint32_t tm2)
+                                                 const uint4 *p3, uint32_t units, uint32_t tm2, const uint4 *stage)
 {
     const uint4 *const ptr[4] = {p0, p1, p2, p3};
     // tiles of >= 16 K documents (the default) have only full steps
-    if (FUSE && units % (8 * kScoreThreads) == 0) return dense_steps16<NB, FUSE, true>(s_acc4, ptr, units, tm2);
-    return dense_steps16<NB, FUSE, false>(s_acc4, ptr, units, tm2);
+    if (FUSE && units % (8 * kScoreThreads) == 0) return dense_steps16<NB, FUSE, true>(s_acc4, ptr, units, tm2, stage);
+    return dense_steps16<NB, FUSE, false>(s_acc4, ptr, units, tm2, stage);
 }
 
 template <bool FUSE>
 __device__ __forceinline__ uint32_t dense_dispatch16(int nb, uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff,
-                                                     uint32_t units, uint32_t tm2)
+                                                     uint32_t units, uint32_t tm2, const uint4 *stage = nullptr)
 {
     const uint4 *p0 = payload4 + doff[0], *p1 = payload4 + doff[1], *p2 = payload4 + doff[2], *p3 = payload4 + doff[3];
     switch (nb) {  // nb is uniform across the CTA
-        case 4: return dense_pass16<4, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
-        case 3: return dense_pass16<3, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
-        case 2: return dense_pass16<2, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
-        case 1: return dense_pass16<1, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2);
-        default: return FUSE ? dense_pass16<0, true>(s_acc4, p0, p1, p2, p3, units, tm2) : 0u;
+        case 4: return dense_pass16<4, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
+        case 3: return dense_pass16<3, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
+        case 2: return dense_pass16<2, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
+        case 1: return dense_pass16<1, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
+        default: return FUSE ? dense_pass16<0, true>(s_acc4, p0, p1, p2, p3, units, tm2, nullptr) : 0u;
     }
 }
 
@@ -455,7 +473,7 @@ __device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t 
 // (i.e. whether the hand-off from the previous item was observed).
 template <bool ACC32>
 __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, uint32_t n_sub, uint32_t slot, uint32_t lane,
-                                           uint32_t step)
+                                           uint32_t step, uint32_t &tma_phase, uint64_t *mbar)
 {
     static_assert(kMaxSeg == 32, "the segment lookup is one warp wide");
     extern __shared__ uint4 s_acc4[];  // tile accumulators
@@ -494,6 +512,16 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                     if ((uint32_t)j < n_sub) d[j] = p.desc[(uint64_t)(tile0 + j) * p.n_terms + t];
             }
         }
+#ifdef DI_L2_PREFETCH
+        // experiment (profiles/README.md): the item's later tiles are needed a few microseconds from now — ask the TMA
+        // unit to pull their segments from HBM into L2 meanwhile (cp.async.bulk.prefetch.L2)
+#pragma unroll
+        for (int j = 1; j < kTilesPerItem; ++j)
+            if ((uint32_t)j < n_sub && d[j].n_flag) {
+                const uint32_t units16 = (d[j].n_flag & kDenseFlag) ? (p.tile_docs >> kDenseUnitShift) : (d[j].n_flag & 0xFFFFu);
+                prefetch_l2_bulk(p.payload + (uint64_t)d[j].off16 * 16, units16 * 16);
+            }
+#endif
 #pragma unroll
         for (int j = 0; j < kTilesPerItem; ++j)
             if ((uint32_t)j < n_sub) fill_seg_lists(s_seg[j], d[j], tid);
@@ -589,6 +617,11 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
             // ---- dense segments that do not go through the fused pass: plain read-modify-write
             nf = (!ACC32 && last) ? min(nd, 4u) : 0u;
             f0 = nd - nf;
+            if (kDenseTma && !ACC32 && nf && tid == 0) {  // experiment: the TMA unit stages the first fused segment meanwhile
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(mbar, T);
+                tma_load_1d(s_acc4 + T / 8, payload4 + L.off[f0], T, mbar);
+            }
             if (!ACC32) {
                 for (uint32_t j0 = 0; j0 < f0; j0 += 4)
                     dense_dispatch16<false>(f0 - j0 < 4 ? (int)(f0 - j0) : 4, s_acc4, payload4, L.off + j0, units, 0u);
@@ -633,7 +666,13 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
         //      s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
         if (!ACC32) {
             const uint32_t tm = ths - 1u;
-            const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, L.off + f0, units, tm | (tm << 16));
+            const uint4 *stage = nullptr;
+            if (kDenseTma && nf) {
+                mbar_wait(mbar, tma_phase & 1u);
+                ++tma_phase;
+                stage = s_acc4 + T / 8;
+            }
+            const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, L.off + f0, units, tm | (tm << 16), stage);
             record_hits16(mask, units, s_hist, &s_nhits);
         } else {
             scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
@@ -715,7 +754,10 @@ __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS
 {
     extern __shared__ uint4 s_acc4[];
     if (!ACC32) zero_words16(s_acc4, p.tile_docs / 8);  // the item's first barrier orders it
-    score_item<ACC32>(p, tile, 1, blockIdx.x, 0, tile);  // p.done == nullptr: the launch boundary orders the tiles
+    uint32_t tma_phase = 0;
+    __shared__ __align__(8) uint64_t s_mbar;  // DI_DENSE_TMA experiment only
+    if (kDenseTma && threadIdx.x == 0) mbar_init(&s_mbar, 1);
+    score_item<ACC32>(p, tile, 1, blockIdx.x, 0, tile, tma_phase, &s_mbar);  // p.done == nullptr: the launch boundary orders the tiles
 }
 
 // ---- launch form B: ONE persistent launch for all tiles of the batch ---------------------------
@@ -739,6 +781,9 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
     if (threadIdx.x == 0) next = atomicAdd(counter, 1ull);
 #endif
     if (!ACC32) zero_words16(s_acc4, p.tile_docs / 8);  // accumulator invariant: zero at every item start
+    uint32_t tma_phase = 0;
+    __shared__ __align__(8) uint64_t s_mbar;  // DI_DENSE_TMA experiment only
+    if (kDenseTma && threadIdx.x == 0) mbar_init(&s_mbar, 1);
     for (;;) {
         __syncthreads();  // everybody is done with the previous item's shared memory
         if (threadIdx.x == 0) {
@@ -765,7 +810,7 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
         const uint32_t tile0 = lane * p.tiles_per_lane + step * kTilesPerItem;
         const uint32_t lane_end = min((lane + 1) * p.tiles_per_lane, p.n_tiles);
         if (tile0 >= lane_end) continue;  // the last lane may be shorter; nobody waits on these steps
-        const bool synced = score_item<ACC32>(p, tile0, min((uint32_t)kTilesPerItem, lane_end - tile0), slot, lane, step);
+        const bool synced = score_item<ACC32>(p, tile0, min((uint32_t)kTilesPerItem, lane_end - tile0), slot, lane, step, tma_phase, &s_mbar);
         // Hand-off: CTA barrier, then ONE thread publishes with a release store (MEMBAR.GPU + store). The
         // barrier orders every thread's candidate / threshold writes before the release (the pattern
         // cooperative-groups grid sync relies on). done[q] must grow one step at a time: an item that had
