@@ -50,6 +50,9 @@ def zipf_tables(vocab_size, torch, dev):
     return (torch.from_numpy(cdf).to(dev), torch.from_numpy(perm.astype(np.int64)).to(dev))
 
 
+IMPACT_SKEW = 0.0   # --impact-skew S: impacts of document d are scaled by 1 / (1 + S * d / N) (a quality-ordered collection)
+
+
 def gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, dev, unique=0):
     """Documents [lo, hi) of chunk `chunk_id` (rows are generated for the whole chunk so that any
     shard split sees identical documents). Returns term ids, float64 impacts and the keep mask, every row
@@ -68,6 +71,9 @@ def gen_chunk(chunk_id, lo, hi, n_docs_total, vocab_size, draws, tables, torch, 
     zero = torch.rand((n, draws), generator=g, device=dev, dtype=torch.float32) < 0.01
     m[zero] = 0
     del z, zero
+    if IMPACT_SKEW:
+        doc = torch.arange(c0, c0 + n, device=dev, dtype=torch.float64)[:, None]
+        m = torch.round(m / (1.0 + IMPACT_SKEW * doc / n_docs_total))
     if unique:
         # first occurrence of every term in DRAW order, then the first `unique` of those
         st, order = torch.sort(terms, dim=1, stable=True)
@@ -120,7 +126,7 @@ def workload_config(args, k):
     name = ("configs[3]: 100K queries of ~6 terms, batches of %d" % args.batch if args.workload == "c4"
             else "configs[1]: MS MARCO passage-shaped synthetic index")
     return {"workload": "%s, Zipf(1) terms, top-%d" % (name, k), "docs": args.docs, "vocab": args.vocab,
-            "draws_per_doc": args.draws,
+            "draws_per_doc": args.draws, "impact_skew": args.impact_skew,
             "unique_terms_per_doc": args.unique_terms or "all distinct terms of the draws (~91 of 120; round-1 workload)",
             "queries": args.queries, "top_k": k}
 
@@ -239,14 +245,15 @@ def run_b200(args):
     docids += doc_lo                                  # docids stay global across shards
     torch.cuda.synchronize()
     t1 = time.time()
+    index_flags = _native.INDEX_TILE_BOUNDS if args.tile_bounds else 0
     if args.index_from == "docmajor":                 # one segmented two-pass sort, no term-major detour
         index = engine.DeviceIndex.from_docmajor_device(terms, imps, offs, doc_hi - doc_lo, V, P, doc_lo=doc_lo,
                                                         tile_docs=args.tile_docs, dense_ratio=args.dense_ratio,
-                                                        cand_slack=args.cand_slack)
+                                                        cand_slack=args.cand_slack, flags=index_flags)
     else:                                             # from the inverted CSR (the reference's index format)
         index = engine.DeviceIndex.from_csr_device(toff, docids, vals, V, P, doc_lo=doc_lo, doc_hi=max(doc_hi, doc_lo + 1),
                                                    tile_docs=args.tile_docs, dense_ratio=args.dense_ratio,
-                                                   cand_slack=args.cand_slack)
+                                                   cand_slack=args.cand_slack, flags=index_flags)
     t_tile = time.time() - t1
     del terms, imps, offs
     info = index.info()
@@ -407,7 +414,8 @@ def run_b200(args):
                          "algorithmic_bytes_per_step_this_gpu": ALGO_BYTES_PER_POSTING * local_postings,
                          "score_ms_per_step": round(float(np.mean(score_ms)), 3),
                          "finalize_ms_per_step": round(float(np.mean(final_ms)), 3),
-                         "tile_lanes": launches["lanes"]},
+                         "tile_lanes": launches["lanes"], "tile_bounds": bool(args.tile_bounds),
+                         "tiles_skipped_per_step": int(launches.get("tiles_skipped", 0))},
             "clocks": clocks.summary(),
             "index": {"postings_this_gpu": info["n_postings"], "payload_gb": round(info["payload_bytes"] / 1e9, 3),
                       "dense_segments": info["n_dense_segments"], "sparse_segments": info["n_sparse_segments"],
@@ -676,6 +684,10 @@ def main():
     ap.add_argument("--top-k", type=int, default=0)
     ap.add_argument("--index-from", default="docmajor", choices=["docmajor", "csr"],
                     help="build the device index straight from the doc-major collection, or from the inverted CSR")
+    ap.add_argument("--impact-skew", type=float, default=0.0,
+                    help="S > 0: impacts of document d are divided by 1 + S*d/N — a quality-ordered collection, the case "
+                         "exact tile skipping (--tile-bounds) is for")
+    ap.add_argument("--tile-bounds", action="store_true", help="build the index with DI_INDEX_TILE_BOUNDS (exact tile skipping)")
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--dense-ratio", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0, help="queries per search call (0 = all queries at once)")
@@ -698,6 +710,8 @@ def main():
     args.top_k = args.top_k or (100 if c4 else 1000)
     if c4 and not args.batch:
         args.batch = 4096
+    global IMPACT_SKEW
+    IMPACT_SKEW = args.impact_skew
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

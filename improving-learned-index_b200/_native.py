@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 OOV = 0xFFFFFFFF
 ALL_DOCS = 0xFFFFFFFF
-INDEX_NO_SEEDS, INDEX_PER_TILE = 1, 2
+INDEX_NO_SEEDS, INDEX_PER_TILE, INDEX_TILE_BOUNDS = 1, 2, 4
 
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _u32p = ctypes.POINTER(ctypes.c_uint32)
@@ -52,7 +52,7 @@ class IndexInfo(ctypes.Structure):
 class Timings(ctypes.Structure):
     _fields_ = [("score_ms", ctypes.c_float), ("finalize_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("score_launches", ctypes.c_uint32), ("other_launches", ctypes.c_uint32),
-                ("lanes", ctypes.c_uint32), ("acc32", ctypes.c_uint32)]
+                ("lanes", ctypes.c_uint32), ("acc32", ctypes.c_uint32), ("tiles_skipped", ctypes.c_uint64)]
 
 
 # name -> (restype, argtypes); must list every symbol include/di_b200.h declares

@@ -461,6 +461,12 @@ __global__ void seg_size_kernel(const uint32_t *__restrict__ seg_begin, const ui
     }
 }
 
+__global__ void narrow_u8_kernel(const uint32_t *__restrict__ in, uint64_t n, uint8_t *__restrict__ out)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)min(in[i], 255u);
+}
+
 __global__ void seg_desc_kernel(const uint32_t *__restrict__ off16, const uint32_t *__restrict__ n_flag, uint64_t n_segs,
                                 SegDesc *__restrict__ desc)
 {
@@ -477,12 +483,25 @@ __global__ void fill_payload_kernel(const uint64_t *__restrict__ ka, const uint6
                                     const uint32_t *__restrict__ cur, uint64_t n_keys, uint32_t n_terms,
                                     const SegDesc *__restrict__ desc, const uint32_t *__restrict__ seg_begin,
                                     const uint32_t *__restrict__ seg_odd, uint32_t tile_docs, uint8_t *__restrict__ payload,
-                                    const uint32_t *__restrict__ seed_slot, uint32_t *__restrict__ seed_hist)
+                                    const uint32_t *__restrict__ seed_slot, uint32_t *__restrict__ seed_hist,
+                                    uint32_t *__restrict__ seg_max32)
 {
     const uint64_t *__restrict__ keys = rs_result(ka, kb, cur);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_keys; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = keys[i];
+    const uint64_t n_round = (n_keys + 31) & ~31ull;  // whole warps stay together for the warp-wide maximum below
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = i < n_keys ? keys[i] : ~0ull;
         const uint32_t term = (uint32_t)(key >> kTkTermShift) & 0xFFFFFFu;
+        if (seg_max32) {  // largest impact per (tile, term): one atomic per warp while the warp stays inside one segment
+            const uint64_t id = key >> kTkTermShift;
+            const bool uniform = __all_sync(0xffffffffu, id == __shfl_sync(0xffffffffu, id, 0));
+            const uint32_t imp = term < n_terms ? ((uint32_t)key & 0xFFu) : 0u;
+            if (uniform) {
+                const uint32_t m = __reduce_max_sync(0xffffffffu, imp);
+                if (lane_id() == 0 && term < n_terms) atomicMax(&seg_max32[seg_index(key, n_terms)], m);
+            } else if (term < n_terms) {
+                atomicMax(&seg_max32[seg_index(key, n_terms)], imp);
+            }
+        }
         if (term >= n_terms) continue;  // hidden
         if (seed_slot) {
             const uint32_t slot = seed_slot[term];

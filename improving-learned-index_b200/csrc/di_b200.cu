@@ -30,6 +30,9 @@ struct di_index {
     unsigned long long *d_df = nullptr;
     // threshold seeds (build.cuh): per-term tables cum[v] = #postings with impact >= v for the frequent terms
     uint32_t *d_seed_slot = nullptr, *d_seed_cum = nullptr;
+    uint8_t *d_seg_max = nullptr;   // [n_tiles][n_terms] largest impact per segment (DI_INDEX_TILE_BOUNDS), else nullptr
+    DevBuf ws_skipped;
+    uint64_t last_skipped = 0;
 
     // search workspace (grown on demand)
     cudaStream_t stream = nullptr;
@@ -51,6 +54,7 @@ struct di_index {
         if (d_df) cudaFree(d_df);
         if (d_seed_slot) cudaFree(d_seed_slot);
         if (d_seed_cum) cudaFree(d_seed_cum);
+        if (d_seg_max) cudaFree(d_seg_max);
         for (auto &b : ev)
             for (auto &e : b)
                 if (e) cudaEventDestroy(e);
@@ -285,10 +289,20 @@ static int finish_tiled(di_index *ix, const uint64_t *ka, const uint64_t *kb, co
     DI_CUDA(cudaMemsetAsync(ix->d_payload, 0, ix->payload_bytes ? ix->payload_bytes : 16, st));
     seg_desc_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_size.as<uint32_t>(), d_nflag.as<uint32_t>(), n_segs, ix->d_desc);
     DI_KERNEL_CHECK();
+    const bool bounds = (ix->flags & DI_INDEX_TILE_BOUNDS) && !ix->has_dup_postings;
+    if (bounds) {  // d_end is free now: it collects the per-segment maxima as u32
+        DI_CUDA(cudaMemsetAsync(d_end.p, 0, n_segs * 4, st));
+        DI_CUDA(cudaMalloc(&ix->d_seg_max, n_segs));
+    }
     fill_payload_kernel<<<grid_for(n_keys, 256), 256, 0, st>>>(ka, kb, cur, n_keys, V, ix->d_desc, d_begin.as<uint32_t>(),
                                                                d_odd.as<uint32_t>(), ix->tile_docs, ix->d_payload,
-                                                               seeds ? ix->d_seed_slot : nullptr, seeds ? ix->d_seed_cum : nullptr);
+                                                               seeds ? ix->d_seed_slot : nullptr, seeds ? ix->d_seed_cum : nullptr,
+                                                               bounds ? d_end.as<uint32_t>() : nullptr);
     DI_KERNEL_CHECK();
+    if (bounds) {
+        narrow_u8_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_end.as<uint32_t>(), n_segs, ix->d_seg_max);
+        DI_KERNEL_CHECK();
+    }
     if (seeds) {
         seed_cum_kernel<<<(unsigned)((max_slots * 32 + 255) / 256), 256, 0, st>>>(ix->d_seed_cum, (uint32_t)max_slots);
         DI_KERNEL_CHECK();
@@ -729,6 +743,10 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     DI_TRY(ensure(ix->ws_theta, n_virtual * 8));
     DI_TRY(ensure(ix->ws_order, (size_t)batch * sizeof(QueryRec)));
     DI_TRY(ensure(ix->ws_done, 8 + n_virtual * 4));
+    if (ix->d_seg_max && !ix->ws_skipped.p) {
+        DI_TRY(ix->ws_skipped.alloc(8));
+        DI_CUDA(cudaMemsetAsync(ix->ws_skipped.p, 0, 8, st));
+    }
     if (lanes > 1) {
         DI_TRY(ensure(ix->ws_lane_keys, n_virtual * top_k * 8));
         DI_TRY(ensure(ix->ws_lane_counts, n_virtual * 4));
@@ -762,6 +780,8 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         a.recs = ix->ws_order.as<QueryRec>();
         a.n_queries = nq;
         a.n_tiles = ix->n_tiles;
+        a.seg_max = ix->d_seg_max;
+        a.n_skipped = ix->d_seg_max ? ix->ws_skipped.as<unsigned long long>() : nullptr;
         a.lanes = lanes;
         a.tiles_per_lane = tiles_per_lane;
 #ifdef DI_PROFILE_PHASES
@@ -1054,6 +1074,12 @@ extern "C" int di_get_timings(di_index_t *ix, di_timings *out)
     out->other_launches = ix->other_launches;
     out->lanes = ix->last_lanes;
     out->acc32 = ix->last_acc32;
+    if (ix->ws_skipped.p) {   // tiles skipped since the previous read (the events above have synchronised the stream's work)
+        unsigned long long n = 0;
+        DI_CUDA(cudaMemcpy(&n, ix->ws_skipped.p, 8, cudaMemcpyDeviceToHost));
+        DI_CUDA(cudaMemset(ix->ws_skipped.p, 0, 8));
+        out->tiles_skipped = n;
+    }
     ix->n_batches = 0;
     ix->score_launches = ix->other_launches = 0;
     return DI_OK;

@@ -116,7 +116,7 @@ inline int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uin
 // independent segments (the document tiles of a shard) that are sorted each within itself. Per call:
 //   * ONE histogram kernel counts every pass's digits in a single read of the keys, one small kernel turns the
 //     counts into digit bases (per segment and pass);
-//   * per pass ONE kernel: a block takes a tile of 8192 keys in ticket order, ranks them (stable: warp match + per-warp
+//   * per pass ONE kernel: a block takes a tile of 8192 keys in ticket order, ranks them (stable: warp ballots + per-warp
 //     running counters), finds its offset inside every digit's output run by DECOUPLED LOOK-BACK over the preceding
 //     blocks of its segment (each block first publishes its own digit counts, then sums its predecessors' until it
 //     meets one that already knows its inclusive prefix), sorts the tile by digit in shared memory and writes each
@@ -288,7 +288,17 @@ rs_onesweep_kernel(uint64_t *__restrict__ buf_a, uint64_t *__restrict__ buf_b, S
     for (int s = 0; s < kRsItems; ++s) {
         const bool valid = wbase + (uint64_t)s * 32 + lane < tile_hi;
         const unsigned digit = valid ? ((unsigned)(key[s] >> shift) & dmask) : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        // lanes holding the same digit, from nine ballots (one per digit bit + validity): MATCH.ANY does this in one
+        // instruction but occupies the address-divergence unit for ~50 cycles per warp — it was the kernel's limiter
+        // (ADU pipe 73 % busy, profiles/r2_sort_ncu.txt)
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+        if (!valid) peers = ~peers;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const unsigned bit = (digit >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+        }
         uint32_t before = 0;
         if (valid) before = warp_cnt[warp][digit];
         __syncwarp();

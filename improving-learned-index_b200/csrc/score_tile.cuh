@@ -46,7 +46,7 @@ constexpr int kHistBins = DI_HIST_BINS;  // score histogram of the tile-local pr
 #define DI_TILES_PER_ITEM 8
 #endif
 constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers
-static_assert(kTilesPerItem >= 1 && kTilesPerItem * 332 + DI_HIST_BINS * 4 <= 4800,
+static_assert(kTilesPerItem >= 1 && kTilesPerItem * 336 + DI_HIST_BINS * 4 <= 4800,
               "segment lists + hit list must leave room for six CTAs of 32 KB accumulators per SM (static smem <= 5 KB)");
 
 constexpr int kRecInlineTerms = 12;
@@ -73,6 +73,11 @@ struct SearchArgs {
     // `lanes` contiguous sub-ranges that run independently (own candidate list and threshold per
     // (lane, query), all per-query arrays are [lanes][n_queries]) and are merged like shards afterwards.
     uint32_t n_queries, n_tiles, lanes, tiles_per_lane;
+    // exact tile skipping (MaxScore-style bound, optional): seg_max[tile][term] = largest impact of the term inside the
+    // tile; a (query, tile) whose bounds add up to less than the query's threshold cannot hold a result and is not
+    // scored at all. nullptr = off (also for an index in which a posting list names a document twice).
+    const uint8_t *seg_max;
+    unsigned long long *n_skipped;  // tiles skipped that way (diagnostic counter)
 #ifdef DI_PROFILE_PHASES
     unsigned long long *prof;   // [n_tiles][8] cycles per phase, summed over the tile's work items (diagnostic build)
 #endif
@@ -442,11 +447,16 @@ struct SegLists {
     uint16_t seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
     uint32_t spref[kMaxSeg + 1];  // exclusive prefix of the sparse segments' unit counts
     uint32_t nd, ns;
+    uint32_t ub;                  // sum over the round's terms of their largest impact in this tile (0xFFFFFFFF = unknown)
     __device__ __forceinline__ uint32_t soff(uint32_t j) const { return off[kMaxSeg - 1 - j]; }
 };
 
-__device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t lane)
+__device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t lane, uint32_t max_impact)
 {
+    uint32_t ub = max_impact;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ub += __shfl_xor_sync(0xffffffffu, ub, o);
+    if (lane == 0) L.ub = ub;
     const bool is_dense = (d.n_flag & kDenseFlag) != 0, is_sparse = !is_dense && d.n_flag != 0;
     const uint32_t bd = __ballot_sync(0xffffffffu, is_dense), bs = __ballot_sync(0xffffffffu, is_sparse);
     const uint32_t su = is_sparse ? (d.n_flag & 0xFFFFu) : 0u;
@@ -502,15 +512,24 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
     // ---- first-round segment lookup of ALL the item's tiles: warp 0, a lane's descriptor loads in flight together
     if (tid < kMaxSeg) {
         SegDesc d[kTilesPerItem];
+        uint32_t mx[kTilesPerItem];   // this term's largest impact in each tile; without the table: unknown (no skipping)
+        const bool bounded = p.seg_max != nullptr && qe - qb <= kMaxSeg;
 #pragma unroll
-        for (int j = 0; j < kTilesPerItem; ++j) d[j] = SegDesc{0u, 0u};
+        for (int j = 0; j < kTilesPerItem; ++j) { d[j] = SegDesc{0u, 0u}; mx[j] = 0u; }
         if (qb + tid < qe) {
             const uint32_t t = tid < kRecInlineTerms ? rec->terms[tid] : p.q_terms[qb + tid];
             if (t < p.n_terms) {  // DI_OOV_TERM and anything out of range: no postings
 #pragma unroll
                 for (int j = 0; j < kTilesPerItem; ++j)
-                    if ((uint32_t)j < n_sub) d[j] = p.desc[(uint64_t)(tile0 + j) * p.n_terms + t];
+                    if ((uint32_t)j < n_sub) {
+                        d[j] = p.desc[(uint64_t)(tile0 + j) * p.n_terms + t];
+                        if (bounded) mx[j] = p.seg_max[(uint64_t)(tile0 + j) * p.n_terms + t];
+                    }
             }
+        }
+        if (!bounded) {
+#pragma unroll
+            for (int j = 0; j < kTilesPerItem; ++j) mx[j] = tid == 0 ? 0xFFFFFFFFu : 0u;  // the sum saturates to "unknown"
         }
 #ifdef DI_L2_PREFETCH
         // experiment (profiles/README.md): the item's later tiles are needed a few microseconds from now — ask the TMA
@@ -524,7 +543,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
 #endif
 #pragma unroll
         for (int j = 0; j < kTilesPerItem; ++j)
-            if ((uint32_t)j < n_sub) fill_seg_lists(s_seg[j], d[j], tid);
+            if ((uint32_t)j < n_sub) fill_seg_lists(s_seg[j], d[j], tid, mx[j]);
     }
 
     DI_PROF_DECL;
@@ -546,7 +565,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                         const uint32_t t = p.q_terms[r0 + tid];
                         if (t < p.n_terms) d = desc[t];
                     }
-                    fill_seg_lists(L, d, tid);
+                    fill_seg_lists(L, d, tid, tid == 0 ? 0xFFFFFFFFu : 0u);  // later rounds: no bound
                 }
             }
             if (ACC32 && first) zero_words16(s_acc4, T / 4);  // overlaps the descriptor loads of warp 0
@@ -558,6 +577,18 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                 theta = ld_cg_u64(p.theta + sq);
                 cnt0 = ld_cg_u32(p.cnt + sq);
                 have_state = true;
+            }
+            if (first && have_state && L.ub != 0xFFFFFFFFu) {
+                // Exact skip: no document of this tile can reach the threshold (every term adds at most its largest
+                // impact in the tile). Same tie rule as below: a tie with a threshold document of an earlier tile loses.
+                uint32_t need = (uint32_t)(theta >> 32);
+                if (need == 0) need = 1;
+                if (theta != 0 && key_docid(theta) < p.doc_lo + (tile << p.tile_shift)) ++need;
+                if (L.ub < need) {
+                    if (tid == 0 && p.n_skipped) atomicAdd(p.n_skipped, 1ull);
+                    skip = true;
+                    break;
+                }
             }
             touched = touched || (nd + ns) != 0;
             DI_PROF_MARK(0);  // segment lookup

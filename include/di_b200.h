@@ -124,6 +124,11 @@ typedef struct di_index_params {
 } di_index_params;
 #define DI_INDEX_NO_SEEDS 1u /* build no threshold-seed tables (every query then starts without a bound) */
 #define DI_INDEX_PER_TILE 2u /* diagnostic: one kernel launch per document tile instead of one persistent launch */
+#define DI_INDEX_TILE_BOUNDS 4u /* keep the largest impact of every (tile, term): a (query, tile) whose bounds add up to less
+                                   than the query's running threshold is skipped without being scored — a proof (MaxScore
+                                   style), results are unchanged. Pays when impacts are skewed across the document range
+                                   (e.g. documents ordered by quality); costs one byte per (tile, term) and one byte load
+                                   per query term and tile */
 
 typedef struct di_index_info {
     uint64_t n_postings;      /* visible postings in the shard */
@@ -263,6 +268,7 @@ typedef struct di_timings {
     uint32_t other_launches;
     uint32_t lanes;      /* tile lanes per query of the last search (1 = one chain of tiles per query) */
     uint32_t acc32;      /* 1 when the last search ran with 32-bit accumulators */
+    uint64_t tiles_skipped; /* (query, tile) pairs proven empty of results by DI_INDEX_TILE_BOUNDS and not scored */
 } di_timings;
 int di_get_timings(di_index_t *index, di_timings *out);
 

@@ -299,6 +299,50 @@ def test_duplicate_postings_force_wide_accumulators():
     index.close()
 
 
+@pytest.mark.parametrize("tile_docs", [256, 1024])
+def test_tile_bounds_skip_tiles_and_keep_results_exact(tile_docs):
+    """DI_INDEX_TILE_BOUNDS: a (query, tile) whose per-term impact maxima add up to less than the query's running
+    threshold is skipped — a proof, so results must equal exhaustive scoring. Impacts fall with the docid here (a
+    quality-ordered collection), so later tiles are provably empty of results and MUST be skipped; on the plain
+    collection nothing can be skipped and nothing may change."""
+    from improving_learned_index_b200 import _native
+    n_docs, V = 40_000, 2000
+    x = quantized_csr(n_docs, V, 60, 71)
+    doc_of = x["docs"].astype(np.float64)
+    skew = np.maximum(1, (x["vals"] * (1.0 - 0.97 * doc_of / n_docs)).astype(np.int64)).astype(np.uint8)
+    queries = syn.make_queries(1500, vocab_size=V, seed=72)
+    queries[0], queries[1] = [], [V + 9]
+    queries[2] = queries[3] * 2
+    queries[5] = np.random.default_rng(3).integers(0, V, size=40).tolist()      # more than one lookup round: never skipped
+    for vals, expect_skips in ((skew, True), (x["vals"], False)):
+        index = engine.DeviceIndex.from_csr(x["toff"], x["docs"], vals, tile_docs=tile_docs, flags=_native.INDEX_TILE_BOUNDS)
+        for k in (10, 1000):
+            got = index.search(queries, k)
+            t = index.timings()
+            assert_same_results(got, oracle.score_topk_csr(x["toff"], x["docs"], vals, n_docs, queries, k), f"k={k}")
+            n_pairs = len(queries) * index.info()["n_tiles"]
+            if expect_skips:
+                assert t["tiles_skipped"] > n_pairs // 4, (t["tiles_skipped"], n_pairs)
+        one = index.search(queries[10:13], 10)                                  # tile lanes: every lane prunes from its seed on
+        assert_same_results(one, oracle.score_topk_csr(x["toff"], x["docs"], vals, n_docs, queries[10:13], 10), "lanes")
+        index.close()
+    plain = engine.DeviceIndex.from_csr(x["toff"], x["docs"], skew, tile_docs=tile_docs)
+    plain.search(queries, 10)
+    assert plain.timings()["tiles_skipped"] == 0
+    # the doc-major build keeps the same bounds
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    y = quantized_csr(20_000, 500, 40, 5)
+    imps = np.maximum(1, (y["imps"] * (1.0 - 0.97 * np.repeat(np.arange(20_000), np.diff(y["offs"].astype(np.int64))) / 20_000)).astype(np.int64)).astype(np.uint8)
+    o_toff, o_docs, o_vals = oracle.invert(y["terms"], imps, y["offs"], 500)
+    dm = engine.DeviceIndex.from_docmajor_device(torch.from_numpy(y["terms"].astype(np.int64)).to(dev).to(torch.int32),
+                                                 torch.from_numpy(imps).to(dev), torch.from_numpy(y["offs"].astype(np.int64)).to(dev),
+                                                 20_000, 500, y["terms"].size, tile_docs=tile_docs, flags=_native.INDEX_TILE_BOUNDS)
+    qs = syn.make_queries(1200, vocab_size=500, seed=9)
+    assert_same_results(dm.search(qs, 100), oracle.score_topk_csr(o_toff, o_docs, o_vals, 20_000, qs, 100), "docmajor bounds")
+    assert dm.timings()["tiles_skipped"] > 0
+
+
 def test_long_queries_use_32bit_accumulators():
     """> 257 term occurrences can overflow a u16 accumulator; > 32 terms need several rounds."""
     x = quantized_csr(3000, 400, 120, 21)

@@ -99,7 +99,10 @@ def main():
         if kernel > 1:
             break
         if r[0].isdigit() and len(r) > 8:
-            agg.append((cur, int(r[0]), r[1].strip()[:78], float(r[6] or 0), float(r[7] or 0)))
+            try:
+                agg.append((cur, int(r[0]), r[1].strip()[:78], float(r[6] or 0), float(r[7] or 0)))
+            except ValueError:
+                pass   # a source line whose text contains the csv separator
     ti = sum(a[4] for a in agg) or 1
     ts = sum(a[3] for a in agg) or 1
     print(f"\n== hottest source lines of the first captured launch (warp instructions {ti:.0f}, stall samples {ts:.0f})")
