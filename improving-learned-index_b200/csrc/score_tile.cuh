@@ -447,15 +447,20 @@ struct SegLists {
     uint16_t seven[kMaxSeg];      // sparse segments: units holding even documents (they come first)
     uint32_t spref[kMaxSeg + 1];  // exclusive prefix of the sparse segments' unit counts
     uint32_t nd, ns;
-    uint32_t ub;                  // sum over the round's terms of their largest impact in this tile (0xFFFFFFFF = unknown)
+    uint32_t ub;                  // sum over the round's terms of their largest impact in this tile (kNoBound = unknown)
     __device__ __forceinline__ uint32_t soff(uint32_t j) const { return off[kMaxSeg - 1 - j]; }
 };
+
+// max_impact: this lane's term's largest impact in the tile, or kNoBound (warp-uniform) when no bound is known.
+constexpr uint32_t kNoBound = 0xFFFFFFFFu;
 
 __device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t lane, uint32_t max_impact)
 {
     uint32_t ub = max_impact;
+    if (max_impact != kNoBound) {  // warp-uniform branch
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ub += __shfl_xor_sync(0xffffffffu, ub, o);
+        for (int o = 16; o > 0; o >>= 1) ub += __shfl_xor_sync(0xffffffffu, ub, o);
+    }
     if (lane == 0) L.ub = ub;
     const bool is_dense = (d.n_flag & kDenseFlag) != 0, is_sparse = !is_dense && d.n_flag != 0;
     const uint32_t bd = __ballot_sync(0xffffffffu, is_dense), bs = __ballot_sync(0xffffffffu, is_sparse);
@@ -529,7 +534,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
         }
         if (!bounded) {
 #pragma unroll
-            for (int j = 0; j < kTilesPerItem; ++j) mx[j] = tid == 0 ? 0xFFFFFFFFu : 0u;  // the sum saturates to "unknown"
+            for (int j = 0; j < kTilesPerItem; ++j) mx[j] = kNoBound;
         }
 #ifdef DI_L2_PREFETCH
         // experiment (profiles/README.md): the item's later tiles are needed a few microseconds from now — ask the TMA
@@ -565,7 +570,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                         const uint32_t t = p.q_terms[r0 + tid];
                         if (t < p.n_terms) d = desc[t];
                     }
-                    fill_seg_lists(L, d, tid, tid == 0 ? 0xFFFFFFFFu : 0u);  // later rounds: no bound
+                    fill_seg_lists(L, d, tid, kNoBound);  // later rounds: no bound
                 }
             }
             if (ACC32 && first) zero_words16(s_acc4, T / 4);  // overlaps the descriptor loads of warp 0
@@ -578,7 +583,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                 cnt0 = ld_cg_u32(p.cnt + sq);
                 have_state = true;
             }
-            if (first && have_state && L.ub != 0xFFFFFFFFu) {
+            if (first && have_state && L.ub != kNoBound) {
                 // Exact skip: no document of this tile can reach the threshold (every term adds at most its largest
                 // impact in the tile). Same tie rule as below: a tie with a threshold document of an earlier tile loses.
                 uint32_t need = (uint32_t)(theta >> 32);

@@ -253,6 +253,11 @@ int di_host_free(void *ptr);
  * arithmetic of metrics.py:36-43 stays with the caller, so the reported numbers are bit-identical. */
 int di_write_run_file(const char *path, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
                       const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride);
+/* optional helpers around it (best effort): allocate `bytes` of file blocks beyond the current end of the run file without
+ * changing its size — e.g. from a helper thread while the GPU is still searching, so that the writer only copies — and
+ * give back whatever was reserved but never written. */
+int di_run_file_reserve(const char *path, uint64_t bytes);
+int di_run_file_trim(const char *path);
 int di_eval_ranks_dev(const uint64_t *d_keys, const uint32_t *d_counts, uint32_t n_queries, uint32_t row_stride,
                       const uint64_t *d_qrel_offsets, const uint32_t *d_qrel_docs, const uint32_t *d_depths,
                       uint32_t n_depths, uint32_t *d_best_rank, uint32_t *d_hits, void *stream);
