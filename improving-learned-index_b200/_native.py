@@ -95,8 +95,6 @@ SIGNATURES = {
     "di_host_alloc": (ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(_vp)]),
     "di_host_free": (ctypes.c_int, [_vp]),
     "di_write_run_file": (ctypes.c_int, [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
-    "di_run_file_reserve": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64]),
-    "di_run_file_trim": (ctypes.c_int, [ctypes.c_char_p]),
     "di_eval_ranks_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]),
     "di_get_timings": (ctypes.c_int, [_vp, ctypes.POINTER(Timings)]),
     "di_collection_parse": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(_vp)]),

@@ -523,6 +523,65 @@ __global__ void fill_payload_kernel(const uint64_t *__restrict__ ka, const uint6
     }
 }
 
+// Sparse segments are added with shared-memory atomics, four per thread and 128-bit load: instruction i of a warp touches
+// the words 4L + i of the lanes' units. In docid order their banks are random (birthday collisions: ~2 wavefronts per
+// instruction, 20 % of the score kernel's shared-memory traffic). The order of postings inside a parity part is free (a
+// sum), so every run of 32 units (128 words) is re-ordered BY BANK: with four words per bank, word 4L + i lands in
+// bank L and the instruction is conflict-free. One warp per (tile, term) segment; counting sort over 32 bins.
+constexpr int kBankSortWarps = 8;
+
+__global__ void __launch_bounds__(kBankSortWarps * 32) sparse_bank_sort_kernel(const SegDesc *__restrict__ desc, uint64_t n_segs,
+                                                                            uint8_t *__restrict__ payload)
+{
+    __shared__ uint32_t s_cnt[kBankSortWarps][32];
+    __shared__ uint32_t s_words[kBankSortWarps][128];
+    const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+    uint4 *payload4 = reinterpret_cast<uint4 *>(payload);
+    for (uint64_t seg = (uint64_t)blockIdx.x * kBankSortWarps + w; seg < n_segs; seg += (uint64_t)gridDim.x * kBankSortWarps) {
+        const SegDesc d = desc[seg];
+        if ((d.n_flag & kDenseFlag) || d.n_flag == 0) continue;
+        const uint32_t total = d.n_flag & 0xFFFFu, even = d.n_flag >> 16;
+        for (int part = 0; part < 2; ++part) {
+            const uint32_t lo = part ? even : 0u, hi = part ? total : even;
+            for (uint32_t u0 = lo; u0 < hi; u0 += 32) {
+                const uint32_t n_units = min(32u, hi - u0);
+                if (n_units < 2) continue;  // a single unit is one thread's four atomics, issued one after the other
+                s_cnt[w][lane] = 0;
+                __syncwarp();
+                uint4 v = make_uint4(0, 0, 0, 0);
+                uint32_t r[4] = {0, 0, 0, 0};
+                if (lane < n_units) {
+                    v = payload4[(size_t)d.off16 + u0 + lane];
+                    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r[i] = atomicAdd(&s_cnt[w][(x[i] >> 2) & 31u], 1u);  // any order inside a bank
+                }
+                __syncwarp();
+                const uint32_t c = s_cnt[w][lane];
+                uint32_t incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (unsigned)o) incl += up;
+                }
+                __syncwarp();
+                s_cnt[w][lane] = incl - c;  // first slot of the bank
+                __syncwarp();
+                if (lane < n_units) {
+                    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s_words[w][s_cnt[w][(x[i] >> 2) & 31u] + r[i]] = x[i];
+                }
+                __syncwarp();
+                if (lane < n_units)
+                    payload4[(size_t)d.off16 + u0 + lane] = make_uint4(s_words[w][4 * lane], s_words[w][4 * lane + 1],
+                                                                       s_words[w][4 * lane + 2], s_words[w][4 * lane + 3]);
+                __syncwarp();
+            }
+        }
+    }
+}
+
 // raw .dat image -> docids / impacts arrays (records may start at any byte offset)
 __global__ void decode_dat_kernel(const uint8_t *__restrict__ dat, const uint64_t *__restrict__ term_offsets,
                                   const uint64_t *__restrict__ term_start_byte, uint32_t n_terms, uint64_t n_post,

@@ -39,7 +39,7 @@ struct di_index {
     DevBuf ws_cand, ws_cnt, ws_theta, ws_order, ws_done, ws_lane_keys, ws_lane_counts;
     DevBuf st_qterms, st_qoffs, st_keys, st_counts, st_docids, st_scores;
     int smem_opt_in = 0;
-    bool attr_set16 = false, attr_set32 = false;
+    uint32_t attr_set = 0;   // score kernel variants whose function attributes are set on this device
 
     // timing of the last search
     static constexpr int kMaxBatches = 64;
@@ -303,6 +303,11 @@ static int finish_tiled(di_index *ix, const uint64_t *ka, const uint64_t *kb, co
         narrow_u8_kernel<<<grid_for(n_segs, 256), 256, 0, st>>>(d_end.as<uint32_t>(), n_segs, ix->d_seg_max);
         DI_KERNEL_CHECK();
     }
+    if (!(ix->flags & DI_INDEX_NO_BANK_SORT)) {
+        sparse_bank_sort_kernel<<<grid_for(n_segs, kBankSortWarps, 148 * 64), kBankSortWarps * 32, 0, st>>>(ix->d_desc, n_segs,
+                                                                                                         ix->d_payload);
+        DI_KERNEL_CHECK();
+    }
     if (seeds) {
         seed_cum_kernel<<<(unsigned)((max_slots * 32 + 255) / 256), 256, 0, st>>>(ix->d_seed_cum, (uint32_t)max_slots);
         DI_KERNEL_CHECK();
@@ -446,6 +451,7 @@ static int new_index(uint32_t n_terms, uint32_t doc_lo, uint32_t doc_hi, const d
     ix->flags = params ? params->flags : 0u;
     if (getenv("DI_B200_NO_SEEDS")) ix->flags |= DI_INDEX_NO_SEEDS;   // tuning switches only
     if (getenv("DI_B200_PER_TILE")) ix->flags |= DI_INDEX_PER_TILE;
+    if (getenv("DI_B200_NO_BANK_SORT")) ix->flags |= DI_INDEX_NO_BANK_SORT;
     cudaDeviceGetAttribute(&ix->smem_opt_in, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device);
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -697,26 +703,29 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     c0 = std::max(c0, top_k);
     const uint32_t cap = std::max(c0 + ix->tile_docs, pow2_ceil(top_k));
 
-    if (acc32 && !ix->attr_set32) {
-        DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-        DI_CUDA(cudaFuncSetAttribute(score_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-        ix->attr_set32 = true;
-    }
-    if (!acc32 && !ix->attr_set16) {
-        DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-        DI_CUDA(cudaFuncSetAttribute(score_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        DI_CUDA(cudaFuncSetAttribute(score_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-        DI_CUDA(cudaFuncSetAttribute(score_persistent_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        ix->attr_set16 = true;
+    // four instantiations: 16- / 32-bit accumulators x with / without the tile bounds (an index without the bound
+    // table runs a kernel that carries no trace of it)
+    using PersistentFn = void (*)(SearchArgs, unsigned long long *);
+    using TileFn = void (*)(SearchArgs, uint32_t);
+    static const PersistentFn kPersistent[4] = {score_persistent_kernel<false, false>, score_persistent_kernel<false, true>,
+                                                score_persistent_kernel<true, false>, score_persistent_kernel<true, true>};
+    static const TileFn kTile[4] = {score_tile_kernel<false, false>, score_tile_kernel<false, true>,
+                                    score_tile_kernel<true, false>, score_tile_kernel<true, true>};
+    const int variant = (acc32 ? 2 : 0) | (ix->d_seg_max ? 1 : 0);
+    if (!(ix->attr_set & (1u << variant))) {
+        DI_CUDA(cudaFuncSetAttribute((const void *)kTile[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+        DI_CUDA(cudaFuncSetAttribute((const void *)kPersistent[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+        if (!acc32) {
+            DI_CUDA(cudaFuncSetAttribute((const void *)kTile[variant], cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+            DI_CUDA(cudaFuncSetAttribute((const void *)kPersistent[variant], cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+        }
+        ix->attr_set |= 1u << variant;
     }
     const bool per_tile_launches = (ix->flags & DI_INDEX_PER_TILE) != 0;
     int ctas_per_sm = 0, n_sms = 0;
-    if (acc32)
-        DI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, score_persistent_kernel<true>, kScoreThreads, acc_bytes));
-    else
-        DI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, score_persistent_kernel<false>, kScoreThreads, acc_bytes));
+    DI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kPersistent[variant], kScoreThreads, acc_bytes));
     DI_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, ix->device));
     const int resident_ctas = std::max(1, ctas_per_sm) * std::max(1, n_sms);
 
@@ -818,10 +827,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         if (per_tile_launches) {  // DI_B200_PER_TILE=1: one launch per tile (to profile a single tile)
             a.done = nullptr;
             for (uint32_t tile = 0; tile < ix->n_tiles; ++tile) {
-                if (acc32)
-                    score_tile_kernel<true><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
-                else
-                    score_tile_kernel<false><<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
+                kTile[variant]<<<nq, kScoreThreads, acc_bytes, st>>>(a, tile);
                 ++ix->score_launches;
             }
         } else if (ix->n_tiles) {  // one persistent launch over all (lane, query, tile) items of the batch
@@ -830,10 +836,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
             DI_CUDA(cudaMemsetAsync(ix->ws_done.p, 0, 8 + nv * 4, st));
             const uint64_t n_items = (uint64_t)((tiles_per_lane + kTilesPerItem - 1) / kTilesPerItem) * nv;
             const unsigned grid = (unsigned)std::min<uint64_t>(n_items, (uint64_t)resident_ctas);
-            if (acc32)
-                score_persistent_kernel<true><<<grid, kScoreThreads, acc_bytes, st>>>(a, counter);
-            else
-                score_persistent_kernel<false><<<grid, kScoreThreads, acc_bytes, st>>>(a, counter);
+            kPersistent[variant]<<<grid, kScoreThreads, acc_bytes, st>>>(a, counter);
             ++ix->score_launches;
         }
         DI_KERNEL_CHECK();

@@ -15,11 +15,7 @@
 #include <thread>
 #include <vector>
 
-#ifndef _GNU_SOURCE
-#define _GNU_SOURCE
-#endif
 #include <fcntl.h>
-#include <linux/falloc.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -172,36 +168,6 @@ extern "C" int di_write_run_file(const char *path, const char *qid_blob, const u
                 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fmt).count());
     for (unsigned t = 0; t < n_threads; ++t)
         if (rcs[t]) return di::set_error(DI_ERR_ARG, "write to %s failed: %s", path, strerror(rcs[t]));
-    return DI_OK;
-}
-
-// Page-cache (or tmpfs) pages of a growing file are allocated at ~4 GB/s however many threads write: for a 144 MB run file
-// that is longer than the GPU needs to produce it. di_run_file_reserve allocates `bytes` beyond the current end of the
-// file WITHOUT changing its size (fallocate KEEP_SIZE), so a caller can have a helper thread do it while the GPU searches;
-// the writer's pwrite then only copies. di_run_file_trim gives back what was reserved but not written. Both are best
-// effort: a file system without fallocate support simply leaves the allocation to the writer.
-extern "C" int di_run_file_reserve(const char *path, uint64_t bytes)
-{
-    if (!path) return di::set_error(DI_ERR_ARG, "NULL argument");
-    const int fd = open(path, O_WRONLY | O_CREAT, 0644);
-    if (fd < 0) return di::set_error(DI_ERR_ARG, "cannot open %s: %s", path, strerror(errno));
-    struct stat st;
-    if (fstat(fd, &st) == 0 && bytes) (void)fallocate(fd, FALLOC_FL_KEEP_SIZE, st.st_size, (off_t)bytes);
-    close(fd);
-    return DI_OK;
-}
-
-extern "C" int di_run_file_trim(const char *path)
-{
-    if (!path) return di::set_error(DI_ERR_ARG, "NULL argument");
-    const int fd = open(path, O_WRONLY);
-    if (fd < 0) return DI_OK;  // nothing was written
-    struct stat st;
-    if (fstat(fd, &st) == 0) {
-        (void)fallocate(fd, FALLOC_FL_PUNCH_HOLE | FALLOC_FL_KEEP_SIZE, st.st_size, (off_t)1 << 40);  // tmpfs
-        (void)!ftruncate(fd, st.st_size);                                                              // ext4 / xfs
-    }
-    close(fd);
     return DI_OK;
 }
 

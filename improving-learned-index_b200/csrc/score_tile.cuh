@@ -486,7 +486,7 @@ __device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t 
 // launch-ordered query records. Two tiles per item halve the per-item fixed costs (claim, record read, hand-off)
 // and put the descriptor loads of both tiles in flight together. Returns whether the query's state was read
 // (i.e. whether the hand-off from the previous item was observed).
-template <bool ACC32>
+template <bool ACC32, bool BOUNDS>
 __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, uint32_t n_sub, uint32_t slot, uint32_t lane,
                                            uint32_t step, uint32_t &tma_phase, uint64_t *mbar)
 {
@@ -518,7 +518,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
     if (tid < kMaxSeg) {
         SegDesc d[kTilesPerItem];
         uint32_t mx[kTilesPerItem];   // this term's largest impact in each tile; without the table: unknown (no skipping)
-        const bool bounded = p.seg_max != nullptr && qe - qb <= kMaxSeg;
+        const bool bounded = BOUNDS && qe - qb <= kMaxSeg;
 #pragma unroll
         for (int j = 0; j < kTilesPerItem; ++j) { d[j] = SegDesc{0u, 0u}; mx[j] = 0u; }
         if (qb + tid < qe) {
@@ -583,7 +583,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                 cnt0 = ld_cg_u32(p.cnt + sq);
                 have_state = true;
             }
-            if (first && have_state && L.ub != kNoBound) {
+            if (BOUNDS && first && have_state && L.ub != kNoBound) {
                 // Exact skip: no document of this tile can reach the threshold (every term adds at most its largest
                 // impact in the tile). Same tie rule as below: a tie with a threshold document of an earlier tile loses.
                 uint32_t need = (uint32_t)(theta >> 32);
@@ -785,7 +785,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
 }
 
 // ---- launch form A: one launch per tile, grid = queries (kept for profiling single tiles) -----
-template <bool ACC32>
+template <bool ACC32, bool BOUNDS>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS) score_tile_kernel(SearchArgs p, uint32_t tile)
 {
     extern __shared__ uint4 s_acc4[];
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS
     uint32_t tma_phase = 0;
     __shared__ __align__(8) uint64_t s_mbar;  // DI_DENSE_TMA experiment only
     if (kDenseTma && threadIdx.x == 0) mbar_init(&s_mbar, 1);
-    score_item<ACC32>(p, tile, 1, blockIdx.x, 0, tile, tma_phase, &s_mbar);  // p.done == nullptr: the launch boundary orders the tiles
+    score_item<ACC32, BOUNDS>(p, tile, 1, blockIdx.x, 0, tile, tma_phase, &s_mbar);  // p.done == nullptr: the launch boundary orders the tiles
 }
 
 // ---- launch form B: ONE persistent launch for all tiles of the batch ---------------------------
@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS
 // tiles (their postings stay L2-resident) and there is no per-tile launch tail. After an item,
 // done[q] = step + 1 is published with release semantics; the next step of the same query acquires it. Waits only
 // ever point at items with a smaller index, and claims are handed out in index order, so the protocol cannot deadlock.
-template <bool ACC32>
+template <bool ACC32, bool BOUNDS>
 __global__ void __launch_bounds__(kScoreThreads, ACC32 ? 1 : DI_SCORE_MIN_BLOCKS)
 score_persistent_kernel(SearchArgs p, unsigned long long *counter)
 {
@@ -846,7 +846,7 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
         const uint32_t tile0 = lane * p.tiles_per_lane + step * kTilesPerItem;
         const uint32_t lane_end = min((lane + 1) * p.tiles_per_lane, p.n_tiles);
         if (tile0 >= lane_end) continue;  // the last lane may be shorter; nobody waits on these steps
-        const bool synced = score_item<ACC32>(p, tile0, min((uint32_t)kTilesPerItem, lane_end - tile0), slot, lane, step, tma_phase, &s_mbar);
+        const bool synced = score_item<ACC32, BOUNDS>(p, tile0, min((uint32_t)kTilesPerItem, lane_end - tile0), slot, lane, step, tma_phase, &s_mbar);
         // Hand-off: CTA barrier, then ONE thread publishes with a release store (MEMBAR.GPU + store). The
         // barrier orders every thread's candidate / threshold writes before the release (the pattern
         // cooperative-groups grid sync relies on). done[q] must grow one step at a time: an item that had

@@ -79,13 +79,7 @@ class Ranker:
 
         # three stages, each on its own thread: Python prepares batch i+1 and the library writes batch i-1 to the run
         # file while the GPU scores batch i (ctypes releases the GIL inside the library); single workers keep the order
-        def reserve_all():     # page allocation of the run file, ahead of the writer and beside the GPU's work
-            for batch in batches:
-                self.run_file.reserve(self.top_k * (sum(len(str(q)) for q in batch) + 24 * len(batch)))
-
-        with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=1) as writer, \
-                ThreadPoolExecutor(max_workers=1) as reserver:
-            reserved = reserver.submit(reserve_all)
+        with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=1) as writer:
             ready = prep.submit(prepare, batches[0]) if batches else None
             pending = None
             for i, batch in enumerate(batches):
@@ -102,8 +96,6 @@ class Ranker:
                 pending = writer.submit(self.run_file.write_batch, batch, docs, scores, counts)
             if pending is not None:
                 pending.result()
-            reserved.result()
-            self.run_file.trim()
         return collector.report() if collector is not None else None
 
 

@@ -118,15 +118,6 @@ class RunFile:
         N.check(N.lib().di_write_run_file(str(self.run_file_path).encode(), b''.join(blob), N.ptr(offs), N.ptr(d), N.ptr(s),
                                           N.ptr(c), len(blob), d.shape[1]))
 
-    def reserve(self, n_bytes: int):
-        """Allocates file blocks for rows still to come (size unchanged); see di_run_file_reserve."""
-        from .. import _native as N
-        N.check(N.lib().di_run_file_reserve(str(self.run_file_path).encode(), int(n_bytes)))
-
-    def trim(self):
-        from .. import _native as N
-        N.check(N.lib().di_run_file_trim(str(self.run_file_path).encode()))
-
     def read(self):
         with open(self.run_file_path, 'r', encoding='utf-8') as f:
             for line in f:

@@ -124,6 +124,8 @@ typedef struct di_index_params {
 } di_index_params;
 #define DI_INDEX_NO_SEEDS 1u /* build no threshold-seed tables (every query then starts without a bound) */
 #define DI_INDEX_PER_TILE 2u /* diagnostic: one kernel launch per document tile instead of one persistent launch */
+#define DI_INDEX_NO_BANK_SORT 8u /* A/B switch: keep sparse postings in docid order (default: runs of 128 postings are ordered by
+                                    shared-memory bank, which makes the scorer's atomics conflict-free) */
 #define DI_INDEX_TILE_BOUNDS 4u /* keep the largest impact of every (tile, term): a (query, tile) whose bounds add up to less
                                    than the query's running threshold is skipped without being scored — a proof (MaxScore
                                    style), results are unchanged. Pays when impacts are skewed across the document range
@@ -253,11 +255,6 @@ int di_host_free(void *ptr);
  * arithmetic of metrics.py:36-43 stays with the caller, so the reported numbers are bit-identical. */
 int di_write_run_file(const char *path, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
                       const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride);
-/* optional helpers around it (best effort): allocate `bytes` of file blocks beyond the current end of the run file without
- * changing its size — e.g. from a helper thread while the GPU is still searching, so that the writer only copies — and
- * give back whatever was reserved but never written. */
-int di_run_file_reserve(const char *path, uint64_t bytes);
-int di_run_file_trim(const char *path);
 int di_eval_ranks_dev(const uint64_t *d_keys, const uint32_t *d_counts, uint32_t n_queries, uint32_t row_stride,
                       const uint64_t *d_qrel_offsets, const uint32_t *d_qrel_docs, const uint32_t *d_depths,
                       uint32_t n_depths, uint32_t *d_best_rank, uint32_t *d_hits, void *stream);
