@@ -23,6 +23,7 @@ struct di_index {
     uint32_t dense_ratio = 8, cand_slack = 0, flags = 0;
     bool has_dup_postings = false;  // some posting list names a document twice: no seeds, 32-bit accumulators
     uint32_t last_lanes = 0, last_acc32 = 0;
+    uint32_t sorted_prefix = 0;   // di_index_set_sorted_prefix: 0 = result rows fully sorted
     uint64_t n_postings = 0, payload_bytes = 0, table_bytes = 0;
     uint64_t n_dense_segments = 0, n_sparse_segments = 0, n_dense_postings = 0;
     SegDesc *d_desc = nullptr;
@@ -632,6 +633,13 @@ extern "C" int di_index_get_info(const di_index_t *ix, di_index_info *info)
     return DI_OK;
 }
 
+extern "C" int di_index_set_sorted_prefix(di_index_t *ix, uint32_t sorted_prefix)
+{
+    if (!ix) return set_error(DI_ERR_ARG, "index is NULL");
+    ix->sorted_prefix = sorted_prefix;
+    return DI_OK;
+}
+
 extern "C" int di_index_term_df(const di_index_t *ix, const uint32_t *term_ids, uint64_t n, uint64_t *df_out)
 {
     if (!ix || (!term_ids && n) || (!df_out && n)) return set_error(DI_ERR_ARG, "NULL argument");
@@ -655,7 +663,8 @@ static uint32_t pow2_ceil(uint32_t x)
 // finalize_topk_kernel with a shared-memory key buffer sized for the longest list it can meet
 // (max_n), between 32 KB and 128 KB; longer lists take the kernel's global-memory path.
 static int launch_finalize(uint64_t *cand, const uint32_t *cnt, uint32_t cap, uint32_t top_k,
-                           uint32_t max_n, uint32_t n_queries, uint64_t *out_keys, uint32_t *out_counts, cudaStream_t st)
+                           uint32_t max_n, uint32_t n_queries, uint64_t *out_keys, uint32_t *out_counts, cudaStream_t st,
+                           uint32_t sort_prefix = 0)
 {
     // function attributes belong to a device: remember per device (not per thread) that the opt-in is done
     static std::atomic<uint64_t> attr_done{0};
@@ -668,8 +677,8 @@ static int launch_finalize(uint64_t *cand, const uint32_t *cnt, uint32_t cap, ui
     }
     uint32_t smem_keys = kSortSmemKeys;
     while (smem_keys < max_n && smem_keys < 16384) smem_keys <<= 1;
-    finalize_topk_kernel<<<n_queries, kScoreThreads, (size_t)smem_keys * 8, st>>>(cand, cnt, cap, top_k,
-                                                                                 smem_keys, out_keys, out_counts);
+    finalize_topk_kernel<<<n_queries, kScoreThreads, (size_t)smem_keys * 8, st>>>(cand, cnt, cap, top_k, smem_keys, sort_prefix,
+                                                                                 out_keys, out_counts);
     DI_KERNEL_CHECK();
     return DI_OK;
 }
@@ -860,7 +869,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
         uint64_t *out_keys = d_out_keys + (uint64_t)q0 * top_k;
         uint32_t *out_counts = d_out_counts + q0;
         if (lanes == 1) {
-            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, /*max_n=*/c0, nq, out_keys, out_counts, st));
+            DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, /*max_n=*/c0, nq, out_keys, out_counts, st, ix->sorted_prefix));
             ++ix->other_launches;
         } else {  // per-lane top-k rows [lanes][nq][k], then the same merge the multi-GPU path uses
             DI_TRY(launch_finalize(a.cand, a.cnt, cap, top_k, /*max_n=*/c0, (uint32_t)nv,
@@ -920,8 +929,12 @@ extern "C" int di_search(di_index_t *ix, const uint32_t *q_terms, const uint64_t
         DI_CUDA(cudaStreamSynchronize(st));
         return DI_OK;
     }
-    DI_TRY(di_search_dev(ix, ix->st_qterms.as<uint32_t>(), ix->st_qoffs.as<uint64_t>(), n_queries, (uint32_t)max_len, top_k,
-                         nullptr, ix->st_keys.as<uint64_t>(), ix->st_counts.as<uint32_t>(), st));
+    const uint32_t row_order = ix->sorted_prefix;  // host rows are always fully sorted
+    ix->sorted_prefix = 0;
+    const int rc = di_search_dev(ix, ix->st_qterms.as<uint32_t>(), ix->st_qoffs.as<uint64_t>(), n_queries, (uint32_t)max_len, top_k,
+                                 nullptr, ix->st_keys.as<uint64_t>(), ix->st_counts.as<uint32_t>(), st);
+    ix->sorted_prefix = row_order;
+    DI_TRY(rc);
     DI_TRY(di_unpack_keys_dev(ix->st_keys.as<uint64_t>(), n_out, ix->st_docids.as<uint32_t>(), ix->st_scores.as<int32_t>(), st));
     ++ix->other_launches;
     DI_CUDA(cudaMemcpyAsync(out_docids, ix->st_docids.p, n_out * 4, cudaMemcpyDeviceToHost, st));

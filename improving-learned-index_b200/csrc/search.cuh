@@ -18,15 +18,19 @@ constexpr uint32_t kSortSmemKeys = 4096;
 // n keys resident in shared memory (s_keys has room for smem_keys >= n entries, a power of two): cut them to the k
 // best, sort descending (score desc, docid asc) and write them to out[0 .. n_out). Returns n_out; *kth receives the
 // k-th key when k keys were written, else 0.
+// sort_prefix (0 = everything): only the first sort_prefix keys of the row need to be in order — the row is then
+// [the sort_prefix best, sorted | the rest of the top k, in any order]. That is all a shard has to deliver to the
+// cross-shard merge (it reads the first k_in columns and, rarely, re-selects from the whole row), and it turns the
+// 1024-key bitonic sort of a top-1000 row into one more select + a 256-key sort.
 __device__ __forceinline__ uint32_t block_topk_sorted_smem(uint64_t *s_keys, uint32_t n, uint32_t k, uint32_t smem_keys,
                                                            uint64_t *out, uint32_t *s_hist, uint32_t *s_scan, uint32_t *s_tmp,
-                                                           uint64_t *kth_out)
+                                                           uint64_t *kth_out, uint32_t sort_prefix = 0)
 {
     uint64_t *keys = s_keys;
+    uint32_t k_pow2 = 1;
+    while (k_pow2 < k) k_pow2 <<= 1;
     if (n > k) {
         const uint64_t kth = block_select_kth(s_keys, n, k, s_hist, s_tmp);
-        uint32_t k_pow2 = 1;
-        while (k_pow2 < k) k_pow2 <<= 1;
         if (n + k_pow2 <= smem_keys) {  // room behind the list: pack the k survivors there (any order, sorted next)
             keys = s_keys + n;
             n = block_compact_ge_unordered(s_keys, n, kth, keys, s_tmp);
@@ -34,8 +38,20 @@ __device__ __forceinline__ uint32_t block_topk_sorted_smem(uint64_t *s_keys, uin
             n = block_compact_ge(s_keys, n, kth, s_scan);
         }
     }
+    uint32_t n_sort = n;  // keys[0, n_sort) get sorted
+    const uint32_t at = (uint32_t)(keys - s_keys);  // the survivors sit at s_keys[at, at + n): one half of the buffer must be free
+    if (sort_prefix && sort_prefix < n && 2 * k_pow2 <= smem_keys && kth_out == nullptr && (at == 0 || at >= k_pow2)) {
+        // partition around the sort_prefix-th key into the free half
+        const uint64_t pth = block_select_kth(keys, n, sort_prefix, s_hist, s_tmp);
+        uint64_t *dst = at ? s_keys : s_keys + k_pow2;
+        block_partition_ge_unordered(keys, n, pth, dst, s_tmp);  // exactly sort_prefix keys in front (keys are unique)
+        keys = dst;
+        n_sort = sort_prefix;
+    }
     uint32_t np2 = 1;
-    while (np2 < n) np2 <<= 1;
+    while (np2 < n_sort) np2 <<= 1;
+    // the sorted window is a power of two: it may take in a few keys of the unsorted rest (they are smaller than every
+    // key of the prefix and end up behind it), or zero padding beyond the row
     for (uint32_t i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
     bitonic_sort_desc(keys, np2);
@@ -48,7 +64,7 @@ __device__ __forceinline__ uint32_t block_topk_sorted_smem(uint64_t *s_keys, uin
 // One CTA per query: cut the candidate list to the k best and sort them descending by key
 // (score desc, docid asc). Sorting happens in shared memory when the list fits.
 __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *cand_all, const uint32_t *cnt, uint32_t cap,
-                                                                    uint32_t k, uint32_t smem_keys,
+                                                                    uint32_t k, uint32_t smem_keys, uint32_t sort_prefix,
                                                                     uint64_t *out_keys, uint32_t *out_counts)
 {
     extern __shared__ uint64_t s_keys[];  // smem_keys entries
@@ -62,7 +78,7 @@ __global__ void __launch_bounds__(kScoreThreads) finalize_topk_kernel(uint64_t *
     if (n <= smem_keys) {  // usual case: everything happens in shared memory after one coalesced read
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = cand[i];
         __syncthreads();
-        n = block_topk_sorted_smem(s_keys, n, k, smem_keys, out, s_hist, s_scan, s_tmp, nullptr);
+        n = block_topk_sorted_smem(s_keys, n, k, smem_keys, out, s_hist, s_scan, s_tmp, nullptr, sort_prefix);
         if (threadIdx.x == 0) out_counts[q] = n;
         return;
     }

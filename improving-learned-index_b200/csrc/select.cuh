@@ -211,6 +211,36 @@ __device__ __forceinline__ uint32_t block_compact_ge_unordered(const uint64_t *s
     return kept;
 }
 
+// Two-way partition of src[0, n) into dst[0, n) (dst must not overlap src): keys >= theta packed from the front, the
+// others from the back, both in arbitrary order; one shared-memory atomic per warp and side. Returns how many are >= theta.
+// s_counter: two shared words.
+__device__ __forceinline__ uint32_t block_partition_ge_unordered(const uint64_t *src, uint32_t n, uint64_t theta, uint64_t *dst,
+                                                                 uint32_t *s_counter)
+{
+    if (threadIdx.x < 2) s_counter[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    for (uint32_t i0 = threadIdx.x - lane; i0 < n; i0 += blockDim.x) {  // warp-uniform
+        const uint32_t i = i0 + lane;
+        const uint64_t key = i < n ? src[i] : 0ull;
+        const bool hi = i < n && key >= theta, lo = i < n && key < theta;
+        const uint32_t bh = __ballot_sync(0xffffffffu, hi), bl = __ballot_sync(0xffffffffu, lo);
+        uint32_t base_h = 0, base_l = 0;
+        if (lane == 0) {
+            if (bh) base_h = atomicAdd(&s_counter[0], (uint32_t)__popc(bh));
+            if (bl) base_l = atomicAdd(&s_counter[1], (uint32_t)__popc(bl));
+        }
+        base_h = __shfl_sync(0xffffffffu, base_h, 0);
+        base_l = __shfl_sync(0xffffffffu, base_l, 0);
+        if (hi) dst[base_h + __popc(bh & lanemask_lt())] = key;
+        if (lo) dst[n - 1 - (base_l + __popc(bl & lanemask_lt()))] = key;
+    }
+    __syncthreads();
+    const uint32_t kept = s_counter[0];
+    __syncthreads();
+    return kept;
+}
+
 // largest bin b such that hist[b] + hist[b+1] + ... >= k, or 0 when the whole histogram holds fewer
 // than k. n_bins is a multiple of 256. Result is returned to every thread of the block.
 __device__ uint32_t block_find_bin_from_top(const uint32_t *s_hist, int n_bins, uint32_t k, uint32_t *s_tmp /*2*/)

@@ -222,6 +222,11 @@ class DeviceIndex:
         N.check(N.lib().di_search_dev(self._h, N.ptr(d_q_terms), N.ptr(d_q_offsets), n_queries, max_query_len, top_k,
                                       N.ptr(d_theta_init), N.ptr(d_out_keys), N.ptr(d_out_counts), stream))
 
+    def set_sorted_prefix(self, p: int):
+        """Row order of search_device results from now on: 0 = fully sorted; p > 0 = [the p best keys, sorted | the rest
+        of the top-k in any order] — what a shard owes the cross-shard merge (di_index_set_sorted_prefix)."""
+        N.check(N.lib().di_index_set_sorted_prefix(self._h, int(p)))
+
     def timings(self) -> dict:
         t = N.Timings()
         N.check(N.lib().di_get_timings(self._h, ctypes.byref(t)))

@@ -135,7 +135,7 @@ class ShardedSearcher:
     incomplete [Q] int32) writes the global top-k and flags the queries whose merge is not proven exact.
     """
 
-    def __init__(self, local_search: Callable, merge: Callable, device, group=None, rows_per_shard=None):
+    def __init__(self, local_search: Callable, merge: Callable, device, group=None, rows_per_shard=None, set_row_order=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -147,6 +147,7 @@ class ShardedSearcher:
         self._buffers = {}
         self.rows_per_shard = rows_per_shard   # optional override of shard_k: k -> keys per shard in round 1
         self.round2_queries = 0          # how many queries of the last search needed their full rows gathered
+        self.set_row_order = set_row_order   # optional: p -> "only the first p keys of a local row need to be sorted"
         self._peer = None                # PeerExchange of the fused path (CUDA, world > 1), created on first use
         self._second = None
 
@@ -161,7 +162,7 @@ class ShardedSearcher:
         def merge(g_keys, g_counts, n_shards, n_q, k_in, k, out_keys, out_counts, incomplete):
             engine.merge_topk_device(g_keys, g_counts, n_shards, n_q, k, out_keys, out_counts,
                                      torch.cuda.current_stream().cuda_stream, k_in=k_in, d_incomplete=incomplete)
-        return cls(local_search, merge, device, group)
+        return cls(local_search, merge, device, group, set_row_order=index.set_sorted_prefix)
 
     def _buf(self, name, shape, dtype):
         key = (name, tuple(shape))
@@ -212,9 +213,11 @@ class ShardedSearcher:
             self._second = torch.zeros(1, dtype=torch.int32, device=self.device)
         ex = self._peer
         rows, counts, row_table, cnt_table = ex.next_set()
-        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, rows, counts)    # this shard's sorted rows
-        ex.barrier(stream)                                   # every shard's rows are written and visible
         k_in = min(k, self.rows_per_shard(k)) if self.rows_per_shard else shard_k(k, self.world)
+        if self.set_row_order:      # the merge reads k_in sorted columns, or (k_in == k) re-selects from whole rows anyway
+            self.set_row_order(k_in if k_in < k else 1)
+        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, rows, counts)    # this shard's rows
+        ex.barrier(stream)                                   # every shard's rows are written and visible
         q_lo, q_hi = shard_range(n_queries, self.world, self.rank)
         n_own = q_hi - q_lo
         out_keys = self._flat("own_keys", max(n_own, 1) * k, torch.int64)[:n_own * k].view(n_own, k)
@@ -246,10 +249,12 @@ class ShardedSearcher:
             return all_keys.view(self.world * per, k)[:n_queries], all_counts[:n_queries]
         keys = self._flat("keys", n_queries * k, torch.int64).view(n_queries, k)
         counts = self._flat("counts", n_queries, torch.int32)
-        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)   # this shard's sorted top-k
+        k_in = min(k, self.rows_per_shard(k)) if self.rows_per_shard else shard_k(k, self.world)
+        if self.set_row_order:
+            self.set_row_order(0 if self.world == 1 else (k_in if k_in < k else 1))
+        self.local_search(d_q_terms, d_q_offsets, n_queries, max_len, k, keys, counts)   # this shard's top-k rows
         if self.world == 1:
             return keys, counts
-        k_in = min(k, self.rows_per_shard(k)) if self.rows_per_shard else shard_k(k, self.world)
         if k_in == k:
             out_keys, out_counts, _ = self._gather_merge(keys, counts, n_queries, k, k, "r1_", prove=False)
             return out_keys, out_counts

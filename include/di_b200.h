@@ -166,6 +166,11 @@ int di_index_create_files(const uint8_t *dat, uint64_t dat_bytes, const uint64_t
                           const di_index_params *params, di_index_t **out);
 void di_index_destroy(di_index_t *index);
 int di_index_get_info(const di_index_t *index, di_index_info *info);
+/* Row order of di_search_dev's result (sticky; 0 = default: rows fully sorted). With sorted_prefix = p > 0 a row is
+ * [its p best keys, sorted | the rest of its top_k keys in any order] — all a SHARD has to deliver to the cross-shard merge,
+ * which reads the first k_in columns and, rarely, re-selects from the whole row; saves most of the per-row sort.
+ * (Batches small enough to run in tile lanes are always fully sorted.) di_search (host rows) ignores it. */
+int di_index_set_sorted_prefix(di_index_t *index, uint32_t sorted_prefix);
 /* visible posting count (document frequency) of each given term id in this shard; OOV -> 0 */
 int di_index_term_df(const di_index_t *index, const uint32_t *term_ids, uint64_t n, uint64_t *df_out);
 

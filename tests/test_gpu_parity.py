@@ -465,6 +465,43 @@ def test_shards_and_merge_equal_single_index():
     assert sum(s.info()["n_postings"] for s in shards) == full.info()["n_postings"]
 
 
+@pytest.mark.parametrize("k,p", [(1000, 221), (1000, 1), (300, 120), (64, 64), (1000, 999), (100, 7)])
+def test_sorted_prefix_rows_hold_the_same_top_k(k, p):
+    """di_index_set_sorted_prefix(p): a device row is [its p best keys, sorted | the rest of the top-k in any order] — the
+    same SET as the fully sorted row and the same first p columns; the host API stays fully sorted."""
+    torch = pytest.importorskip("torch")
+    x = quantized_csr(40_000, 2000, 60, 71)
+    index = engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], tile_docs=1024)
+    queries = syn.make_queries(1500, vocab_size=2000, seed=8)         # more than resident CTAs: one lane, the sharded case
+    queries[0], queries[1] = [], [int(np.argmax(np.diff(x["toff"].astype(np.int64))))]
+    flat, offs = engine.flatten_queries(queries)
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    d_flat = torch.from_numpy(flat.astype(np.int64)).to(dev).to(torch.int32)
+    d_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    n, max_len = len(queries), max(len(q) for q in queries)
+
+    def rows():
+        keys = torch.zeros((n, k), dtype=torch.int64, device=dev)
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        index.search_device(d_flat, d_offs, n, max_len, k, keys, counts, st)
+        torch.cuda.synchronize()
+        return keys.cpu().numpy().view(np.uint64), counts.cpu().numpy()
+    full, c_full = rows()
+    index.set_sorted_prefix(p)
+    part, c_part = rows()
+    host = index.search(queries, k)                                   # host rows ignore the setting
+    index.set_sorted_prefix(0)
+    assert np.array_equal(c_full, c_part)
+    for i in range(n):
+        c = int(c_full[i])
+        assert np.all(full[i, 1:c] < full[i, :c - 1])
+        assert np.array_equal(part[i, :min(p, c)], full[i, :min(p, c)]), i
+        assert np.array_equal(np.sort(part[i, :c]), np.sort(full[i, :c])), i
+        assert np.array_equal((~(full[i, :c] & np.uint64(0xFFFFFFFF)).astype(np.uint32)), host[0][i, :c])
+    index.close()
+
+
 def test_initial_thresholds_cut_the_result_exactly():
     """di_search_dev with caller-proven lower bounds returns exactly the keys at or above them."""
     torch = pytest.importorskip("torch")

@@ -51,6 +51,7 @@ def test_pull_merge_equals_single_index(k, k_in):
     counts = [torch.zeros(Q, dtype=torch.int32, device=dev) for _ in bounds]
     for (lo, hi), r, c in zip(bounds, rows, counts):
         shard = engine.DeviceIndex.from_csr(toff, docs, vals, doc_lo=lo, doc_hi=hi, tile_docs=1024)
+        shard.set_sorted_prefix(k_in if k_in < k else 1)                    # what a shard owes the merge, no more
         shard.search_device(d_flat, d_offs, Q, max(len(q) for q in queries), k, r, c, st)
     row_ptrs = torch.tensor([r.data_ptr() for r in rows], dtype=torch.int64, device=dev)
     cnt_ptrs = torch.tensor([c.data_ptr() for c in counts], dtype=torch.int64, device=dev)
