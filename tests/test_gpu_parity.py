@@ -495,7 +495,7 @@ def test_sorted_prefix_rows_hold_the_same_top_k(k, p):
     assert np.array_equal(c_full, c_part)
     for i in range(n):
         c = int(c_full[i])
-        assert np.all(full[i, 1:c] < full[i, :c - 1])
+        assert c < 2 or np.all(full[i, 1:c] < full[i, :c - 1])
         assert np.array_equal(part[i, :min(p, c)], full[i, :min(p, c)]), i
         assert np.array_equal(np.sort(part[i, :c]), np.sort(full[i, :c])), i
         assert np.array_equal((~(full[i, :c] & np.uint64(0xFFFFFFFF)).astype(np.uint32)), host[0][i, :c])

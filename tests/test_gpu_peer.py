@@ -126,7 +126,7 @@ shard = engine.DeviceIndex.from_csr(x['toff'], x['docs'], x['vals'], doc_lo=lo, 
 searcher = ShardedSearcher.for_device_index(shard, dev)
 assert searcher.peer_exchange_available()
 ok = True
-for it, (nq, k) in enumerate([(200, 100), (200, 100), (200, 100), (333, 1000), (333, 1000), (50, 7)]):
+for it, (nq, k) in enumerate([(200, 100), (200, 100), (1200, 300), (1200, 300), (333, 1000), (333, 1000), (50, 7)]):   # 1200 > resident CTAs: one lane, prefix-sorted rows
     queries = syn.make_queries(nq, vocab_size=1500, seed=100 + it)
     queries[0] = []
     searcher.rows_per_shard = (lambda kk: max(1, kk // 3)) if it %% 2 == 0 else None     # short rows force second passes
