@@ -24,6 +24,7 @@ of 1+Poisson(5) distinct Zipf terms — generated on the GPU with torch (plumbin
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -308,9 +309,10 @@ def run_b200(args):
         for q0, q1 in batches:
             if world == 1:      # H2D + kernels + D2H inside the C-ABI call
                 index.search_flat(h_flat, h_offs[q0:q1 + 1], k, h_docs[q0:q1], h_scores[q0:q1], h_counts[q0:q1])
-            else:               # every rank: queries H2D, search + exchange, its own slice of the results D2H
-                d_flat.copy_(h_flat, non_blocking=True)
-                d_offs.copy_(h_offs, non_blocking=True)
+            else:               # every rank: this batch's queries H2D, search + exchange, its own slice of the results D2H
+                t0, t1 = int(h_offs[q0]), int(h_offs[q1])
+                d_flat[t0:t1].copy_(h_flat[t0:t1], non_blocking=True)
+                d_offs[q0:q1 + 1].copy_(h_offs[q0:q1 + 1], non_blocking=True)
                 (r0, r1), m_keys, m_counts = search_batch(q0, q1)
                 n = r1 - r0
                 if n:
@@ -331,7 +333,8 @@ def run_b200(args):
     index.timings()                          # the library accumulates until read: drop the warm-up records
     # ---- timed: device-resident
     score_ms, final_ms, step_ms = [], [], []
-    with ClockSampler(local) as clocks:
+    # (rank 0 samples the clocks: eight ranks forking nvidia-smi ten times a second starve the host threads that drive the GPUs)
+    with (ClockSampler(local) if rank == 0 else contextlib.nullcontext()) as clocks:
         barrier()
         for _ in range(args.steps):
             flush.fill_(1)                      # L2 flush between iterations (outside the event pair)

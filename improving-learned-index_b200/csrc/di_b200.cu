@@ -981,24 +981,36 @@ extern "C" int di_merge_pull_dev(const uint64_t *const *d_rows, const uint32_t *
     if (n_shards > kMaxPeerShards) return set_error(DI_ERR_ARG, "at most %u shards, got %u", kMaxPeerShards, n_shards);
     if (top_k == 0 || top_k > 65536) return set_error(DI_ERR_ARG, "top_k must be in [1, 65536], got %u", top_k);
     if (k_in == 0 || row_stride == 0) return set_error(DI_ERR_ARG, "k_in and row_stride must be positive");
+    const uint32_t lim1 = std::min(k_in, row_stride);
+    const uint32_t smem1 = pow2_ceil((uint32_t)std::min<uint64_t>((uint64_t)n_shards * lim1 + pow2_ceil(top_k), 1u << 20));
     // the second pass of a query holds every shard's full row in shared memory
-    const uint64_t worst = (uint64_t)n_shards * std::min(row_stride, top_k) + pow2_ceil(top_k);
-    const uint32_t smem_keys = pow2_ceil((uint32_t)std::min<uint64_t>(worst, 1u << 20));
+    const uint32_t smem2 = pow2_ceil((uint32_t)std::min<uint64_t>((uint64_t)n_shards * std::min(row_stride, top_k) + pow2_ceil(top_k), 1u << 20));
     int dev = 0, smem_max = 0;
     DI_CUDA(cudaGetDevice(&dev));
     DI_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if (row_stride > top_k || (uint64_t)smem_keys * 8 + 4096 > (uint64_t)smem_max)
+    if (row_stride > top_k || (uint64_t)smem2 * 8 + 4096 > (uint64_t)smem_max)
         return set_error(DI_ERR_ARG, "%u shards x rows of %u keys do not fit the merge kernel's shared memory; "
                          "gather the rows and use di_merge_topk_dev", n_shards, row_stride);
     static std::atomic<uint64_t> attr_done{0};
     const uint64_t bit = 1ull << (dev & 63);
     if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-        DI_CUDA(cudaFuncSetAttribute(merge_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 4096));
+        DI_CUDA(cudaFuncSetAttribute(merge_pull_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 4096));
+        DI_CUDA(cudaFuncSetAttribute(merge_pull_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 4096));
         attr_done.fetch_or(bit, std::memory_order_release);
     }
-    merge_pull_kernel<<<n_queries, kMergeThreads, (size_t)smem_keys * 8, (cudaStream_t)stream>>>(
-        d_rows, d_counts, n_shards, q_first, row_stride, k_in, top_k, smem_keys, d_keys_out, d_counts_out, d_n_second_pass);
+    cudaStream_t st = (cudaStream_t)stream;
+    StreamBuf redo(st);
+    DI_TRY(redo.alloc((size_t)n_queries * 4));
+    merge_pull_kernel<false><<<n_queries, kMergeThreads, (size_t)smem1 * 8, st>>>(
+        d_rows, d_counts, n_shards, q_first, row_stride, k_in, top_k, smem1, d_keys_out, d_counts_out, redo.as<uint32_t>(),
+        d_n_second_pass);
     DI_KERNEL_CHECK();
+    if (lim1 < row_stride) {
+        merge_pull_kernel<true><<<n_queries, kMergeThreads, (size_t)smem2 * 8, st>>>(
+            d_rows, d_counts, n_shards, q_first, row_stride, k_in, top_k, smem2, d_keys_out, d_counts_out, redo.as<uint32_t>(),
+            d_n_second_pass);
+        DI_KERNEL_CHECK();
+    }
     return DI_OK;
 }
 

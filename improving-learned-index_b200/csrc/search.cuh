@@ -163,60 +163,69 @@ __global__ void merge_check_kernel(const uint64_t *__restrict__ keys_in, const u
 //   3. PROVE the result: a shard that holds more than k_in keys hides only keys below its k_in-th, so the merge is
 //      exact iff that key <= the merged k-th;
 //   4. a query that fails the proof pulls the full rows (they are already there, nothing is searched twice) and
-//      selects again — inside the same CTA: no host round trip, no second launch, no compaction of query ids.
+//      selects again — in a second launch of the same shape in which the CTAs of proven queries leave at once: no host
+//      round trip, no compaction of query ids, and the first pass keeps a small shared-memory footprint (several CTAs
+//      per SM) instead of one sized for the rare full-row case.
 constexpr uint32_t kMaxPeerShards = 64;
 constexpr int kMergeThreads = 256;
 
+// SECOND = false: first pass over every owned query with rows cut at k_in columns (small shared memory: several CTAs per
+// SM); writes the result and redo[i] = 1 for a query whose proof failed. SECOND = true: the same launch shape, CTAs of
+// proven queries leave at once, the others pull the full rows (shared memory sized for n_shards full rows).
+template <bool SECOND>
 __global__ void __launch_bounds__(kMergeThreads) merge_pull_kernel(const uint64_t *const *__restrict__ rows,
                                                                  const uint32_t *const *__restrict__ counts,
                                                                  uint32_t n_shards, uint32_t q_first, uint32_t row_stride,
                                                                  uint32_t k_in, uint32_t k, uint32_t smem_keys,
                                                                  uint64_t *__restrict__ out_keys,
-                                                                 uint32_t *__restrict__ out_counts,
+                                                                 uint32_t *__restrict__ out_counts, uint32_t *__restrict__ redo,
                                                                  uint32_t *__restrict__ n_second_pass)
 {
-    extern __shared__ uint64_t s_keys[];  // smem_keys entries >= n_shards * min(row_stride, k)
+    extern __shared__ uint64_t s_keys[];  // smem_keys entries
     __shared__ __align__(16) uint32_t s_hist[kSelectSmemWords];
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tmp[2];
     __shared__ uint32_t s_cnt[kMaxPeerShards], s_pref[kMaxPeerShards + 1], s_bad;
     __shared__ const uint64_t *s_row[kMaxPeerShards];
     const uint32_t i = blockIdx.x, q = q_first + i;
+    if (SECOND && !redo[i]) return;
+    const uint32_t lim = SECOND ? row_stride : (k_in < row_stride ? k_in : row_stride);
     if (threadIdx.x < n_shards) {  // one remote 4-byte read per shard, all in flight together
         const uint32_t c = counts[threadIdx.x][q];
         s_cnt[threadIdx.x] = c < row_stride ? c : row_stride;
         s_row[threadIdx.x] = rows[threadIdx.x] + (uint64_t)q * row_stride;
     }
-    uint64_t *out = out_keys + (uint64_t)i * k;
-    uint32_t n_out = 0;
-    for (uint32_t lim = k_in < row_stride ? k_in : row_stride;; lim = row_stride) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t run = 0;
-            for (uint32_t s = 0; s < n_shards; ++s) {
-                s_pref[s] = run;
-                run += s_cnt[s] < lim ? s_cnt[s] : lim;
-            }
-            s_pref[n_shards] = run;
-            s_bad = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t s = 0; s < n_shards; ++s) {
+            s_pref[s] = run;
+            run += s_cnt[s] < lim ? s_cnt[s] : lim;
         }
-        __syncthreads();
-        const uint32_t total = s_pref[n_shards];
-        uint32_t s = 0;
-        for (uint32_t j = threadIdx.x; j < total; j += kMergeThreads) {  // flattened over the shards: loads from different peers overlap
-            while (j >= s_pref[s + 1]) ++s;
-            s_keys[j] = s_row[s][j - s_pref[s]];
-        }
-        __syncthreads();
-        uint64_t kth;
-        n_out = block_topk_sorted_smem(s_keys, total, k, smem_keys, out, s_hist, s_scan, s_tmp, &kth);
-        if (lim == row_stride) break;  // full rows: nothing is hidden
-        if (threadIdx.x < n_shards && s_cnt[threadIdx.x] > lim && s_row[threadIdx.x][lim - 1] > kth) s_bad = 1;
-        __syncthreads();
-        if (!s_bad) break;
-        if (threadIdx.x == 0 && n_second_pass) atomicAdd(n_second_pass, 1u);
+        s_pref[n_shards] = run;
+        s_bad = 0;
     }
+    __syncthreads();
+    const uint32_t total = s_pref[n_shards];
+    uint32_t s = 0;
+    for (uint32_t j = threadIdx.x; j < total; j += kMergeThreads) {  // flattened over the shards: loads from different peers overlap
+        while (j >= s_pref[s + 1]) ++s;
+        s_keys[j] = s_row[s][j - s_pref[s]];
+    }
+    __syncthreads();
+    uint64_t kth;
+    const uint32_t n_out = block_topk_sorted_smem(s_keys, total, k, smem_keys, out_keys + (uint64_t)i * k, s_hist, s_scan, s_tmp, &kth);
     if (threadIdx.x == 0) out_counts[i] = n_out;
+    if (SECOND || lim == row_stride) {  // full rows: nothing is hidden
+        if (!SECOND && threadIdx.x == 0) redo[i] = 0;
+        return;
+    }
+    if (threadIdx.x < n_shards && s_cnt[threadIdx.x] > lim && s_row[threadIdx.x][lim - 1] > kth) s_bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        redo[i] = s_bad;
+        if (s_bad && n_second_pass) atomicAdd(n_second_pass, 1u);
+    }
 }
 
 // Cross-GPU barrier on the launching stream, without a collective library: flags[r] points at rank r's flag array

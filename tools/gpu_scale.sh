@@ -16,11 +16,10 @@ run() { # n, extra args, tag
 }
 {
 timeout 600 python -m pytest tests/test_gpu_peer.py -m gpu -x -q 2>&1 | tail -2
-echo -n "N=1: "; run 1 "--no-file-legs --cpu-sample 32" n1
-for n in 2 4 8; do echo -n "N=$n: "; run $n "--verify-sharded" n$n; done
+echo -n "N=2: "; run 2 "" n2
+for n in 4 8; do echo -n "N=$n: "; run $n "--verify-sharded" n$n; done
 echo -n "N=8 nccl fallback: "; DI_B200_NO_PEER=1 run 8 "" n8_nccl
 echo -n "N=8 c4: "; run 8 "--workload c4 --steps 3" c4_n8
-echo -n "N=1 c4: "; run 1 "--workload c4 --steps 3 --cpu-sample 32" c4_n1
 for n in 2 4 8; do
   port=$((port+1))
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port tools/sharded_timeline.py 2>>$O/scale_$TAG.err | tee $O/timeline_${TAG}_n$n.txt
