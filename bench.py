@@ -276,7 +276,9 @@ def run_b200(args):
     d_flat, d_offs = h_flat.to(dev), h_offs.to(dev)
     df = index.term_df(flat)
     local_postings = int(df.sum())
-    searcher = ShardedSearcher.for_device_index(index, dev)      # local top-k -> NCCL all-gather -> K5 merge
+    searcher = ShardedSearcher.for_device_index(index, dev)      # local rows -> stream barrier -> fused pull-merge
+    if world > 1 and not args.local_seeds:
+        searcher.share_seeds(index)           # one all-reduce at build time: every shard seeds from the whole collection
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     B = args.batch or Q                       # queries per search call (configs[3] uses batches of 4096)
@@ -427,6 +429,7 @@ def run_b200(args):
             "build": build_info,
             "postings_per_query": round(total_postings / Q),
             "build_parity": build_parity,
+            "shared_seeds": bool(world > 1 and not args.local_seeds),
             "exchange": ("fused peer-memory pull (CUDA IPC + stream barrier + di_merge_pull_dev), queries partitioned over ranks"
                          if fused else ("NCCL all-gather + K5" if world > 1 else None)),
             "second_pass_queries_rank0_last_step": int(searcher.round2_queries),
@@ -690,6 +693,7 @@ def main():
     ap.add_argument("--impact-skew", type=float, default=0.0,
                     help="S > 0: impacts of document d are divided by 1 + S*d/N — a quality-ordered collection, the case "
                          "exact tile skipping (--tile-bounds) is for")
+    ap.add_argument("--local-seeds", action="store_true", help="N > 1: keep per-shard seed tables (A/B of share_seeds)")
     ap.add_argument("--tile-bounds", action="store_true", help="build the index with DI_INDEX_TILE_BOUNDS (exact tile skipping)")
     ap.add_argument("--tile-docs", type=int, default=0)
     ap.add_argument("--dense-ratio", type=int, default=0)

@@ -79,6 +79,8 @@ SIGNATURES = {
                                              ctypes.POINTER(IndexParams), ctypes.POINTER(_vp)]),
     "di_index_destroy": (None, [_vp]),
     "di_index_get_info": (ctypes.c_int, [_vp, ctypes.POINTER(IndexInfo)]),
+    "di_index_export_seed_hist_dev": (ctypes.c_int, [_vp, _vp, _vp]),
+    "di_index_import_seed_hist_dev": (ctypes.c_int, [_vp, _vp, _vp]),
     "di_index_set_sorted_prefix": (ctypes.c_int, [_vp, ctypes.c_uint32]),
     "di_index_term_df": (ctypes.c_int, [_vp, _vp, ctypes.c_uint64, _vp]),
     "di_search": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp]),

@@ -308,6 +308,80 @@ __global__ void seed_theta_kernel(const uint32_t *__restrict__ q_terms, const ui
     }
 }
 
+// ---- seeds of a SHARDED collection ------------------------------------------------------------------------------------
+// The seed of a query is a lower bound of the k-th best score over the documents the tables count. A shard that only knows
+// its own postings can only bound its OWN k-th score; with the tables of all shards added up every shard starts from a
+// bound of the GLOBAL k-th score and never emits what the cross-shard merge would throw away (measured at 8 shards:
+// score kernel 4.06 -> 3.86 ms, finalize 0.23 -> 0.20 ms). export: this shard's impact histogram of EVERY term as a dense
+// [n_terms][256] table (read back from the tiled payload; the caller sums the tables of all shards, e.g. with one
+// all-reduce); import: new seed tables from such a sum.
+__global__ void __launch_bounds__(256) seed_export_kernel(const SegDesc *__restrict__ desc, const uint8_t *__restrict__ payload,
+                                                          uint64_t n_segs, uint32_t n_terms, uint32_t tile_docs,
+                                                          uint32_t *__restrict__ hist /* [n_terms][256] */)
+{
+    __shared__ uint32_t s_h[8][256];
+    const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+    const uint4 *payload4 = reinterpret_cast<const uint4 *>(payload);
+    for (uint64_t seg = (uint64_t)blockIdx.x * 8 + w; seg < n_segs; seg += (uint64_t)gridDim.x * 8) {
+        const SegDesc d = desc[seg];
+        if (d.n_flag == 0) continue;
+        uint32_t *h = hist + (size_t)(seg % n_terms) * 256;
+        if (d.n_flag & kDenseFlag) {  // one byte per document, 0 = absent: count in shared memory, flush the bins in use
+            for (int i = lane; i < 256; i += 32) s_h[w][i] = 0;
+            __syncwarp();
+            for (uint32_t u = lane; u < (tile_docs >> kDenseUnitShift); u += 32) {
+                const uint4 v = payload4[(size_t)d.off16 + u];
+                const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t b = (x[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    if (b) atomicAdd(&s_h[w][b], 1u);
+                }
+            }
+            __syncwarp();
+            for (int i = lane; i < 256; i += 32)
+                if (s_h[w][i]) atomicAdd(&h[i], s_h[w][i]);
+            __syncwarp();
+        } else {  // u32 postings, impact in bits 16..23; padding words carry impact 0
+            const uint32_t total = d.n_flag & 0xFFFFu;
+            for (uint32_t u = lane; u < total; u += 32) {
+                const uint4 v = payload4[(size_t)d.off16 + u];
+                const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t b = (x[i] >> 16) & 0xFFu;
+                    if (b) atomicAdd(&h[b], 1u);
+                }
+            }
+        }
+    }
+}
+
+// one warp per term: terms with at least kSeedMinDf postings in the summed histogram get a slot and their 256 bins
+__global__ void seed_import_kernel(const uint32_t *__restrict__ hist, uint32_t n_terms, uint32_t *__restrict__ slot_of_term,
+                                   uint32_t *__restrict__ counter, uint32_t *__restrict__ cum)
+{
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (t >= n_terms) return;
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = hist[(size_t)t * 256 + lane * 8 + j];
+        sum += v[j];
+    }
+    unsigned long long total = sum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    uint32_t slot = kNoSeedSlot;
+    if (total >= kSeedMinDf) {
+        if (lane == 0) slot = atomicAdd(counter, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cum[(size_t)slot * 256 + lane * 8 + j] = v[j];
+    }
+    if (lane == 0) slot_of_term[t] = slot;
+}
+
 __global__ void tile_keys_kernel(const uint64_t *__restrict__ term_offsets, uint32_t n_terms,
                                  const uint32_t *__restrict__ docids, const uint8_t *__restrict__ impacts,
                                  uint64_t n_post, const unsigned long long *__restrict__ first_zero,

@@ -24,6 +24,7 @@ struct di_index {
     bool has_dup_postings = false;  // some posting list names a document twice: no seeds, 32-bit accumulators
     uint32_t last_lanes = 0, last_acc32 = 0;
     uint32_t sorted_prefix = 0;   // di_index_set_sorted_prefix: 0 = result rows fully sorted
+    bool global_seeds = false;    // the seed tables count the postings of a larger collection (di_index_import_seed_hist_dev)
     uint64_t n_postings = 0, payload_bytes = 0, table_bytes = 0;
     uint64_t n_dense_segments = 0, n_sparse_segments = 0, n_dense_postings = 0;
     SegDesc *d_desc = nullptr;
@@ -630,6 +631,53 @@ extern "C" int di_index_get_info(const di_index_t *ix, di_index_info *info)
     info->n_tiles = ix->n_tiles;
     info->tile_docs = ix->tile_docs;
     info->max_docid_plus1 = ix->max_docid_plus1;
+    return DI_OK;
+}
+
+extern "C" int di_index_export_seed_hist_dev(const di_index_t *ix, uint32_t *d_hist, void *stream)
+{
+    if (!ix || !d_hist) return set_error(DI_ERR_ARG, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DI_CUDA(cudaSetDevice(ix->device));
+    DI_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)ix->n_terms * 256 * 4, st));
+    const uint64_t n_segs = (uint64_t)ix->n_tiles * ix->n_terms;
+    if (n_segs) {
+        seed_export_kernel<<<grid_for(n_segs, 8, 148 * 32), 256, 0, st>>>(ix->d_desc, ix->d_payload, n_segs, ix->n_terms,
+                                                                         ix->tile_docs, d_hist);
+        DI_KERNEL_CHECK();
+    }
+    return DI_OK;
+}
+
+extern "C" int di_index_import_seed_hist_dev(di_index_t *ix, const uint32_t *d_hist, void *stream)
+{
+    if (!ix || !d_hist) return set_error(DI_ERR_ARG, "NULL argument");
+    if (ix->has_dup_postings) return DI_OK;  // k postings are not k documents here: such an index never seeds
+    cudaStream_t st = (cudaStream_t)stream;
+    DI_CUDA(cudaSetDevice(ix->device));
+    DI_CUDA(cudaStreamSynchronize(ix->stream));  // no search of this index may still read the old tables
+    if (ix->d_seed_cum) cudaFree(ix->d_seed_cum);
+    if (ix->d_seed_slot) cudaFree(ix->d_seed_slot);
+    ix->d_seed_cum = ix->d_seed_slot = nullptr;
+    const uint32_t V = ix->n_terms;
+    if (V == 0 || (ix->flags & DI_INDEX_NO_SEEDS)) return DI_OK;
+    DevBuf d_cnt;
+    DI_TRY(d_cnt.alloc(4));
+    DI_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4, st));
+    DI_CUDA(cudaMalloc(&ix->d_seed_slot, (size_t)V * 4));
+    DI_CUDA(cudaMalloc(&ix->d_seed_cum, (size_t)V * 256 * 4));
+    seed_import_kernel<<<(unsigned)(((uint64_t)V * 32 + 255) / 256), 256, 0, st>>>(d_hist, V, ix->d_seed_slot, d_cnt.as<uint32_t>(),
+                                                                                 ix->d_seed_cum);
+    DI_KERNEL_CHECK();
+    uint32_t n_slots = 0;
+    DI_CUDA(cudaMemcpyAsync(&n_slots, d_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+    DI_CUDA(cudaStreamSynchronize(st));
+    if (n_slots) {
+        seed_cum_kernel<<<(unsigned)(((uint64_t)n_slots * 32 + 255) / 256), 256, 0, st>>>(ix->d_seed_cum, n_slots);
+        DI_KERNEL_CHECK();
+    }
+    DI_CUDA(cudaStreamSynchronize(st));
+    ix->global_seeds = true;
     return DI_OK;
 }
 

@@ -222,6 +222,15 @@ class DeviceIndex:
         N.check(N.lib().di_search_dev(self._h, N.ptr(d_q_terms), N.ptr(d_q_offsets), n_queries, max_query_len, top_k,
                                       N.ptr(d_theta_init), N.ptr(d_out_keys), N.ptr(d_out_counts), stream))
 
+    def export_seed_hist(self, d_hist, stream: int = 0):
+        """This shard's impact histogram of every term into d_hist [n_terms, 256] (uint32 on the device)."""
+        N.check(N.lib().di_index_export_seed_hist_dev(self._h, N.ptr(d_hist), stream))
+
+    def import_seed_hist(self, d_hist, stream: int = 0):
+        """New seed tables from a histogram summed over all shards: searches then start from a bound of the GLOBAL k-th
+        score and return only what can be in the top-k of the whole collection (rows for the cross-shard merge)."""
+        N.check(N.lib().di_index_import_seed_hist_dev(self._h, N.ptr(d_hist), stream))
+
     def set_sorted_prefix(self, p: int):
         """Row order of search_device results from now on: 0 = fully sorted; p > 0 = [the p best keys, sorted | the rest
         of the top-k in any order] — what a shard owes the cross-shard merge (di_index_set_sorted_prefix)."""

@@ -164,6 +164,20 @@ class ShardedSearcher:
                                      torch.cuda.current_stream().cuda_stream, k_in=k_in, d_incomplete=incomplete)
         return cls(local_search, merge, device, group, set_row_order=index.set_sorted_prefix)
 
+    def share_seeds(self, index: "engine.DeviceIndex"):
+        """Collective, once after the shards are built: adds up the per-term impact histograms of all shards (one
+        all-reduce of n_terms x 256 counters) and gives every shard seed tables of the WHOLE collection, so that its
+        searches start from a bound of the global k-th score instead of its own."""
+        if self.world == 1:
+            return
+        torch = self.torch
+        n_terms = index.info()["n_terms"]
+        hist = torch.zeros((n_terms, 256), dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        index.export_seed_hist(hist, stream)
+        self.dist.all_reduce(hist, op=self.dist.ReduceOp.SUM, group=self.group)
+        index.import_seed_hist(hist, stream)
+
     def _buf(self, name, shape, dtype):
         key = (name, tuple(shape))
         if key not in self._buffers:

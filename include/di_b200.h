@@ -166,6 +166,14 @@ int di_index_create_files(const uint8_t *dat, uint64_t dat_bytes, const uint64_t
                           const di_index_params *params, di_index_t **out);
 void di_index_destroy(di_index_t *index);
 int di_index_get_info(const di_index_t *index, di_index_info *info);
+/* Seeds for a SHARD of a larger collection. A query's seed is a proven lower bound of its k-th best score over the documents
+ * the seed tables count; with the tables of all shards added up, every shard starts from a bound of the GLOBAL k-th score and
+ * does not emit what the cross-shard merge would discard. export: this shard's impact histogram of every term, dense
+ * d_hist[n_terms][256] (u32, device). The caller adds the tables of all shards (e.g. one all-reduce) and imports the sum into
+ * every shard. AFTER an import a search of this index returns only keys that can be in the top_k of the WHOLE collection: its
+ * rows are meant for the merge, not a top_k of the shard on its own. (No-op for an index with duplicate postings.) */
+int di_index_export_seed_hist_dev(const di_index_t *index, uint32_t *d_hist, void *stream);
+int di_index_import_seed_hist_dev(di_index_t *index, const uint32_t *d_hist, void *stream);
 /* Row order of di_search_dev's result (sticky; 0 = default: rows fully sorted). With sorted_prefix = p > 0 a row is
  * [its p best keys, sorted | the rest of its top_k keys in any order] — all a SHARD has to deliver to the cross-shard merge,
  * which reads the first k_in columns and, rarely, re-selects from the whole row; saves most of the per-row sort.

@@ -502,6 +502,51 @@ def test_sorted_prefix_rows_hold_the_same_top_k(k, p):
     index.close()
 
 
+def test_global_seed_tables_make_shards_emit_less_and_merge_exactly():
+    """di_index_export_seed_hist_dev / import: with the impact histograms of all shards added up, a shard's seeds bound the
+    GLOBAL k-th score: its rows shrink to what can be in the global top-k, and the merged result is unchanged."""
+    torch = pytest.importorskip("torch")
+    n_docs, V, k = 120_000, 300, 100
+    x = quantized_csr(n_docs, V, 40, 91)
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    queries = syn.make_queries(1200, vocab_size=V, seed=92)
+    flat, offs = engine.flatten_queries(queries)
+    d_flat = torch.from_numpy(flat.astype(np.int64)).to(dev).to(torch.int32)
+    d_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    Q, max_len = len(queries), max(len(q) for q in queries)
+    want = oracle.score_topk_csr(x["toff"], x["docs"], x["vals"], n_docs, queries, k)
+    bounds = [(0, 30_000), (30_000, 60_000), (60_000, 90_000), (90_000, n_docs)]
+    shards = [engine.DeviceIndex.from_csr(x["toff"], x["docs"], x["vals"], doc_lo=lo, doc_hi=hi, tile_docs=4096) for lo, hi in bounds]
+
+    def run():
+        keys = torch.zeros((len(shards), Q, k), dtype=torch.int64, device=dev)
+        counts = torch.zeros((len(shards), Q), dtype=torch.int32, device=dev)
+        for s, shard in enumerate(shards):
+            shard.search_device(d_flat, d_offs, Q, max_len, k, keys[s], counts[s], st)
+        out_keys = torch.zeros((Q, k), dtype=torch.int64, device=dev)
+        out_counts = torch.zeros(Q, dtype=torch.int32, device=dev)
+        engine.merge_topk_device(keys, counts, len(shards), Q, k, out_keys, out_counts, st)
+        torch.cuda.synchronize()
+        kk = out_keys.cpu().numpy().view(np.uint64)
+        return ((~(kk & np.uint64(0xFFFFFFFF)).astype(np.uint32)), (kk >> np.uint64(32)).astype(np.int32),
+                out_counts.cpu().numpy().view(np.uint32)), int(counts.sum())
+    got, emitted_local = run()
+    assert_same_results(got, want, "local seeds")
+    total = torch.zeros((V, 256), dtype=torch.int32, device=dev)
+    for shard in shards:
+        h = torch.zeros_like(total)
+        shard.export_seed_hist(h, st)
+        total += h
+    torch.cuda.synchronize()
+    assert int(total.sum()) == x["docs"].size and int(total[:, 0].sum()) == 0
+    for shard in shards:
+        shard.import_seed_hist(total, st)
+    got, emitted_global = run()
+    assert_same_results(got, want, "global seeds")
+    assert emitted_global < emitted_local, (emitted_global, emitted_local)
+
+
 def test_initial_thresholds_cut_the_result_exactly():
     """di_search_dev with caller-proven lower bounds returns exactly the keys at or above them."""
     torch = pytest.importorskip("torch")

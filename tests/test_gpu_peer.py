@@ -34,8 +34,9 @@ def _clustered_collection():
     return toff, docs, vals, queries
 
 
+@pytest.mark.parametrize("shared_seeds", [False, True])
 @pytest.mark.parametrize("k,k_in", [(300, 120), (300, 300), (1000, 221), (10, 4)])
-def test_pull_merge_equals_single_index(k, k_in):
+def test_pull_merge_equals_single_index(k, k_in, shared_seeds):
     torch = pytest.importorskip("torch")
     toff, docs, vals, queries = _clustered_collection()
     full = engine.DeviceIndex.from_csr(toff, docs, vals, tile_docs=1024)
@@ -49,8 +50,21 @@ def test_pull_merge_equals_single_index(k, k_in):
     Q, G = len(queries), len(bounds)
     rows = [torch.zeros((Q, k), dtype=torch.int64, device=dev) for _ in bounds]
     counts = [torch.zeros(Q, dtype=torch.int32, device=dev) for _ in bounds]
-    for (lo, hi), r, c in zip(bounds, rows, counts):
-        shard = engine.DeviceIndex.from_csr(toff, docs, vals, doc_lo=lo, doc_hi=hi, tile_docs=1024)
+    shards = [engine.DeviceIndex.from_csr(toff, docs, vals, doc_lo=lo, doc_hi=hi, tile_docs=1024) for lo, hi in bounds]
+    if shared_seeds:     # every shard gets the seed tables of the whole collection (sum of the shards' impact histograms)
+        total = torch.zeros((toff.size - 1, 256), dtype=torch.int32, device=dev)
+        for shard in shards:
+            h = torch.zeros_like(total)
+            shard.export_seed_hist(h, st)
+            total += h
+        torch.cuda.synchronize()
+        whole = torch.zeros_like(total)
+        full.export_seed_hist(whole, st)
+        torch.cuda.synchronize()
+        assert torch.equal(total, whole)                                    # shards partition the postings
+        for shard in shards:
+            shard.import_seed_hist(total, st)
+    for shard, r, c in zip(shards, rows, counts):
         shard.set_sorted_prefix(k_in if k_in < k else 1)                    # what a shard owes the merge, no more
         shard.search_device(d_flat, d_offs, Q, max(len(q) for q in queries), k, r, c, st)
     row_ptrs = torch.tensor([r.data_ptr() for r in rows], dtype=torch.int64, device=dev)
@@ -125,6 +139,7 @@ lo, hi = shard_range(30000, world, rank)
 shard = engine.DeviceIndex.from_csr(x['toff'], x['docs'], x['vals'], doc_lo=lo, doc_hi=hi, tile_docs=1024)
 searcher = ShardedSearcher.for_device_index(shard, dev)
 assert searcher.peer_exchange_available()
+searcher.share_seeds(shard)           # collective: seed tables of the whole collection on every shard
 ok = True
 for it, (nq, k) in enumerate([(200, 100), (200, 100), (1200, 300), (1200, 300), (333, 1000), (333, 1000), (50, 7)]):   # 1200 > resident CTAs: one lane, prefix-sorted rows
     queries = syn.make_queries(nq, vocab_size=1500, seed=100 + it)

@@ -58,6 +58,25 @@ def main():
     kth = torch.where(counts == k, keys[:, k - 1], torch.zeros_like(keys[:, 0])).contiguous()
     index.set_sorted_prefix(shard_k(k, args.shards))
     b = timed(kth)
+    # (c) GLOBAL single-term seeds: the k-th highest impact of a term over the WHOLE collection (what all-reducing the shards'
+    # seed tables at build time would give every shard), from the full term-major inversion
+    del terms, imps, offs
+    t_all, v_all, o_all = bench.build_shard_arrays(0, N, N, V, 208, torch, dev, quantize_fn, 120)
+    P = t_all.numel()
+    toff = torch.empty(V + 1, dtype=torch.int64, device=dev)
+    docs = torch.empty(P, dtype=torch.int32, device=dev)
+    vals = torch.empty(P, dtype=torch.uint8, device=dev)
+    _native.check(L.di_invert_dev(t_all.data_ptr(), v_all.data_ptr(), o_all.data_ptr(), N, V, P, toff.data_ptr(), docs.data_ptr(),
+                                  vals.data_ptr(), None, st))
+    torch.cuda.synchronize()
+    del t_all, v_all, o_all, docs
+    df = toff[1:] - toff[:-1]
+    kth_impact = torch.where(df >= k, vals[(toff[:-1] + k - 1).clamp(max=P - 1)].to(torch.int64), torch.zeros_like(df))
+    seeds = torch.zeros(Q, dtype=torch.int64, device=dev)
+    for i, q in enumerate(queries):
+        seeds[i] = int(kth_impact[torch.tensor(q, device=dev)].max()) << 32
+    c = timed(seeds.contiguous())
+    print(f"  with GLOBAL single-term seeds (k-th highest impact of a term over all {N} documents): score kernel {c[0]:.3f} ms, finalize {c[1]:.3f}")
     print(f"shard 0 of {args.shards} ({hi - lo} docs, {index.info()['n_tiles']} tiles): score kernel {a[0]:.3f} ms with its own seeds, "
           f"{b[0]:.3f} ms when every query starts from its final k-th key (finalize {a[1]:.3f} / {b[1]:.3f})")
 
