@@ -1,5 +1,5 @@
 #!/bin/bash
-# Builds the diagnostic library variants used by tools/gpu_round.sh (git-ignored; they travel to the GPU box):
+# Builds the diagnostic library variants used by tools/gpu_prof.sh and tools/gpu_ab2.sh (git-ignored; they travel to the GPU box):
 #   variants/libdi_prof.so   -DDI_PROFILE_PHASES: per-tile, per-phase cycle counters ($DI_B200_PROF=file.csv)
 # Extra variants: tools/build_variants.sh NAME "-DDI_SCORE_THREADS=256 -DDI_SCORE_MIN_BLOCKS=3" ...
 set -eu
