@@ -69,6 +69,8 @@ class PeerExchange:
     library (cudaMalloc + CUDA IPC handle); torch.distributed only carries the 64-byte handles once."""
 
     def __init__(self, device, rank: int, world: int, q_cap: int, k: int, group=None):
+        """Collective. Raises RuntimeError ON EVERY RANK when any rank could not allocate, export or map the buffers
+        (no CUDA IPC / peer access on this box): the ranks agree on the outcome before anybody relies on it."""
         import ctypes
         import torch
         import torch.distributed as dist
@@ -76,32 +78,46 @@ class PeerExchange:
         self.N, self.torch = N, torch
         self.rank, self.world, self.q_cap, self.k = rank, world, q_cap, k
         self.calls = self.epoch = 0
+        self.own, self.opened = [], []
         L = N.lib()
         sizes = [q_cap * k * 8, q_cap * 4, q_cap * k * 8, q_cap * 4, max(world, 64) * 4]     # rows0 counts0 rows1 counts1 flags
-        self.own, handles = [], []
-        for nbytes in sizes:
-            ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-            N.check(L.di_shared_alloc(nbytes, ctypes.byref(ptr), h))
-            self.own.append(ptr.value)
-            handles.append(h.raw)
+        handles, error = [], None
+        try:
+            for nbytes in sizes:
+                ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+                N.check(L.di_shared_alloc(nbytes, ctypes.byref(ptr), h))
+                self.own.append(ptr.value)
+                handles.append(h.raw)
+        except Exception as e:       # keep going: the collectives below must be entered by every rank
+            error = e
         everyone = [None] * world
-        dist.all_gather_object(everyone, handles, group=group)
-        self.opened, table = [], []
-        for r in range(world):
-            if r == rank:
-                table.append(list(self.own))
-                continue
-            ptrs = []
-            for h in everyone[r]:
-                ptr = ctypes.c_void_p()
-                N.check(L.di_shared_open(h, ctypes.byref(ptr)))
-                ptrs.append(ptr.value)
-                self.opened.append(ptr.value)
-            table.append(ptrs)
+        dist.all_gather_object(everyone, None if error else handles, group=group)
+        table = []
+        if error is None and all(h is not None for h in everyone):
+            try:
+                for r in range(world):
+                    if r == rank:
+                        table.append(list(self.own))
+                        continue
+                    ptrs = []
+                    for h in everyone[r]:
+                        ptr = ctypes.c_void_p()
+                        N.check(L.di_shared_open(h, ctypes.byref(ptr)))
+                        ptrs.append(ptr.value)
+                        self.opened.append(ptr.value)
+                    table.append(ptrs)
+            except Exception as e:
+                error = e
+        elif error is None:
+            error = RuntimeError("a peer rank could not allocate its buffers")
+        ok = torch.tensor([0 if error else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also: nobody starts a barrier kernel before every rank has mapped the flags
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer-memory exchange unavailable ({error or 'failure on another rank'})")
         as_table = lambda j: torch.tensor([table[r][j] for r in range(world)], dtype=torch.int64, device=device)
         self.sets = [(self.own[0], self.own[1], as_table(0), as_table(1)), (self.own[2], self.own[3], as_table(2), as_table(3))]
         self.flag_table = as_table(4)
-        dist.barrier(group=group)               # nobody starts a barrier kernel before every rank has mapped the flags
 
     def next_set(self):
         s = self.sets[self.calls % 2]
@@ -149,6 +165,7 @@ class ShardedSearcher:
         self.round2_queries = 0          # how many queries of the last search needed their full rows gathered
         self.set_row_order = set_row_order   # optional: p -> "only the first p keys of a local row need to be sorted"
         self._peer = None                # PeerExchange of the fused path (CUDA, world > 1), created on first use
+        self._peer_ok = None             # None = not tried yet
         self._second = None
 
     @classmethod
@@ -211,7 +228,20 @@ class ShardedSearcher:
 
     # ---- fused exchange over peer memory (CUDA only) --------------------------------------------------
     def peer_exchange_available(self) -> bool:
-        return self.world > 1 and getattr(self.device, "type", "cpu") == "cuda" and os.environ.get("DI_B200_NO_PEER") != "1"
+        """Collective on first use (every rank must call it at the same point): tries to set the peer buffers up; when
+        that fails anywhere (no CUDA IPC / peer access), every rank falls back to the all-gather form for good."""
+        if self.world <= 1 or getattr(self.device, "type", "cpu") != "cuda" or os.environ.get("DI_B200_NO_PEER") == "1":
+            return False
+        if self._peer_ok is None:
+            try:
+                self._peer = PeerExchange(self.device, self.rank, self.world, 1024, 64, self.group)
+                self._second = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
+                self._peer_ok = True
+            except RuntimeError as e:
+                import warnings
+                warnings.warn(f"{e}; using the all-gather exchange")
+                self._peer, self._peer_ok = None, False
+        return self._peer_ok
 
     def search_partitioned(self, d_q_terms, d_q_offsets, n_queries: int, max_len: int, k: int):
         """Fused form: returns ((q_lo, q_hi), keys [q_hi - q_lo, k] int64, counts [q_hi - q_lo] int32) — the GLOBAL
