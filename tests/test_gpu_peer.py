@@ -162,7 +162,7 @@ for it, (nq, k) in enumerate([(200, 100), (200, 100), (1200, 300), (1200, 300), 
     for i in range(q_lo, q_hi):
         n = int(want[2][i])
         ok = ok and int(cc[i - q_lo]) == n and np.array_equal(dd[i - q_lo, :n], want[0][i, :n]) and np.array_equal(sc[i - q_lo, :n], want[1][i, :n])
-print('RANK', rank, 'OK' if ok else 'MISMATCH', flush=True)
+open(os.path.join(%r, 'rank%%d.%%s' %% (rank, 'ok' if ok else 'mismatch')), 'w').close()    # stdout of the ranks interleaves
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
@@ -176,11 +176,12 @@ def test_two_process_peer_exchange(tmp_path):
     if world < 2:
         pytest.skip("needs at least two GPUs (gpurun --gpus 2)")
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER % (REPO, REPO))
+    script.write_text(_WORKER % (REPO, REPO, str(tmp_path)))
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and r.stdout.count(" OK") == world, r.stdout[-3000:] + r.stderr[-3000:]
+    verdicts = sorted(f.name for f in tmp_path.glob("rank*.*"))
+    assert r.returncode == 0 and verdicts == [f"rank{i}.ok" for i in range(world)], (verdicts, r.stdout[-3000:] + r.stderr[-3000:])
