@@ -318,33 +318,14 @@ rs_onesweep_kernel(uint64_t *__restrict__ buf_a, uint64_t *__restrict__ buf_b, S
         st_relaxed_u32(cell, (blk == seg_block0 ? kLbPrefix : kLbAggregate) | (total + 1u));
         uint32_t excl = 0;
         if (blk != seg_block0) {
-            // Walk back over the predecessors kLbWindow cells at a time: the loads of a window are independent and in
-            // flight together (a one-cell-at-a-time walk over the ~300 blocks of a wave, one L2 round trip each, was
-            // the sort's critical path). Blocks before the segment's first one count as "prefix 0".
-            constexpr int kLbWindow = 8;
-            int64_t t = (int64_t)blk - 1;
-            uint32_t spins = 0;
-            for (bool done = false; !done;) {
-                uint32_t v[kLbWindow];
-#pragma unroll
-                for (int w = 0; w < kLbWindow; ++w)
-                    v[w] = t - w >= (int64_t)seg_block0 ? ld_relaxed_u32(lookback + (size_t)(t - w) * 256 + d) : (kLbPrefix | 1u);
-                int used = 0;
-#pragma unroll
-                for (int w = 0; w < kLbWindow; ++w) {
-                    if (!done && used == w) {
-                        if (v[w] != 0u) {
-                            excl += (v[w] & kLbValue) - 1u;
-                            done = (v[w] & kLbPrefix) != 0u;
-                            used = w + 1;
-                        }
-                    }
-                }
-                t -= used;
-                if (!done && used < kLbWindow) {  // ran into a cell that is not published yet
+            for (uint32_t t = blk - 1;; --t) {
+                uint32_t v, spins = 0;
+                while ((v = ld_relaxed_u32(lookback + (size_t)t * 256 + d)) == 0u) {
                     __nanosleep(32);
                     if (++spins > (1u << 24)) __trap();  // a block with a smaller ticket is always running: never expected
                 }
+                excl += (v & kLbValue) - 1u;
+                if (v & kLbPrefix) break;
             }
             // an inclusive prefix only fits the cell below 2^30 - 1; above that the cell stays an aggregate (successors
             // simply walk further back), which keeps the sort correct for any n < 2^32
