@@ -288,16 +288,22 @@ rs_onesweep_kernel(uint64_t *__restrict__ buf_a, uint64_t *__restrict__ buf_b, S
     for (int s = 0; s < kRsItems; ++s) {
         const bool valid = wbase + (uint64_t)s * 32 + lane < tile_hi;
         const unsigned digit = valid ? ((unsigned)(key[s] >> shift) & dmask) : 256u;
-        // lanes holding the same digit, from nine ballots (one per digit bit + validity): MATCH.ANY does this in one
-        // instruction but occupies the address-divergence unit for ~50 cycles per warp — it was the kernel's limiter
-        // (ADU pipe 73 % busy, profiles/r2_sort_ncu.txt)
-        unsigned peers = __ballot_sync(0xffffffffu, valid);
-        if (!valid) peers = ~peers;
+        // Lanes holding the same digit. MATCH.ANY answers in one instruction but occupies the address-divergence unit
+        // for ~50 cycles per warp (all sixteen steps on it: ADU 73 % busy, the limiter); nine ballots + masks answer on
+        // the integer pipe (all sixteen there: ALU 66 % busy, the limiter). The steps alternate, so both units share
+        // the work (profiles/r2_sort_ncu.txt).
+        unsigned peers;
+        if (s & 1) {
+            peers = __match_any_sync(0xffffffffu, digit);  // invalid lanes carry digit 256: a group of their own
+        } else {
+            peers = __ballot_sync(0xffffffffu, valid);
+            if (!valid) peers = ~peers;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const unsigned bit = (digit >> b) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? m : ~m;
+            for (int b = 0; b < 8; ++b) {
+                const unsigned bit = (digit >> b) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? m : ~m;
+            }
         }
         uint32_t before = 0;
         if (valid) before = warp_cnt[warp][digit];
