@@ -52,10 +52,16 @@ __device__ __forceinline__ uint64_t upper_bound_u64(const uint64_t *a, uint64_t 
     return lo;
 }
 
-__global__ void invert_keys_kernel(const uint32_t *__restrict__ term_ids, const uint8_t *__restrict__ impacts,
-                                   const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, uint32_t n_terms,
-                                   uint64_t *__restrict__ keys, uint32_t *__restrict__ status)
+// The sort's digit counts are taken here, while the key is in a register (the sort would otherwise read all keys once
+// more just to count them): sort_hist = [n_passes][256] counters of radix_sort_u64's bits [sort_lo, sort_hi).
+__global__ void __launch_bounds__(256) invert_keys_kernel(const uint32_t *__restrict__ term_ids, const uint8_t *__restrict__ impacts,
+                                                          const uint64_t *__restrict__ doc_offsets, uint64_t n_docs, uint32_t n_terms,
+                                                          uint64_t *__restrict__ keys, uint32_t *__restrict__ status,
+                                                          uint32_t *__restrict__ sort_hist, int sort_lo, int sort_hi, int n_passes)
 {
+    __shared__ uint32_t s_counts[4][256];
+    for (int i = threadIdx.x; i < n_passes * 256; i += blockDim.x) (&s_counts[0][0])[i] = 0;
+    __syncthreads();
     // one warp per document (lists are ~100 postings): the docid comes for free and the accesses stay
     // coalesced, instead of a 23-step binary search over doc_offsets per posting
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -68,9 +74,13 @@ __global__ void invert_keys_kernel(const uint32_t *__restrict__ term_ids, const 
                 t = n_terms;
                 if (status) *status = 1u;
             }
-            keys[i] = ((uint64_t)t << kInvTermShift) | ((uint64_t)(255u - impacts[i]) << 32) | (uint64_t)(uint32_t)doc;
+            const uint64_t key = ((uint64_t)t << kInvTermShift) | ((uint64_t)(255u - impacts[i]) << 32) | (uint64_t)(uint32_t)doc;
+            keys[i] = key;
+            rs_count_key(s_counts, key, sort_lo, sort_hi, n_passes);
         }
     }
+    __syncthreads();
+    rs_flush_counts(s_counts, n_passes, sort_hist);
 }
 
 __global__ void invert_extract_kernel(const uint64_t *__restrict__ ka, const uint64_t *__restrict__ kb,
@@ -129,12 +139,15 @@ inline int invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, cons
     RadixSortScratch ws(st);
     DI_TRY(ka.alloc(n_post * sizeof(uint64_t)));
     DI_TRY(kb.alloc(n_post * sizeof(uint64_t)));
-    invert_keys_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(d_term_ids, d_impacts, d_doc_offsets, n_docs, n_terms,
-                                                              ka.as<uint64_t>(), d_status);
-    DI_KERNEL_CHECK();
     int term_bits = 1;
     while ((1ull << term_bits) < (uint64_t)n_terms + 1) ++term_bits;  // the value n_terms marks unknown terms
-    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, 32, kInvTermShift + term_bits, nullptr, 1, ws, st));
+    const int sort_lo = 32, sort_hi = kInvTermShift + term_bits, n_passes = (sort_hi - sort_lo + 7) / 8;  // <= 4 passes (24 + 8 bits)
+    DI_TRY(rs_prepare_counts(ws, n_passes, st));
+    invert_keys_kernel<<<grid_for(n_post, 256, 148 * 8), 256, 0, st>>>(d_term_ids, d_impacts, d_doc_offsets, n_docs, n_terms,
+                                                                       ka.as<uint64_t>(), d_status, ws.hist.as<uint32_t>(), sort_lo,
+                                                                       sort_hi, n_passes);
+    DI_KERNEL_CHECK();
+    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, sort_lo, sort_hi, nullptr, 1, ws, st, /*precounted=*/true));
     invert_extract_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(ka.as<uint64_t>(), kb.as<uint64_t>(), ws.cur(), n_post,
                                                                  n_terms, d_term_offsets, d_out_docids, d_out_impacts);
     DI_KERNEL_CHECK();

@@ -386,8 +386,33 @@ struct RadixSortScratch {
 // input, `b` is a same-sized buffer; the result is rs_result(a, b, ws.cur()) — device-side state. d_seg_first_key:
 // nullptr = one segment, else [n_segs + 1] key boundaries (device). Fully asynchronous on `st`; `ws` must outlive
 // the kernels that read ws.cur().
+// precounted: the caller's key-building kernel has already added every key's digits into ws.hist (zeroed by
+// rs_prepare_counts below, one segment only) — the sort then does not read the keys an extra time to count them.
+inline int rs_prepare_counts(RadixSortScratch &ws, int n_passes, cudaStream_t st)
+{
+    DI_TRY(ws.hist.alloc((size_t)n_passes * 256 * sizeof(uint32_t)));
+    DI_CUDA(cudaMemsetAsync(ws.hist.p, 0, (size_t)n_passes * 256 * sizeof(uint32_t), st));
+    return DI_OK;
+}
+
+// block-level digit counting for a key-building kernel: counts[pass][digit] in shared memory (zeroed by the caller),
+// flushed into the global table by rs_flush_counts after a barrier
+__device__ __forceinline__ void rs_count_key(uint32_t (*s_counts)[256], uint64_t key, int bit_lo, int bit_hi, int n_passes)
+{
+    for (int p = 0; p < n_passes; ++p) {
+        const int shift = bit_lo + 8 * p;
+        const int width = bit_hi - shift < 8 ? bit_hi - shift : 8;
+        atomicAdd(&s_counts[p][(unsigned)(key >> shift) & ((1u << width) - 1u)], 1u);
+    }
+}
+__device__ __forceinline__ void rs_flush_counts(uint32_t (*s_counts)[256], int n_passes, uint32_t *hist)
+{
+    for (int i = threadIdx.x; i < n_passes * 256; i += blockDim.x)
+        if ((&s_counts[0][0])[i]) atomicAdd(&hist[i], (&s_counts[0][0])[i]);
+}
+
 inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, int bit_lo, int bit_hi, const uint64_t *d_seg_first_key,
-                          uint32_t n_segs, RadixSortScratch &ws, cudaStream_t st)
+                          uint32_t n_segs, RadixSortScratch &ws, cudaStream_t st, bool precounted = false)
 {
     if (n >= (1ull << 32) - 1) return set_error(DI_ERR_ARG, "radix_sort_u64: %llu keys exceed 2^32-2", (unsigned long long)n);
     const int n_passes = bit_hi > bit_lo ? (bit_hi - bit_lo + 7) / 8 : 0;
@@ -397,7 +422,8 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, int bit_lo, int 
     if (n <= 1 || n_passes == 0) return DI_OK;
     if (!d_seg_first_key) n_segs = 1;
     const uint32_t max_blocks = (uint32_t)((n + kRsTile - 1) / kRsTile) + n_segs;  // upper bound: one partial block per segment
-    DI_TRY(ws.hist.alloc((size_t)n_segs * n_passes * 256 * sizeof(uint32_t)));
+    if (precounted && n_segs != 1) return set_error(DI_ERR_ARG, "radix_sort_u64: precounted digits need a one-segment sort");
+    if (!precounted) DI_TRY(ws.hist.alloc((size_t)n_segs * n_passes * 256 * sizeof(uint32_t)));
     DI_TRY(ws.lookback.alloc((size_t)max_blocks * 256 * n_passes * sizeof(uint32_t)));
     DI_TRY(ws.lay_blocks.alloc(((size_t)n_segs + 1) * sizeof(uint32_t)));
     SortLayout lay{d_seg_first_key, ws.lay_blocks.as<uint32_t>(), n_segs};
@@ -419,10 +445,12 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, int bit_lo, int 
     }
     uint32_t *hist = ws.hist.as<uint32_t>();
     uint32_t *tickets = ws.ctl.as<uint32_t>(), *needed = tickets + kRsMaxPasses;
-    DI_CUDA(cudaMemsetAsync(ws.hist.p, 0, (size_t)n_segs * n_passes * 256 * sizeof(uint32_t), st));
     DI_CUDA(cudaMemsetAsync(ws.lookback.p, 0, (size_t)max_blocks * 256 * n_passes * sizeof(uint32_t), st));
-    rs_histogram_kernel<<<max_blocks, kRsHistThreads, 0, st>>>(a, lay, bit_lo, bit_hi, n_passes, hist);
-    DI_KERNEL_CHECK();
+    if (!precounted) {
+        DI_CUDA(cudaMemsetAsync(ws.hist.p, 0, (size_t)n_segs * n_passes * 256 * sizeof(uint32_t), st));
+        rs_histogram_kernel<<<max_blocks, kRsHistThreads, 0, st>>>(a, lay, bit_lo, bit_hi, n_passes, hist);
+        DI_KERNEL_CHECK();
+    }
     rs_bases_kernel<<<n_segs * n_passes, 256, 0, st>>>(hist, lay, n_passes, needed);
     DI_KERNEL_CHECK();
     for (int p = 0; p < n_passes; ++p) {
