@@ -97,6 +97,9 @@ SIGNATURES = {
     "di_peer_barrier_dev": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _vp]),
     "di_host_alloc": (ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(_vp)]),
     "di_host_free": (ctypes.c_int, [_vp]),
+    "di_run_writer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "di_run_writer_submit": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
+    "di_run_writer_close": (ctypes.c_int, [_vp]),
     "di_write_run_file": (ctypes.c_int, [ctypes.c_char_p, _vp, _vp, _vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
     "di_eval_ranks_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]),
     "di_get_timings": (ctypes.c_int, [_vp, ctypes.POINTER(Timings)]),

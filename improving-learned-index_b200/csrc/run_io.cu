@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -62,28 +63,69 @@ unsigned io_threads(uint64_t n_rows)
 
 }  // namespace
 
-// Appends the rows of n_queries result lists to `path`. Query i has the id bytes qid_blob[qid_offsets[i] ..
-// qid_offsets[i+1]) and counts[i] hits at docids[i * row_stride ...] / scores[i * row_stride ...] (int `{pid}` and int
-// `{score}` exactly as Python prints them). The queries are cut into one contiguous piece per host thread; every piece is
-// formatted into its own buffer and written with pwrite at its final offset, so formatting and the copy into the page
-// cache both run on all cores. The file grows by exactly the bytes RunFile.writelines would have appended.
-extern "C" int di_write_run_file(const char *path, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
-                                 const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride)
+// A run file being appended to. di_run_writer_submit formats a batch on the calling thread (all host threads) and hands the
+// formatted pieces to a background thread group that pwrite()s them at their final offsets; it returns as soon as the
+// PREVIOUS batch has reached the page cache, so the formatting of batch i overlaps the copy of batch i-1 and the caller's
+// arrays are free again on return. Batches reach the file in submission order.
+struct di_run_writer {
+    int fd = -1;
+    off_t end = 0;                       // file offset of the next batch
+    std::string path;
+    std::vector<std::string> in_flight;  // pieces the background threads are writing
+    std::thread bg;
+    int bg_errno = 0;
+
+    int wait()
+    {
+        if (bg.joinable()) bg.join();
+        in_flight.clear();
+        if (bg_errno) {
+            const int e = bg_errno;
+            bg_errno = 0;
+            return di::set_error(DI_ERR_ARG, "write to %s failed: %s", path.c_str(), strerror(e));
+        }
+        return DI_OK;
+    }
+};
+
+extern "C" int di_run_writer_open(const char *path, di_run_writer **out)
 {
-    if (!path || (n_queries && (!qid_blob || !qid_offsets || !docids || !scores || !counts)))
+    if (!path || !out) return di::set_error(DI_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    const int fd = open(path, O_WRONLY | O_CREAT, 0644);
+    if (fd < 0) return di::set_error(DI_ERR_ARG, "cannot open %s: %s", path, strerror(errno));
+    const off_t end = lseek(fd, 0, SEEK_END);  // append, like RunFile (datasets.py:310,315)
+    if (end < 0) {
+        close(fd);
+        return di::set_error(DI_ERR_ARG, "cannot seek in %s: %s", path, strerror(errno));
+    }
+    di_run_writer *w = new (std::nothrow) di_run_writer();
+    if (!w) {
+        close(fd);
+        return di::set_error(DI_ERR_NOMEM, "host allocation failed");
+    }
+    w->fd = fd;
+    w->end = end;
+    w->path = path;
+    *out = w;
+    return DI_OK;
+}
+
+// Query i has the id bytes qid_blob[qid_offsets[i] .. qid_offsets[i+1]) and counts[i] hits at docids[i * row_stride ...] /
+// scores[i * row_stride ...] (int `{pid}` and int `{score}` exactly as Python prints them). The queries are cut into one
+// contiguous piece per host thread; every piece is formatted into its own buffer and written with pwrite at its final
+// offset. The file grows by exactly the bytes RunFile.writelines would have appended.
+extern "C" int di_run_writer_submit(di_run_writer *w, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
+                                    const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride)
+{
+    if (!w || (n_queries && (!qid_blob || !qid_offsets || !docids || !scores || !counts)))
         return di::set_error(DI_ERR_ARG, "NULL argument");
     uint64_t n_rows = 0;
     for (uint32_t q = 0; q < n_queries; ++q) {
         if (counts[q] > row_stride) return di::set_error(DI_ERR_ARG, "counts[%u] = %u exceeds the row stride %u", q, counts[q], row_stride);
         n_rows += counts[q];
     }
-    const int fd = open(path, O_WRONLY | O_CREAT, 0644);
-    if (fd < 0) return di::set_error(DI_ERR_ARG, "cannot open %s: %s", path, strerror(errno));
-    const off_t base = lseek(fd, 0, SEEK_END);
-    if (base < 0 || n_rows == 0) {
-        close(fd);
-        return base < 0 ? di::set_error(DI_ERR_ARG, "cannot seek in %s: %s", path, strerror(errno)) : DI_OK;
-    }
+    if (n_rows == 0) return DI_OK;
     const unsigned n_threads = io_threads(n_rows);
     // pieces of about equal row counts, on query boundaries
     std::vector<uint32_t> cut(n_threads + 1, n_queries);
@@ -98,7 +140,6 @@ extern "C" int di_write_run_file(const char *path, const char *qid_blob, const u
     }
     const auto t_start = std::chrono::steady_clock::now();
     std::vector<std::string> bufs(n_threads);
-    std::vector<int> rcs(n_threads, 0);
     auto format_piece = [&](unsigned t) {
         std::string &out = bufs[t];
         uint64_t rows = 0, qid_bytes = 0;
@@ -134,41 +175,66 @@ extern "C" int di_write_run_file(const char *path, const char *qid_blob, const u
         for (std::thread &th : pool) th.join();
     }
     const auto t_fmt = std::chrono::steady_clock::now();
+    DI_TRY(w->wait());  // the previous batch is in the page cache
     std::vector<uint64_t> at(n_threads + 1, 0);
     for (unsigned t = 0; t < n_threads; ++t) at[t + 1] = at[t] + bufs[t].size();
-    if (ftruncate(fd, base + (off_t)at[n_threads]) != 0) {
-        close(fd);
-        return di::set_error(DI_ERR_ARG, "cannot grow %s: %s", path, strerror(errno));
-    }
-    auto write_piece = [&](unsigned t) {
-        const char *p = bufs[t].data();
-        uint64_t left = bufs[t].size(), off = (uint64_t)base + at[t];
-        while (left) {
-            const ssize_t w = pwrite(fd, p, left, (off_t)off);
-            if (w < 0) {
-                if (errno == EINTR) continue;
-                rcs[t] = errno;
-                return;
+    const off_t base = w->end;
+    if (ftruncate(w->fd, base + (off_t)at[n_threads]) != 0)
+        return di::set_error(DI_ERR_ARG, "cannot grow %s: %s", w->path.c_str(), strerror(errno));
+    w->end = base + (off_t)at[n_threads];
+    w->in_flight = std::move(bufs);
+    const bool trace = getenv("DI_B200_IO_TRACE") != nullptr;
+    const double fmt_ms = 1e3 * std::chrono::duration<double>(t_fmt - t_start).count();
+    w->bg = std::thread([w, at, base, n_threads, trace, fmt_ms, n_rows] {
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<int> rcs(n_threads, 0);
+        auto write_piece = [&](unsigned t) {
+            const char *p = w->in_flight[t].data();
+            uint64_t left = w->in_flight[t].size(), off = (uint64_t)base + at[t];
+            while (left) {
+                const ssize_t n = pwrite(w->fd, p, left, (off_t)off);
+                if (n < 0) {
+                    if (errno == EINTR) continue;
+                    rcs[t] = errno;
+                    return;
+                }
+                p += n;
+                left -= (uint64_t)n;
+                off += (uint64_t)n;
             }
-            p += w;
-            left -= (uint64_t)w;
-            off += (uint64_t)w;
-        }
-    };
-    {
+        };
         std::vector<std::thread> pool;
         for (unsigned t = 1; t < n_threads; ++t) pool.emplace_back(write_piece, t);
         write_piece(0);
         for (std::thread &th : pool) th.join();
-    }
-    close(fd);
-    if (getenv("DI_B200_IO_TRACE"))
-        fprintf(stderr, "di_write_run_file: %llu rows, %u threads, format %.1f ms, write %.1f ms\n", (unsigned long long)n_rows,
-                n_threads, 1e3 * std::chrono::duration<double>(t_fmt - t_start).count(),
-                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fmt).count());
-    for (unsigned t = 0; t < n_threads; ++t)
-        if (rcs[t]) return di::set_error(DI_ERR_ARG, "write to %s failed: %s", path, strerror(rcs[t]));
+        for (unsigned t = 0; t < n_threads; ++t)
+            if (rcs[t]) w->bg_errno = rcs[t];
+        if (trace)
+            fprintf(stderr, "di_run_writer: %llu rows, %u threads, format %.1f ms, write %.1f ms (in the background)\n",
+                    (unsigned long long)n_rows, n_threads, fmt_ms,
+                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    });
     return DI_OK;
+}
+
+extern "C" int di_run_writer_close(di_run_writer *w)
+{
+    if (!w) return DI_OK;
+    const int rc = w->wait();
+    close(w->fd);
+    delete w;
+    return rc;
+}
+
+// one batch, synchronously (RunFile.write_batch): open + submit + close
+extern "C" int di_write_run_file(const char *path, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
+                                 const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride)
+{
+    di_run_writer *w = nullptr;
+    DI_TRY(di_run_writer_open(path, &w));
+    const int rc = di_run_writer_submit(w, qid_blob, qid_offsets, docids, scores, counts, n_queries, row_stride);
+    const int rc2 = di_run_writer_close(w);
+    return rc != DI_OK ? rc : rc2;
 }
 
 // ---------------------------------------------------------------------------- rank facts for Metrics, on the device

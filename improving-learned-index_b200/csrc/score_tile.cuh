@@ -4,8 +4,9 @@
 // Replaces the two hot loops of InvertedIndex.score (inverted_index.py:57-60: read the term's
 // postings, scores[doc] += impact) and of SparseSearch.search (nano_beir_evaluator.py:118-121).
 //
-// One CTA = one (query, tile) work item. The shared-memory accumulators are ZERO when an item starts
-// (invariant of the 16-bit form: every pass that reads an accumulator word leaves a zero behind).
+// One CTA = one work item = one query against kTilesPerItem adjacent tiles, one tile after the other. The shared-memory
+// accumulators are ZERO when a tile starts (invariant of the 16-bit form: every pass that reads an accumulator word
+// leaves a zero behind).
 //   phase 1  sparse segments (u32 postings) of all the query's terms are flattened into one index
 //            space, streamed with 128-bit loads and added with shared-memory atomics;
 //   phase 2  ONE fused pass over the tile: dense segments (one impact byte per document, 128-bit loads)
@@ -482,10 +483,11 @@ __device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t 
     if (lane == 0) { L.nd = __popc(bd); L.ns = __popc(bs); }
 }
 
-// One work item = one query against n_sub (1 or 2) ADJACENT tiles starting at tile0; `slot` indexes the batch's
-// launch-ordered query records. Two tiles per item halve the per-item fixed costs (claim, record read, hand-off)
-// and put the descriptor loads of both tiles in flight together. Returns whether the query's state was read
-// (i.e. whether the hand-off from the previous item was observed).
+// One work item = one query against n_sub (1 .. kTilesPerItem) ADJACENT tiles starting at tile0; `slot` indexes the
+// batch's launch-ordered query records. Several tiles per item divide the per-item fixed costs (claim, record read,
+// hand-off) and put the descriptor loads of all the tiles in flight together; the query's threshold and count travel
+// from tile to tile in registers. Returns whether the query's state was read (i.e. whether the hand-off from the
+// previous item was observed).
 template <bool ACC32, bool BOUNDS>
 __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, uint32_t n_sub, uint32_t slot, uint32_t lane,
                                            uint32_t step, uint32_t &tma_phase, uint64_t *mbar)

@@ -77,9 +77,11 @@ class Ranker:
         def prepare(batch):                                     # query text -> term strings -> term ids (pure Python)
             return [self.index._term_ids(self.get_query_terms(q)) for q in batch]
 
-        # three stages, each on its own thread: Python prepares batch i+1 and the library writes batch i-1 to the run
-        # file while the GPU scores batch i (ctypes releases the GIL inside the library); single workers keep the order
-        with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=1) as writer:
+        # four things overlap: Python prepares batch i+1, the GPU scores batch i, the library formats batch i-1 (writer
+        # thread) and copies batch i-2 into the file (its own background threads); ctypes releases the GIL inside the
+        # library, single workers keep the order
+        with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=1) as writer, \
+                self.run_file.stream() as out:
             ready = prep.submit(prepare, batches[0]) if batches else None
             pending = None
             for i, batch in enumerate(batches):
@@ -93,7 +95,7 @@ class Ranker:
                     docs, scores, counts = res.docids, res.scores, res.counts
                 if pending is not None:
                     pending.result()
-                pending = writer.submit(self.run_file.write_batch, batch, docs, scores, counts)
+                pending = writer.submit(out.write_batch, batch, docs, scores, counts)
             if pending is not None:
                 pending.result()
         return collector.report() if collector is not None else None

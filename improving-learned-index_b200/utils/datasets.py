@@ -101,12 +101,9 @@ class RunFile:
         with open(self.run_file_path, 'a', encoding='utf-8') as f:
             f.writelines(rows)
 
-    def write_batch(self, qids, docids, scores, counts):
-        """writelines() for a whole batch straight from result arrays (docids / scores: [n, k] rows, counts[i] valid
-        entries of row i): the same bytes, formatted and written by all host threads inside the library
-        (di_write_run_file) instead of one Python string per row."""
+    @staticmethod
+    def _batch_args(qids, docids, scores, counts):
         import numpy as np
-        from .. import _native as N
         blob = [str(q).encode('utf-8') for q in qids]
         offs = np.zeros(len(blob) + 1, dtype=np.uint64)
         offs[1:] = np.cumsum([len(b) for b in blob])
@@ -115,11 +112,50 @@ class RunFile:
         c = np.ascontiguousarray(counts, dtype=np.uint32)
         if d.ndim != 2 or d.shape != s.shape or d.shape[0] != len(blob) or c.shape != (len(blob),):
             raise ValueError("write_batch: docids/scores must be [len(qids), k] and counts [len(qids)]")
-        N.check(N.lib().di_write_run_file(str(self.run_file_path).encode(), b''.join(blob), N.ptr(offs), N.ptr(d), N.ptr(s),
-                                          N.ptr(c), len(blob), d.shape[1]))
+        return b''.join(blob), offs, d, s, c
+
+    def write_batch(self, qids, docids, scores, counts):
+        """writelines() for a whole batch straight from result arrays (docids / scores: [n, k] rows, counts[i] valid
+        entries of row i): the same bytes, formatted and written by all host threads inside the library
+        (di_write_run_file) instead of one Python string per row."""
+        from .. import _native as N
+        blob, offs, d, s, c = self._batch_args(qids, docids, scores, counts)
+        N.check(N.lib().di_write_run_file(str(self.run_file_path).encode(), blob, N.ptr(offs), N.ptr(d), N.ptr(s),
+                                          N.ptr(c), len(offs) - 1, d.shape[1]))
+
+    def stream(self):
+        """Context manager for many batches: `with run_file.stream() as out: out.write_batch(...)`. A batch is copied into
+        the file in the background while the next one is searched and formatted (di_run_writer_*); the arrays passed
+        to write_batch may be reused as soon as it returns."""
+        return _RunStream(self)
 
     def read(self):
         with open(self.run_file_path, 'r', encoding='utf-8') as f:
             for line in f:
                 qid, pid, rank, score = line.strip().split('\t')
                 yield str(qid), str(pid), int(rank), float(score)
+
+
+class _RunStream:
+    def __init__(self, run_file: RunFile):
+        self.run_file, self._w = run_file, None
+
+    def __enter__(self):
+        import ctypes
+        from .. import _native as N
+        self._w = ctypes.c_void_p()
+        N.check(N.lib().di_run_writer_open(str(self.run_file.run_file_path).encode(), ctypes.byref(self._w)))
+        return self
+
+    def write_batch(self, qids, docids, scores, counts):
+        from .. import _native as N
+        blob, offs, d, s, c = RunFile._batch_args(qids, docids, scores, counts)
+        N.check(N.lib().di_run_writer_submit(self._w, blob, N.ptr(offs), N.ptr(d), N.ptr(s), N.ptr(c), len(offs) - 1, d.shape[1]))
+
+    def __exit__(self, exc_type, exc, tb):
+        from .. import _native as N
+        w, self._w = self._w, None
+        rc = N.lib().di_run_writer_close(w)
+        if exc_type is None:
+            N.check(rc)
+        return False

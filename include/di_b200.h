@@ -266,6 +266,14 @@ int di_host_free(void *ptr);
  * d_qrel_docs[d_qrel_offsets[i] .. d_qrel_offsets[i+1]); d_best_rank[i] = rank (from 1) of its first relevant hit (0 =
  * none retrieved), d_hits[i * n_depths + j] = relevant hits with rank <= d_depths[j] (n_depths <= 8). The float
  * arithmetic of metrics.py:36-43 stays with the caller, so the reported numbers are bit-identical. */
+/* The same as a stream: submit() formats a batch on the calling thread (all host threads) and returns once the PREVIOUS
+ * batch has reached the page cache — the copy of a batch into the file overlaps the formatting (and the search) of the next
+ * one, and the caller's arrays are free again when submit() returns. Batches reach the file in submission order. */
+typedef struct di_run_writer di_run_writer_t;
+int di_run_writer_open(const char *path, di_run_writer_t **out);
+int di_run_writer_submit(di_run_writer_t *writer, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
+                         const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride);
+int di_run_writer_close(di_run_writer_t *writer);
 int di_write_run_file(const char *path, const char *qid_blob, const uint64_t *qid_offsets, const uint32_t *docids,
                       const int32_t *scores, const uint32_t *counts, uint32_t n_queries, uint32_t row_stride);
 int di_eval_ranks_dev(const uint64_t *d_keys, const uint32_t *d_counts, uint32_t n_queries, uint32_t row_stride,

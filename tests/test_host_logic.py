@@ -281,6 +281,15 @@ def test_run_file_writer_matches_python_writelines(tmp_path, monkeypatch):
         RunFile(got).write_batch(qids[:300], docids[:300], scores[:300], counts[:300])      # two appends, like two batches
         RunFile(got).write_batch(qids[300:], docids[300:], scores[300:], counts[300:])
         assert got.read_bytes() == want.read_bytes(), threads
+        streamed = tmp_path / f"stream{threads}.tsv"
+        streamed.write_text("0\t1\t1\t5\n", encoding="utf-8")
+        with RunFile(streamed).stream() as out:                   # background copy of batch i while batch i+1 is formatted
+            for lo in range(0, n, 150):
+                d, s = docids[lo:lo + 150].copy(), scores[lo:lo + 150].copy()
+                out.write_batch(qids[lo:lo + 150], d, s, counts[lo:lo + 150])
+                d[:] = 0                                          # the arrays are the caller's again once write_batch returns
+                s[:] = 0
+        assert streamed.read_bytes() == want.read_bytes(), threads
     rows = list(RunFile(want).read())
     assert rows[1][2] == 1 and len(rows) == 1 + int(counts.sum())
     with pytest.raises(ValueError):
