@@ -72,14 +72,7 @@ class Ranker:
         qids = list(self.query_iterator)
         want_metrics = (mrr_depths or recall_depths) and self.qrels is not None
         collector = _DeviceMetrics(self.qrels, mrr_depths or [], recall_depths or []) if want_metrics else None
-        # a shorter first batch gets the pipeline going sooner (nothing overlaps the first search); not below ~1 000 queries:
-        # a batch smaller than the GPU's resident CTAs runs in tile lanes, which costs more per query
-        first = min(self.batch_size, max(1024, self.batch_size // 2)) if len(qids) > self.batch_size else len(qids)
-        rest = len(qids) - first
-        n_rest = -(-rest // self.batch_size) if rest > 0 else 0
-        size = -(-rest // n_rest) if n_rest else 0
-        batches = [qids[:first]] + [qids[first + i * size:first + (i + 1) * size] for i in range(n_rest)]
-        batches = [b for b in batches if b]
+        batches = [qids[lo:lo + self.batch_size] for lo in range(0, len(qids), self.batch_size)]
 
         def prepare(batch):                                     # query text -> term strings -> term ids (pure Python)
             return [self.index._term_ids(self.get_query_terms(q)) for q in batch]
