@@ -350,7 +350,9 @@ def run_b200(args):
             score_ms.append(t["score_ms"])
             final_ms.append(t["finalize_ms"])
             launches = t                     # kernels this rank's library launched in this step
-            n_launches = t["score_launches"] + t["other_launches"] + ((2 if fused else 3) * len(batches) if world > 1 else 0)
+            # + the exchange per batch: fused = stream barrier + pull-merge pass 1 (+ pass 2 when rows are cut, world > 2);
+            #   fallback = merge_gather + finalize + merge_check
+            n_launches = t["score_launches"] + t["other_launches"] + (((3 if world > 2 else 2) if fused else 3) * len(batches) if world > 1 else 0)
         barrier()
         # ---- timed: end to end through the host-buffer call
         step_e2e()

@@ -807,7 +807,7 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
     DI_TRY(ensure(ix->ws_cand, n_virtual * per_query));
     DI_TRY(ensure(ix->ws_cnt, n_virtual * 4));
     DI_TRY(ensure(ix->ws_theta, n_virtual * 8));
-    DI_TRY(ensure(ix->ws_order, (size_t)batch * sizeof(QueryRec)));
+    DI_TRY(ensure(ix->ws_order, (size_t)batch * (sizeof(QueryRec) + 1)));  // records + one bucket byte per query
     DI_TRY(ensure(ix->ws_done, 8 + n_virtual * 4));
     if (ix->d_seg_max && !ix->ws_skipped.p) {
         DI_TRY(ix->ws_skipped.alloc(8));
@@ -876,10 +876,12 @@ extern "C" int di_search_dev(di_index_t *ix, const uint32_t *d_q_terms, const ui
             ++ix->other_launches;
         }
         if (ix->n_tiles) {
-            query_order_kernel<<<1, 1024, 0, st>>>(d_q_terms, a.q_offsets, ix->d_df, ix->n_terms, nq,
-                                                   ix->ws_order.as<QueryRec>());
+            uint8_t *bucket = reinterpret_cast<uint8_t *>(ix->ws_order.as<QueryRec>() + batch);
+            query_bucket_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_q_terms, a.q_offsets, ix->d_df, ix->n_terms, nq, bucket);
             DI_KERNEL_CHECK();
-            ++ix->other_launches;
+            query_order_kernel<<<1, 1024, 0, st>>>(d_q_terms, a.q_offsets, bucket, nq, ix->ws_order.as<QueryRec>());
+            DI_KERNEL_CHECK();
+            ix->other_launches += 2;
         }
         if (per_tile_launches) {  // DI_B200_PER_TILE=1: one launch per tile (to profile a single tile)
             a.done = nullptr;

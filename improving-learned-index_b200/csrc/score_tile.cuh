@@ -102,29 +102,36 @@ struct SearchArgs {
 #endif
 
 // Launch order of a batch: queries bucketed by log2 of their total posting count (sum of the document
-// frequencies of their terms), heaviest bucket first. One block; the order inside a bucket is arbitrary
-// (results do not depend on it).
+// frequencies of their terms), heaviest bucket first; the order inside a bucket is arbitrary (results do not
+// depend on it). Two kernels: the buckets are found by the whole grid (one thread per query: the df lookups are
+// dependent global loads), the counting sort over 64 buckets and the 64-byte records by one block.
+__global__ void query_bucket_kernel(const uint32_t *__restrict__ q_terms, const uint64_t *__restrict__ q_offsets,
+                                    const unsigned long long *__restrict__ df, uint32_t n_terms, uint32_t n_queries,
+                                    uint8_t *__restrict__ bucket)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    unsigned long long cost = 0;
+    for (uint64_t j = q_offsets[q]; j < q_offsets[q + 1]; ++j) {
+        const uint32_t t = q_terms[j];
+        if (t < n_terms) cost += df[t];
+    }
+    // two buckets per power of two, descending cost = ascending bucket
+    const int msb = cost ? 63 - __clzll((long long)cost) : 0;
+    const int half = msb ? (int)((cost >> (msb - 1)) & 1ull) : 0;
+    const int b = 2 * msb + half;
+    bucket[q] = (uint8_t)(63 - (b > 63 ? 63 : b));
+}
+
 __global__ void __launch_bounds__(1024) query_order_kernel(const uint32_t *__restrict__ q_terms,
                                                          const uint64_t *__restrict__ q_offsets,
-                                                         const unsigned long long *__restrict__ df, uint32_t n_terms,
-                                                         uint32_t n_queries, QueryRec *__restrict__ recs)
+                                                         const uint8_t *__restrict__ bucket, uint32_t n_queries,
+                                                         QueryRec *__restrict__ recs)
 {
     __shared__ uint32_t s_cursor[64];
     if (threadIdx.x < 64) s_cursor[threadIdx.x] = 0;
     __syncthreads();
-    auto bucket_of = [&](uint32_t q) {
-        unsigned long long cost = 0;
-        for (uint64_t j = q_offsets[q]; j < q_offsets[q + 1]; ++j) {
-            const uint32_t t = q_terms[j];
-            if (t < n_terms) cost += df[t];
-        }
-        // two buckets per power of two, descending cost = ascending bucket
-        const int msb = cost ? 63 - __clzll((long long)cost) : 0;
-        const int half = msb ? (int)((cost >> (msb - 1)) & 1ull) : 0;
-        const int b = 2 * msb + half;
-        return (uint32_t)(63 - (b > 63 ? 63 : b));
-    };
-    for (uint32_t q = threadIdx.x; q < n_queries; q += blockDim.x) atomicAdd(&s_cursor[bucket_of(q)], 1u);
+    for (uint32_t q = threadIdx.x; q < n_queries; q += blockDim.x) atomicAdd(&s_cursor[bucket[q]], 1u);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(1024) query_order_kernel(const uint32_t *__res
         r.begin = q_offsets[q];
         r.n = (uint32_t)(q_offsets[q + 1] - r.begin);
         for (int i = 0; i < kRecInlineTerms; ++i) r.terms[i] = (uint32_t)i < r.n ? q_terms[r.begin + i] : DI_OOV_TERM;
-        recs[atomicAdd(&s_cursor[bucket_of(q)], 1u)] = r;
+        recs[atomicAdd(&s_cursor[bucket[q]], 1u)] = r;
     }
 }
 
