@@ -200,7 +200,8 @@ int di_index_term_df(const di_index_t *index, const uint32_t *term_ids, uint64_t
 int di_search(di_index_t *index, const uint32_t *q_terms, const uint64_t *q_offsets,
               uint32_t n_queries, uint32_t top_k,
               uint32_t *out_docids, int32_t *out_scores, uint32_t *out_counts);
-/* device variant: packed keys (score << 32 | ~docid), sorted descending, for the multi-GPU merge.
+/* device variant: packed keys (score << 32 | ~docid), sorted descending (or only up to di_index_set_sorted_prefix
+ * columns), for the multi-GPU merge. Asynchronous on `stream`; the index's workspace serves one search at a time.
  * max_query_len = longest query in the batch (chooses 16- or 32-bit accumulators).
  * d_theta_init (optional, may be NULL): per query a key that the caller KNOWS to be a lower bound of the
  * query's final k-th best key over the whole collection (e.g. the k-th key of a previous, partial merge);
@@ -231,8 +232,10 @@ int di_merge_topk_dev(const uint64_t *d_keys_in, const uint32_t *d_counts_in,
  * ranks: this call merges queries [q_first, q_first + n_queries) only; output rows / counts are indexed from 0.
  * Per query, one CTA pulls the first min(count, k_in) keys of each shard's row over NVLink into shared memory, selects
  * and sorts the top_k, proves the result complete (a shard holding more than k_in keys hides only keys below its
- * k_in-th) and, for a query that fails the proof, pulls the full rows and selects again — all inside the kernel.
- * *d_n_second_pass (optional counter, caller-zeroed) counts those queries. row_stride <= top_k. */
+ * k_in-th) and, for a query that fails the proof, pulls the full rows and selects again (a second launch of the same
+ * shape in which the CTAs of proven queries leave at once) — no host round trip, no compaction of query ids.
+ * Rows need to be sorted only in their first k_in columns. *d_n_second_pass (optional counter, caller-zeroed) counts the
+ * queries of the second pass. row_stride <= top_k. */
 int di_merge_pull_dev(const uint64_t *const *d_rows, const uint32_t *const *d_counts, uint32_t n_shards,
                       uint32_t q_first, uint32_t n_queries, uint32_t row_stride, uint32_t k_in, uint32_t top_k,
                       uint64_t *d_keys_out, uint32_t *d_counts_out, uint32_t *d_n_second_pass, void *stream);
