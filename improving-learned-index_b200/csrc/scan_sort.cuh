@@ -124,9 +124,22 @@ inline int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uin
 // No separate scan kernels, no host synchronisation, no allocation inside (scratch is a caller-owned
 // RadixSortScratch). Which of the two buffers holds the result is device-side state (passes whose digit is uniform are
 // skipped on the device): consumers read it through rs_result().
-constexpr int kRsThreads = 512;
+#ifndef DI_RS_THREADS
+#define DI_RS_THREADS 512
+#endif
+#ifndef DI_RS_ITEMS
+#define DI_RS_ITEMS 16
+#endif
+#ifndef DI_RS_MIN_BLOCKS
+#define DI_RS_MIN_BLOCKS 2
+#endif
+#ifndef DI_RS_MATCH_STEPS
+#define DI_RS_MATCH_STEPS 0xAAAAu   // bit s set: ranking step s finds its peers with MATCH.ANY, else with ballots
+#endif
+constexpr int kRsThreads = DI_RS_THREADS;
 constexpr int kRsWarps = kRsThreads / 32;
-constexpr int kRsItems = 16;                       // keys per thread
+constexpr int kRsItems = DI_RS_ITEMS;              // keys per thread (even)
+static_assert(kRsThreads >= 256 && kRsThreads % 32 == 0 && kRsItems % 2 == 0 && kRsItems <= 16, "sort block shape");
 constexpr int kRsTile = kRsThreads * kRsItems;     // 8192 keys per block
 constexpr int kRsWarpTile = 32 * kRsItems;         // 512 contiguous keys per warp
 constexpr int kRsMaxPasses = 8;
@@ -245,7 +258,7 @@ __device__ __forceinline__ const uint64_t *rs_result(const uint64_t *a, const ui
     return (*cur & 1u) ? b : a;
 }
 
-__global__ void __launch_bounds__(kRsThreads, 2)
+__global__ void __launch_bounds__(kRsThreads, DI_RS_MIN_BLOCKS)
 rs_onesweep_kernel(uint64_t *__restrict__ buf_a, uint64_t *__restrict__ buf_b, SortLayout lay, int shift, unsigned dmask,
                    int pass, int n_passes, const uint32_t *__restrict__ digit_base /* [n_segs][n_passes][256] */,
                    uint32_t *__restrict__ lookback /* [n_blocks][256] of this pass, zeroed */, uint32_t *__restrict__ ticket,
@@ -293,7 +306,7 @@ rs_onesweep_kernel(uint64_t *__restrict__ buf_a, uint64_t *__restrict__ buf_b, S
         // the integer pipe (all sixteen there: ALU 66 % busy, the limiter). The steps alternate, so both units share
         // the work (profiles/r2_sort_ncu.txt).
         unsigned peers;
-        if (s & 1) {
+        if ((DI_RS_MATCH_STEPS >> s) & 1u) {
             peers = __match_any_sync(0xffffffffu, digit);  // invalid lanes carry digit 256: a group of their own
         } else {
             peers = __ballot_sync(0xffffffffu, valid);

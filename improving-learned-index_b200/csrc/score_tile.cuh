@@ -47,6 +47,11 @@ constexpr int kHistBins = DI_HIST_BINS;  // score histogram of the tile-local pr
 #define DI_TILES_PER_ITEM 8
 #endif
 constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers
+#ifndef DI_FUSE_MAX
+#define DI_FUSE_MAX 4
+#endif
+constexpr int kFuseMax = DI_FUSE_MAX;  // dense segments the fused dense + threshold pass sums in registers (4 .. 8)
+static_assert(kFuseMax >= 4 && kFuseMax <= 8, "fused pass handles 4 to 8 dense segments");
 static_assert(kTilesPerItem >= 1 && kTilesPerItem * 336 + DI_HIST_BINS * 4 <= 4800,
               "segment lists + hit list must leave room for six CTAs of 32 KB accumulators per SM (static smem <= 5 KB)");
 
@@ -207,15 +212,116 @@ __host__ __device__ inline size_t score_smem_bytes(uint32_t tile_docs, bool acc3
     return (size_t)tile_docs * (acc32 ? 4 : 2) + ((kDenseTma && !acc32) ? tile_docs : 0);
 }
 
-template <int NB, bool FUSE, bool FULL>
-__device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *const (&ptr)[4], uint32_t units, uint32_t tm2,
-                                                  const uint4 *stage = nullptr)
+// units per step so that about 8 independent 128-bit loads are in flight per thread whatever the number of dense
+// terms (a work item is latency-bound: few CTAs per SM, L2-resident postings)
+template <int NB> __device__ __forceinline__ constexpr int dense_units_per_step() { return NB <= 1 ? 8 : (NB == 2 ? 4 : (NB <= 4 ? 2 : 1)); }
+
+// DI_DENSE_PRELOAD (variant): the loads of the fused pass's FIRST step are issued before the sparse phase and wait in
+// registers (`pre`), so that their latency overlaps the sparse phase's own load -> atomic -> barrier chain.
+#ifdef DI_DENSE_PRELOAD
+constexpr bool kDensePreload = true;
+#else
+constexpr bool kDensePreload = false;
+#endif
+#ifndef DI_PRE_WORDS
+#define DI_PRE_WORDS 4
+#endif
+constexpr int kPreWords = DI_PRE_WORDS;  // 128-bit words held per thread (8 = the whole first step; more than 4 spill at 80 registers)
+template <int NB> __device__ __forceinline__ constexpr int dense_pre_units()
 {
-    // U units per step so that about 8 independent 128-bit loads are in flight per thread whatever
-    // the number of dense terms (a work item is latency-bound: few CTAs per SM, L2-resident postings)
-    constexpr int U = NB <= 1 ? 8 : (NB == 2 ? 4 : 2);
+    return NB == 0 ? 0 : (dense_units_per_step<NB>() * NB <= kPreWords ? dense_units_per_step<NB>() : kPreWords / NB);
+}
+
+template <int NB>
+__device__ __forceinline__ void dense_preload(uint4 (&pre)[kPreWords], const uint4 *payload4, const uint32_t *doff)
+{
+#ifdef DI_DENSE_PREFETCH_L1   // variant: no registers held, the first step's lines are only asked into L1
+    constexpr int U = dense_units_per_step<NB>();
+#pragma unroll
+    for (int s = 0; s < U; ++s)
+#pragma unroll
+        for (int u = 0; u < NB; ++u)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(payload4 + doff[u] + threadIdx.x + s * kScoreThreads));
+#else
+    constexpr int UP = dense_pre_units<NB>();
+#pragma unroll
+    for (int s = 0; s < UP; ++s)
+#pragma unroll
+        for (int u = 0; u < NB; ++u) pre[s * NB + u] = ldg_dense_v4(payload4 + doff[u] + threadIdx.x + s * kScoreThreads);
+#endif
+}
+
+__device__ __forceinline__ void dense_preload_dispatch(int nb, uint4 (&pre)[kPreWords], const uint4 *payload4, const uint32_t *doff)
+{
+    switch (nb) {  // nb is uniform across the CTA
+#if DI_FUSE_MAX >= 8
+        case 8: dense_preload<8>(pre, payload4, doff); break;
+#endif
+#if DI_FUSE_MAX >= 7
+        case 7: dense_preload<7>(pre, payload4, doff); break;
+#endif
+#if DI_FUSE_MAX >= 6
+        case 6: dense_preload<6>(pre, payload4, doff); break;
+#endif
+#if DI_FUSE_MAX >= 5
+        case 5: dense_preload<5>(pre, payload4, doff); break;
+#endif
+        case 4: dense_preload<4>(pre, payload4, doff); break;
+        case 3: dense_preload<3>(pre, payload4, doff); break;
+        case 2: dense_preload<2>(pre, payload4, doff); break;
+        case 1: dense_preload<1>(pre, payload4, doff); break;
+        default: break;
+    }
+}
+
+// one step of a dense pass: the U units g0, g0 + threads, ... whose NB dense words are in v
+template <int NB, int U, bool FUSE, bool FULL>
+__device__ __forceinline__ void dense_consume(uint4 *s_acc4, const uint4 (&v)[U][NB > 0 ? NB : 1], uint32_t g0, uint32_t ord,
+                                              uint32_t units, uint32_t tm2, uint32_t &mask)
+{
+#pragma unroll
+    for (int s = 0; s < U; ++s) {
+        const uint32_t g = g0 + s * kScoreThreads;
+        if (FULL || g < units) {
+            uint4 a = s_acc4[g];
+            uint4 b = s_acc4[g + units];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                add_bytes8(a, v[s][u].x, v[s][u].y);
+                add_bytes8(b, v[s][u].z, v[s][u].w);
+            }
+            if (!FUSE) {
+                s_acc4[g] = a;
+                s_acc4[g + units] = b;
+            } else {
+                const bool ha = group_hit<false>(a, 0, tm2), hb = group_hit<false>(b, 0, tm2);
+                s_acc4[g] = ha ? a : make_uint4(0, 0, 0, 0);
+                s_acc4[g + units] = hb ? b : make_uint4(0, 0, 0, 0);
+                mask |= ((ha ? 1u : 0u) | (hb ? 2u : 0u)) << (2 * (ord + s));
+            }
+        }
+    }
+}
+
+template <int NB, bool FUSE, bool FULL>
+__device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *const (&ptr)[kFuseMax], uint32_t units, uint32_t tm2,
+                                                  const uint4 *stage, const uint4 (*pre)[kPreWords])
+{
+    constexpr int U = dense_units_per_step<NB>();
     uint32_t mask = 0, ord = 0;
-    for (uint32_t g0 = threadIdx.x; g0 < units; g0 += U * kScoreThreads, ord += U) {
+    uint32_t g0 = threadIdx.x;
+    if (kDensePreload && FUSE && FULL && dense_pre_units<NB>() > 0 && pre) {  // first step: (some of) the words are already in registers
+        constexpr int UP = dense_pre_units<NB>();
+        uint4 v[U][NB > 0 ? NB : 1];
+#pragma unroll
+        for (int s = 0; s < U; ++s)
+#pragma unroll
+            for (int u = 0; u < NB; ++u) v[s][u] = s < UP ? (*pre)[s * NB + u] : ldg_dense_v4(ptr[u] + g0 + s * kScoreThreads);
+        dense_consume<NB, U, FUSE, FULL>(s_acc4, v, g0, ord, units, tm2, mask);
+        g0 += U * kScoreThreads;
+        ord += U;
+    }
+    for (; g0 < units; g0 += U * kScoreThreads, ord += U) {
         uint4 v[U][NB > 0 ? NB : 1];
 #pragma unroll
         for (int s = 0; s < U; ++s) {
@@ -228,53 +334,48 @@ __device__ __forceinline__ uint32_t dense_steps16(uint4 *s_acc4, const uint4 *co
                     v[s][u] = (FULL || g < units) ? ldg_dense_v4(ptr[u] + g) : make_uint4(0, 0, 0, 0);
             }
         }
-#pragma unroll
-        for (int s = 0; s < U; ++s) {
-            const uint32_t g = g0 + s * kScoreThreads;
-            if (FULL || g < units) {
-                uint4 a = s_acc4[g];
-                uint4 b = s_acc4[g + units];
-#pragma unroll
-                for (int u = 0; u < NB; ++u) {
-                    add_bytes8(a, v[s][u].x, v[s][u].y);
-                    add_bytes8(b, v[s][u].z, v[s][u].w);
-                }
-                if (!FUSE) {
-                    s_acc4[g] = a;
-                    s_acc4[g + units] = b;
-                } else {
-                    const bool ha = group_hit<false>(a, 0, tm2), hb = group_hit<false>(b, 0, tm2);
-                    s_acc4[g] = ha ? a : make_uint4(0, 0, 0, 0);
-                    s_acc4[g + units] = hb ? b : make_uint4(0, 0, 0, 0);
-                    mask |= ((ha ? 1u : 0u) | (hb ? 2u : 0u)) << (2 * (ord + s));
-                }
-            }
-        }
+        dense_consume<NB, U, FUSE, FULL>(s_acc4, v, g0, ord, units, tm2, mask);
     }
     return mask;
 }
 
+// tiles of >= 16 K documents (the default) have only full steps in the fused pass
+__device__ __forceinline__ bool dense_full_steps(uint32_t units) { return units % (8 * kScoreThreads) == 0; }
+
 template <int NB, bool FUSE>
-__device__ __forceinline__ uint32_t dense_pass16(uint4 *s_acc4, const uint4 *p0, const uint4 *p1, const uint4 *p2,
-                                                 const uint4 *p3, uint32_t units, uint32_t tm2, const uint4 *stage)
+__device__ __forceinline__ uint32_t dense_pass16(uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff, uint32_t units,
+                                                 uint32_t tm2, const uint4 *stage, const uint4 (*pre)[kPreWords])
 {
-    const uint4 *const ptr[4] = {p0, p1, p2, p3};
-    // tiles of >= 16 K documents (the default) have only full steps
-    if (FUSE && units % (8 * kScoreThreads) == 0) return dense_steps16<NB, FUSE, true>(s_acc4, ptr, units, tm2, stage);
-    return dense_steps16<NB, FUSE, false>(s_acc4, ptr, units, tm2, stage);
+    const uint4 *ptr[kFuseMax];
+#pragma unroll
+    for (int u = 0; u < kFuseMax; ++u) ptr[u] = payload4 + doff[u < NB ? u : 0];
+    if (FUSE && dense_full_steps(units)) return dense_steps16<NB, FUSE, true>(s_acc4, ptr, units, tm2, stage, pre);
+    return dense_steps16<NB, FUSE, false>(s_acc4, ptr, units, tm2, stage, nullptr);
 }
 
 template <bool FUSE>
 __device__ __forceinline__ uint32_t dense_dispatch16(int nb, uint4 *s_acc4, const uint4 *payload4, const uint32_t *doff,
-                                                     uint32_t units, uint32_t tm2, const uint4 *stage = nullptr)
+                                                     uint32_t units, uint32_t tm2, const uint4 *stage = nullptr,
+                                                     const uint4 (*pre)[kPreWords] = nullptr)
 {
-    const uint4 *p0 = payload4 + doff[0], *p1 = payload4 + doff[1], *p2 = payload4 + doff[2], *p3 = payload4 + doff[3];
     switch (nb) {  // nb is uniform across the CTA
-        case 4: return dense_pass16<4, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
-        case 3: return dense_pass16<3, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
-        case 2: return dense_pass16<2, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
-        case 1: return dense_pass16<1, FUSE>(s_acc4, p0, p1, p2, p3, units, tm2, stage);
-        default: return FUSE ? dense_pass16<0, true>(s_acc4, p0, p1, p2, p3, units, tm2, nullptr) : 0u;
+#if DI_FUSE_MAX >= 8
+        case 8: return dense_pass16<8, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+#endif
+#if DI_FUSE_MAX >= 7
+        case 7: return dense_pass16<7, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+#endif
+#if DI_FUSE_MAX >= 6
+        case 6: return dense_pass16<6, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+#endif
+#if DI_FUSE_MAX >= 5
+        case 5: return dense_pass16<5, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+#endif
+        case 4: return dense_pass16<4, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+        case 3: return dense_pass16<3, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+        case 2: return dense_pass16<2, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+        case 1: return dense_pass16<1, FUSE>(s_acc4, payload4, doff, units, tm2, stage, pre);
+        default: return FUSE ? dense_pass16<0, true>(s_acc4, payload4, doff, units, tm2, nullptr, nullptr) : 0u;
     }
 }
 
@@ -569,6 +670,8 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
         SegLists &L = s_seg[sub];
         const SegDesc *__restrict__ desc = p.desc + (uint64_t)tile * p.n_terms;
         uint32_t f0 = 0, nf = 0;  // L.doff[f0 .. f0 + nf): dense segments left for the fused pass
+        uint4 pre[kPreWords];            // DI_DENSE_PRELOAD: first step of the fused pass, loaded ahead of the sparse phase
+        bool preloaded = false;
         bool first = true, touched = false, skip = false;
         for (uint64_t r0 = qb; first || r0 < qe; r0 += kMaxSeg) {
             if (!first) {
@@ -606,6 +709,14 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
             }
             touched = touched || (nd + ns) != 0;
             DI_PROF_MARK(0);  // segment lookup
+
+            // ---- dense segments of the fused pass (the last four .. kFuseMax of the last round)
+            nf = (!ACC32 && last) ? min(nd, (uint32_t)kFuseMax) : 0u;
+            f0 = nd - nf;
+            if (kDensePreload && !ACC32) {
+                preloaded = nf != 0 && ns != 0 && dense_full_steps(units);
+                if (preloaded) dense_preload_dispatch((int)nf, pre, payload4, L.off + f0);
+            }
 
             // ---- phase 1: sparse segments. word = impact << 16 | byte offset of the accumulator word;
             //      units [0, even) of a segment hold even documents, the rest odd ones.
@@ -660,16 +771,14 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
             DI_PROF_MARK(2);  // sparse
 
             // ---- dense segments that do not go through the fused pass: plain read-modify-write
-            nf = (!ACC32 && last) ? min(nd, 4u) : 0u;
-            f0 = nd - nf;
             if (kDenseTma && !ACC32 && nf && tid == 0) {  // experiment: the TMA unit stages the first fused segment meanwhile
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(mbar, T);
                 tma_load_1d(s_acc4 + T / 8, payload4 + L.off[f0], T, mbar);
             }
             if (!ACC32) {
-                for (uint32_t j0 = 0; j0 < f0; j0 += 4)
-                    dense_dispatch16<false>(f0 - j0 < 4 ? (int)(f0 - j0) : 4, s_acc4, payload4, L.off + j0, units, 0u);
+                for (uint32_t j0 = 0; j0 < f0; j0 += kFuseMax)
+                    dense_dispatch16<false>(f0 - j0 < (uint32_t)kFuseMax ? (int)(f0 - j0) : kFuseMax, s_acc4, payload4, L.off + j0, units, 0u);
             } else if (nd) {
                 dense_pass32(s_acc4, payload4, L.off, (int)nd, units);
             }
@@ -717,7 +826,12 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                 ++tma_phase;
                 stage = s_acc4 + T / 8;
             }
-            const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, L.off + f0, units, tm | (tm << 16), stage);
+            const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, L.off + f0, units, tm | (tm << 16), stage,
+#ifdef DI_DENSE_PREFETCH_L1
+                                                         nullptr);
+#else
+                                                         (kDensePreload && preloaded) ? &pre : nullptr);
+#endif
             record_hits16(mask, units, s_hist, &s_nhits);
         } else {
             scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);

@@ -3,7 +3,10 @@
 src/deep_impact/evaluation/nano_beir_evaluator.py:230-231.
 
 ``beir`` and ``pytrec_eval`` are not vendored in the reference and not installed here, so this
-restates trec_eval's published definitions (PARITY UNPINNED at this boundary):
+restates trec_eval's published definitions. Against beir itself PARITY IS UNPINNED; the
+arithmetic is checked against an independent published implementation, scikit-learn's ``ndcg_score`` /
+``average_precision_score`` (tests/test_host_logic.py::test_trec_metrics_against_scikit_learn), and hand-computed
+cases. The definitions:
 ranking = score descending with ties broken by document id descending; ndcg_cut uses linear
 gain and log2(rank + 1) discount with the ideal ranking taken from the qrels; map_cut sums
 precision at relevant ranks <= k and divides by the number of relevant documents; recall.k and

@@ -110,6 +110,56 @@ def test_trec_metrics_hand_computed():
     assert prec["P@1"] == 0.5 and prec["P@3"] == round((2 / 3) / 2, 5)
 
 
+def test_trec_metrics_against_scikit_learn():
+    """An independent, published implementation as the external check of trec_metrics.py (beir / pytrec_eval are not
+    installable here): scikit-learn's ndcg_score (linear gain, log2 discount, ideal ranking from the true gains) and
+    average_precision_score (sum of precision at the relevant ranks / number of relevant documents) on random graded
+    qrels. sklearn sees the whole corpus (documents the run did not retrieve rank below every retrieved one), which is
+    how trec_eval counts relevant-but-unretrieved documents in the ideal DCG and in the AP / recall denominators."""
+    sk = pytest.importorskip("sklearn.metrics")
+    rng = np.random.default_rng(5)
+    n_docs, n_queries, depth = 400, 40, 150
+    docs = [f"d{i:04d}" for i in range(n_docs)]
+    qrels, results, truth, scores = {}, {}, {}, {}
+    for qi in range(n_queries):
+        q = f"q{qi}"
+        gains = np.zeros(n_docs, dtype=np.int64)
+        rel = rng.choice(n_docs, size=int(rng.integers(1, 30)), replace=False)
+        gains[rel] = rng.integers(1, 4, size=rel.size)          # graded relevance 1..3
+        judged_zero = rng.choice(n_docs, size=10, replace=False)  # explicit 0 judgements must not count
+        sc = rng.permutation(n_docs).astype(np.float64) + 1.0    # distinct scores: no tie rule involved
+        retrieved = np.argsort(-sc)[:depth]
+        qrels[q] = {docs[d]: int(gains[d]) for d in rel}
+        qrels[q].update({docs[d]: 0 for d in judged_zero if gains[d] == 0})
+        results[q] = {docs[d]: float(sc[d]) for d in retrieved}
+        full = np.full(n_docs, 0.0)
+        full[retrieved] = sc[retrieved]                           # unretrieved: below every retrieved score
+        full[np.setdiff1d(np.arange(n_docs), retrieved)] = -1.0 - np.arange(n_docs - depth)
+        truth[q], scores[q] = gains, full
+    ks = [1, 5, 10, 100]
+    ndcg, _map, recall, prec = EvaluateRetrieval().evaluate(qrels, results, ks + [depth])
+    for k in ks:
+        want = np.mean([sk.ndcg_score(truth[q][None, :], scores[q][None, :], k=k) for q in qrels])
+        assert ndcg[f"NDCG@{k}"] == round(float(want), 5)
+        order = {q: np.argsort(-scores[q])[:k] for q in qrels}
+        assert recall[f"Recall@{k}"] == round(float(np.mean([(truth[q][order[q]] > 0).sum() / (truth[q] > 0).sum() for q in qrels])), 5)
+        assert prec[f"P@{k}"] == round(float(np.mean([(truth[q][order[q]] > 0).sum() / k for q in qrels])), 5)
+    # MAP: sklearn has no cut-off; map_cut.k is the same sum restricted to ranks <= k, so compare on a run that holds every
+    # relevant document above the cut (retrieve everything, cut at the corpus size)
+    results_all = {q: {docs[d]: float(scores[q][d]) for d in range(n_docs)} for q in qrels}
+    _, map_all, _, _ = EvaluateRetrieval().evaluate(qrels, results_all, [n_docs])
+    want = np.mean([sk.average_precision_score(truth[q] > 0, scores[q]) for q in qrels])
+    assert map_all[f"MAP@{n_docs}"] == round(float(want), 5)
+    # and the cut version against a direct restatement of trec_eval's map_cut on the same ranking
+    for k in ks:
+        vals = []
+        for q in qrels:
+            order = np.argsort(-scores[q])[:k]
+            hit = truth[q][order] > 0
+            vals.append(float((np.cumsum(hit)[hit] / (np.flatnonzero(hit) + 1)).sum() / (truth[q] > 0).sum()))
+        assert _map[f"MAP@{k}"] == round(float(np.mean(vals)), 5)
+
+
 # ------------------------------------------------------------------ host-side collection parser (no GPU involved)
 def _same(a, b):
     return (a.vocab() == b.vocab() and np.array_equal(a.doc_offsets, b.doc_offsets)
