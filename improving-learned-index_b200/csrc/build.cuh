@@ -83,11 +83,13 @@ __global__ void __launch_bounds__(256) invert_keys_kernel(const uint32_t *__rest
     rs_flush_counts(s_counts, n_passes, sort_hist);
 }
 
+// `skip_if` (device word, may be nullptr): non-zero = the sort's last pass has already stored docids / impacts itself.
 __global__ void invert_extract_kernel(const uint64_t *__restrict__ ka, const uint64_t *__restrict__ kb,
                                       const uint32_t *__restrict__ cur, uint64_t n_post, uint32_t n_terms,
                                       uint64_t *__restrict__ term_offsets, uint32_t *__restrict__ docids,
-                                      uint8_t *__restrict__ impacts)
+                                      uint8_t *__restrict__ impacts, const uint32_t *__restrict__ skip_if)
 {
+    if (skip_if && *skip_if) return;
     const uint64_t *__restrict__ keys = rs_result(ka, kb, cur);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_post; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[i];
@@ -98,6 +100,30 @@ __global__ void invert_extract_kernel(const uint64_t *__restrict__ ka, const uin
         for (int64_t tt = tprev + 1; tt <= t; ++tt) term_offsets[tt] = i;  // also covers empty terms
         if (i == n_post - 1)
             for (int64_t tt = t + 1; tt <= (int64_t)n_terms; ++tt) term_offsets[tt] = n_post;
+    }
+}
+
+// term_offsets[t] = first position of a term >= t = suffix minimum of the first positions the sort's last pass noted
+// (terms without postings have none), n_post behind the last one. One block; `run_if`: see invert_extract_kernel.
+__global__ void __launch_bounds__(1024) invert_offsets_kernel(const unsigned long long *__restrict__ first, uint32_t n_terms,
+                                                            uint64_t n_post, uint64_t *__restrict__ term_offsets,
+                                                            const uint32_t *__restrict__ run_if)
+{
+    if (!*run_if) return;
+    __shared__ unsigned long long s_min[1024];
+    const uint32_t n = n_terms + 1, per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned long long m = n_post;
+    for (uint32_t t = hi; t > lo; --t) m = min(m, first[t - 1]);
+    s_min[threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.x == 0)  // suffix minimum over the chunks (1024 steps)
+        for (int c = (int)blockDim.x - 2; c >= 0; --c) s_min[c] = min(s_min[c], s_min[c + 1]);
+    __syncthreads();
+    m = threadIdx.x + 1 < blockDim.x ? s_min[threadIdx.x + 1] : n_post;
+    for (uint32_t t = hi; t > lo; --t) {
+        m = min(m, first[t - 1]);
+        term_offsets[t - 1] = m;
     }
 }
 
@@ -147,10 +173,31 @@ inline int invert_dev(const uint32_t *d_term_ids, const uint8_t *d_impacts, cons
                                                                        ka.as<uint64_t>(), d_status, ws.hist.as<uint32_t>(), sort_lo,
                                                                        sort_hi, n_passes);
     DI_KERNEL_CHECK();
-    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, sort_lo, sort_hi, nullptr, 1, ws, st, /*precounted=*/true));
+    // the sort's last pass stores docids / impacts itself and notes where every term starts (RsEpilogue); the separate
+    // pass over the sorted keys only runs when the device skipped that pass (every posting in one digit)
+    StreamBuf first(st);
+    DI_TRY(first.alloc(((size_t)n_terms + 1) * sizeof(unsigned long long)));
+    DI_CUDA(cudaMemsetAsync(first.p, 0xFF, ((size_t)n_terms + 1) * sizeof(unsigned long long), st));
+    RsEpilogue epi;
+    epi.low = d_out_docids;
+    epi.byte = d_out_impacts;
+    epi.first = first.as<unsigned long long>();
+    epi.field_shift = kInvTermShift;
+#ifdef DI_INVERT_NO_EPILOGUE
+    const RsEpilogue *use_epi = nullptr;
+#else
+    const RsEpilogue *use_epi = &epi;
+#endif
+    DI_TRY(radix_sort_u64(ka.as<uint64_t>(), kb.as<uint64_t>(), n_post, sort_lo, sort_hi, nullptr, 1, ws, st, /*precounted=*/true,
+                          use_epi));
+    const uint32_t *fused = use_epi && n_post > 1 ? ws.needed(n_passes - 1) : nullptr;
     invert_extract_kernel<<<grid_for(n_post, 256), 256, 0, st>>>(ka.as<uint64_t>(), kb.as<uint64_t>(), ws.cur(), n_post,
-                                                                 n_terms, d_term_offsets, d_out_docids, d_out_impacts);
+                                                                 n_terms, d_term_offsets, d_out_docids, d_out_impacts, fused);
     DI_KERNEL_CHECK();
+    if (fused) {
+        invert_offsets_kernel<<<1, 1024, 0, st>>>(first.as<unsigned long long>(), n_terms, n_post, d_term_offsets, fused);
+        DI_KERNEL_CHECK();
+    }
     return DI_OK;
 }
 

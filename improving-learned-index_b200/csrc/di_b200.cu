@@ -242,7 +242,8 @@ static int finish_tiled(di_index *ix, const uint64_t *ka, const uint64_t *kb, co
         return set_error(DI_ERR_NOMEM, "segment table of %llu entries is too large; use larger tiles",
                          (unsigned long long)n_segs);
     TileStats stats{};
-    DevBuf d_begin, d_end, d_odd, d_size, d_nflag, d_scan, d_cnt;
+    // scratch from the stream-ordered pool: a rebuild (or a build after an inversion) reuses the blocks already mapped
+    StreamBuf d_begin(st), d_end(st), d_odd(st), d_size(st), d_nflag(st), d_scan(st), d_cnt(st);
     DI_TRY(d_begin.alloc(n_segs * 4));
     DI_TRY(d_end.alloc(n_segs * 4));
     DI_TRY(d_odd.alloc(n_segs * 4));
@@ -331,7 +332,8 @@ static int build_tiled(di_index *ix, const uint64_t *d_term_offsets, const uint3
     if (V >= kMaxTerms) return set_error(DI_ERR_ARG, "n_terms %u exceeds 2^24 - 1", V);
     if (n_post >= (1ull << 32) - 1) return set_error(DI_ERR_ARG, "more than 2^32-2 postings in one shard");
 
-    DevBuf d_stats, d_fz, ka, kb;
+    DevBuf d_stats, d_fz;
+    StreamBuf ka(st), kb(st);
     RadixSortScratch ws(st);
     DI_TRY(d_stats.alloc(sizeof(TileStats)));
     DI_CUDA(cudaMemsetAsync(d_stats.p, 0, sizeof(TileStats), st));
@@ -399,7 +401,8 @@ static int build_tiled_docmajor(di_index *ix, const uint32_t *d_term_ids, const 
     const uint64_t n_tiles = (n_docs + ix->tile_docs - 1) / ix->tile_docs;
     if (n_tiles >= 0xFFFFu)
         return set_error(DI_ERR_RANGE, "shard spans more than 65535 tiles of %u docs; raise tile_docs or shard further", ix->tile_docs);
-    DevBuf d_stats, ka, kb, d_first;
+    DevBuf d_stats;
+    StreamBuf ka(st), kb(st), d_first(st);
     RadixSortScratch ws(st);
     DI_TRY(d_stats.alloc(sizeof(TileStats)));
     DI_CUDA(cudaMemsetAsync(d_stats.p, 0, sizeof(TileStats), st));

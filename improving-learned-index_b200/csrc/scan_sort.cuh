@@ -258,11 +258,25 @@ __device__ __forceinline__ const uint64_t *rs_result(const uint64_t *a, const ui
     return (*cur & 1u) ? b : a;
 }
 
+// Optional epilogue of the LAST pass (the inversion): instead of writing the sorted 64-bit keys and reading them once more
+// to take them apart, the pass stores the two halves of a posting where they belong — low[pos] = low 32 bits of the key,
+// byte[pos] = 255 - bits 32..39 — and notes where each value of the field above `field_shift` first appears
+// (first[field] = min position; every block reports the first key of each run of equal fields inside its sorted tile, and
+// the first key of a field in the whole array is the first one of some tile). A pass the device skips (all keys share the
+// digit) leaves this undone; the caller reads needed[last pass] to know and runs its separate pass instead.
+struct RsEpilogue {
+    uint32_t *low = nullptr;
+    uint8_t *byte = nullptr;
+    unsigned long long *first = nullptr;
+    int field_shift = 0;
+};
+
+template <bool EPI>
 __global__ void __launch_bounds__(kRsThreads, DI_RS_MIN_BLOCKS)
 rs_onesweep_kernel(uint64_t *__restrict__ buf_a, uint64_t *__restrict__ buf_b, SortLayout lay, int shift, unsigned dmask,
                    int pass, int n_passes, const uint32_t *__restrict__ digit_base /* [n_segs][n_passes][256] */,
                    uint32_t *__restrict__ lookback /* [n_blocks][256] of this pass, zeroed */, uint32_t *__restrict__ ticket,
-                   const uint32_t *__restrict__ needed_this, const uint32_t *__restrict__ cur)
+                   const uint32_t *__restrict__ needed_this, const uint32_t *__restrict__ cur, RsEpilogue epi)
 {
     if (!*needed_this) return;  // every segment has one digit only: identity pass
     const uint64_t *__restrict__ keys_in = (*cur & 1u) ? buf_b : buf_a;
@@ -376,9 +390,20 @@ rs_onesweep_kernel(uint64_t *__restrict__ buf_a, uint64_t *__restrict__ buf_b, S
     }
     __syncthreads();
     const uint32_t n_here = (uint32_t)(tile_hi - tile_lo);
-    for (uint32_t i = threadIdx.x; i < n_here; i += kRsThreads) {
-        const uint64_t k = s_keys[i];
-        keys_out[s_global[(unsigned)(k >> shift) & dmask] + i] = k;  // = global start + (i - local start)
+    if (!EPI) {
+        for (uint32_t i = threadIdx.x; i < n_here; i += kRsThreads) {
+            const uint64_t k = s_keys[i];
+            keys_out[s_global[(unsigned)(k >> shift) & dmask] + i] = k;  // = global start + (i - local start)
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n_here; i += kRsThreads) {
+            const uint64_t k = s_keys[i];
+            const uint32_t pos = s_global[(unsigned)(k >> shift) & dmask] + i;
+            epi.low[pos] = (uint32_t)k;
+            epi.byte[pos] = (uint8_t)(255u - ((uint32_t)(k >> 32) & 255u));
+            const uint64_t field = k >> epi.field_shift;
+            if (i == 0 || (s_keys[i - 1] >> epi.field_shift) != field) atomicMin(epi.first + field, (unsigned long long)pos);
+        }
     }
 }
 
@@ -393,6 +418,7 @@ struct RadixSortScratch {
     StreamBuf hist, lookback, ctl, lay_keys, lay_blocks;
     explicit RadixSortScratch(cudaStream_t st) : hist(st), lookback(st), ctl(st), lay_keys(st), lay_blocks(st) {}
     uint32_t *cur() const { return ctl.as<uint32_t>() + 2 * kRsMaxPasses; }  // bit 0: the result is in buffer b
+    const uint32_t *needed(int pass) const { return ctl.as<uint32_t>() + kRsMaxPasses + pass; }  // 0: the device skipped the pass
 };
 
 // Sorts keys ascending by bits [bit_lo, bit_hi) (stable: ties keep input order) inside every segment. `a` holds the
@@ -425,7 +451,8 @@ __device__ __forceinline__ void rs_flush_counts(uint32_t (*s_counts)[256], int n
 }
 
 inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, int bit_lo, int bit_hi, const uint64_t *d_seg_first_key,
-                          uint32_t n_segs, RadixSortScratch &ws, cudaStream_t st, bool precounted = false)
+                          uint32_t n_segs, RadixSortScratch &ws, cudaStream_t st, bool precounted = false,
+                          const RsEpilogue *last_pass_epilogue = nullptr)
 {
     if (n >= (1ull << 32) - 1) return set_error(DI_ERR_ARG, "radix_sort_u64: %llu keys exceed 2^32-2", (unsigned long long)n);
     const int n_passes = bit_hi > bit_lo ? (bit_hi - bit_lo + 7) / 8 : 0;
@@ -453,7 +480,8 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, int bit_lo, int 
     DI_CUDA(cudaGetDevice(&dev));
     constexpr size_t kSmem = (size_t)kRsTile * 8 + (size_t)kRsWarps * 256 * 4;
     if (!(attr_done.load(std::memory_order_acquire) & (1ull << (dev & 63)))) {
-        DI_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+        DI_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+        DI_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
         attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     uint32_t *hist = ws.hist.as<uint32_t>();
@@ -469,9 +497,14 @@ inline int radix_sort_u64(uint64_t *a, uint64_t *b, uint64_t n, int bit_lo, int 
     for (int p = 0; p < n_passes; ++p) {
         const int shift = bit_lo + 8 * p;
         const int width = bit_hi - shift < 8 ? bit_hi - shift : 8;
-        rs_onesweep_kernel<<<max_blocks, kRsThreads, kSmem, st>>>(a, b, lay, shift, (1u << width) - 1u, p, n_passes, hist,
-                                                                  ws.lookback.as<uint32_t>() + (size_t)p * max_blocks * 256,
-                                                                  tickets + p, needed + p, ws.cur());
+        if (last_pass_epilogue && p == n_passes - 1)
+            rs_onesweep_kernel<true><<<max_blocks, kRsThreads, kSmem, st>>>(a, b, lay, shift, (1u << width) - 1u, p, n_passes, hist,
+                                                                            ws.lookback.as<uint32_t>() + (size_t)p * max_blocks * 256,
+                                                                            tickets + p, needed + p, ws.cur(), *last_pass_epilogue);
+        else
+            rs_onesweep_kernel<false><<<max_blocks, kRsThreads, kSmem, st>>>(a, b, lay, shift, (1u << width) - 1u, p, n_passes, hist,
+                                                                             ws.lookback.as<uint32_t>() + (size_t)p * max_blocks * 256,
+                                                                             tickets + p, needed + p, ws.cur(), RsEpilogue{});
         DI_KERNEL_CHECK();
         rs_flip_kernel<<<1, 1, 0, st>>>(ws.cur(), needed + p);
         DI_KERNEL_CHECK();

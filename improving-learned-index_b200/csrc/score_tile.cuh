@@ -48,7 +48,15 @@ constexpr int kHistBins = DI_HIST_BINS;  // score histogram of the tile-local pr
 #endif
 constexpr int kTilesPerItem = DI_TILES_PER_ITEM;  // adjacent tiles one work item covers
 #ifndef DI_FUSE_MAX
-#define DI_FUSE_MAX 4
+#define DI_FUSE_MAX 6   // measured: 4 -> 28.19, 6 -> 28.15, 8 -> 30.4 ms per step (one unit per step leaves too few loads in flight)
+#endif
+// Barrier-lean tile loop of the 16-bit form (default): the hit / emit counters grow over the whole work item (every thread
+// keeps their values at tile start in registers) instead of being reset behind a barrier per tile, and the barriers that
+// only separated a tile from the next one are dropped: sparse -> fused pass -> hit expansion are the three that remain.
+#if defined(DI_NO_LEAN_BARRIERS) || defined(DI_DENSE_TMA)
+constexpr bool kLean = false;
+#else
+constexpr bool kLean = true;
 #endif
 constexpr int kFuseMax = DI_FUSE_MAX;  // dense segments the fused dense + threshold pass sums in registers (4 .. 8)
 static_assert(kFuseMax >= 4 && kFuseMax <= 8, "fused pass handles 4 to 8 dense segments");
@@ -295,8 +303,15 @@ __device__ __forceinline__ void dense_consume(uint4 *s_acc4, const uint4 (&v)[U]
                 s_acc4[g + units] = b;
             } else {
                 const bool ha = group_hit<false>(a, 0, tm2), hb = group_hit<false>(b, 0, tm2);
+#ifdef DI_STORE_SELECT   // round-2 form: eight SEL + two stores per unit
                 s_acc4[g] = ha ? a : make_uint4(0, 0, 0, 0);
                 s_acc4[g + units] = hb ? b : make_uint4(0, 0, 0, 0);
+#else                    // unconditional zero store, then the (rare) predicated store of a hit group's sums: -0.15 ms per step
+                s_acc4[g] = make_uint4(0, 0, 0, 0);
+                s_acc4[g + units] = make_uint4(0, 0, 0, 0);
+                if (ha) s_acc4[g] = a;
+                if (hb) s_acc4[g + units] = b;
+#endif
                 mask |= ((ha ? 1u : 0u) | (hb ? 2u : 0u)) << (2 * (ord + s));
             }
         }
@@ -424,7 +439,8 @@ __device__ __forceinline__ void emit_group(const uint4 &x, uint32_t g, uint32_t 
 
 // The fused pass leaves one hit mask per thread; the warp compacts them into the hit-group list s_hits with
 // one prefix sum and one shared-memory atomic (first kHistBins groups are remembered; *s_nhits counts all).
-__device__ __forceinline__ void record_hits16(uint32_t mask, uint32_t units, uint32_t *s_hits, uint32_t *s_nhits)
+// *s_nhits is never reset inside a work item (no barrier needed for that): `nhits_base` is its value when the tile started.
+__device__ __forceinline__ void record_hits16(uint32_t mask, uint32_t units, uint32_t *s_hits, uint32_t *s_nhits, uint32_t nhits_base)
 {
     if (!__any_sync(0xffffffffu, mask != 0)) return;  // the usual case once the query has a threshold
     const uint32_t lane = lane_id(), c = __popc(mask);
@@ -435,7 +451,7 @@ __device__ __forceinline__ void record_hits16(uint32_t mask, uint32_t units, uin
         if (lane >= (unsigned)o) incl += up;
     }
     uint32_t base = 0;
-    if (lane == 31) base = atomicAdd(s_nhits, incl);
+    if (lane == 31) base = atomicAdd(s_nhits, incl) - nhits_base;
     uint32_t slot = __shfl_sync(0xffffffffu, base, 31) + incl - c;
     while (mask) {
         const uint32_t bit = (uint32_t)(__ffs(mask) - 1);
@@ -604,7 +620,7 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
     extern __shared__ uint4 s_acc4[];  // tile accumulators
     uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_acc4);
     __shared__ SegLists s_seg[kTilesPerItem];  // one per tile of the item
-    __shared__ uint32_t s_emit, s_ready, s_nhits;
+    __shared__ uint32_t s_emit, s_ready, s_nhits, s_cut;
     __shared__ __align__(16) uint32_t s_hist[kHistBins];  // score histogram / hit-group list / radix-select scratch
     __shared__ uint32_t s_scan[33];
     __shared__ uint32_t s_tmp[2];
@@ -622,6 +638,9 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
     // Items are dispatched in tile-major order, so this is almost always already true: probe now,
     // and only wait (before the first fused pass) in the rare case it is not.
     if (tid == 0) s_ready = p.done == nullptr || step == 0 || ld_flag_u32(p.done + sq) >= step;
+    constexpr bool lean = kLean && !ACC32;
+    if (lean && tid == 0) { s_emit = 0; s_nhits = 0; }  // ordered by the first tile's list barrier; never reset inside the item
+    uint32_t emit_base = 0, nhits_base = 0;              // the counters' values when the current tile started (uniform)
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
 
     // ---- first-round segment lookup of ALL the item's tiles: warp 0, a lane's descriptor loads in flight together
@@ -686,7 +705,8 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                 }
             }
             if (ACC32 && first) zero_words16(s_acc4, T / 4);  // overlaps the descriptor loads of warp 0
-            __syncthreads();
+            // the lists of ALL the item's tiles were published by the first tile's barrier
+            if (!lean || !first || sub == 0) __syncthreads();
             const uint32_t nd = L.nd, ns = L.ns;
             const bool last = r0 + kMaxSeg >= qe;
             if (first && last && nd + ns == 0) { skip = true; break; }  // query has no posting in this tile
@@ -811,13 +831,16 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
         // this tile loses: compare against score + 1 and keep the (many) ties out of the slow path.
         if (theta != 0 && key_docid(theta) < doc_base) ++ths;
         if (!ACC32 && ths > 0x10000u) ths = 0x10000u;  // a caller-given bound no 16-bit sum can reach: nothing hits
-        if (tid == 0) { s_emit = 0; s_nhits = 0; }
         uint64_t theta_pre = 0;
-        __syncthreads();
+        if (!lean) {
+            if (tid == 0) { s_emit = 0; s_nhits = 0; }
+            __syncthreads();
+        }
         DI_PROF_MARK(3);  // state wait
 
         // ---- phase 2: fused dense + threshold pass (16-bit), or the plain scan (32-bit).
         //      s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
+        uint32_t mask = 0;
         if (!ACC32) {
             const uint32_t tm = ths - 1u;
             const uint4 *stage = nullptr;
@@ -826,18 +849,28 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                 ++tma_phase;
                 stage = s_acc4 + T / 8;
             }
-            const uint32_t mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, L.off + f0, units, tm | (tm << 16), stage,
+            mask = dense_dispatch16<true>((int)nf, s_acc4, payload4, L.off + f0, units, tm | (tm << 16), stage,
 #ifdef DI_DENSE_PREFETCH_L1
                                                          nullptr);
 #else
                                                          (kDensePreload && preloaded) ? &pre : nullptr);
 #endif
-            record_hits16(mask, units, s_hist, &s_nhits);
+            record_hits16(mask, units, s_hist, &s_nhits, nhits_base);
         } else {
             scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
         }
-        __syncthreads();
-        if (s_nhits > (uint32_t)kHistBins) {
+        if (lean) {
+            // the usual case for small k: no group of the tile holds a candidate — nothing to expand, the count and the
+            // threshold stay as they are (the vote is uniform, so every thread takes the same way)
+            if (!__syncthreads_or(mask != 0)) {
+                DI_PROF_MARK(4);
+                continue;
+            }
+        } else {
+            __syncthreads();
+        }
+        const uint32_t cnt_adj = cnt0 - emit_base;  // emission slots are cnt0 + (counter - its value at tile start)
+        if (s_nhits - nhits_base > (uint32_t)kHistBins) {
             // Flooded: more groups than slots hold a document at or above the threshold (the first tiles of a
             // frequent-term query whose bound is still loose). In the 16-bit form every hit group still holds its
             // sums (the others are zero, i.e. below any threshold), so the accumulators can simply be re-scanned.
@@ -869,32 +902,39 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
             }
             __syncthreads();  // everybody has read s_nhits
             if (tid == 0) s_nhits = 0;
+            nhits_base = 0;
             __syncthreads();
-            scan_groups<ACC32, true>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
+            scan_groups<ACC32, true>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt_adj, &s_emit);
             __syncthreads();
         }
-        expand_hits<ACC32>(s_acc4, s_hist, min(s_nhits, (uint32_t)kHistBins), ths, doc_base, theta, cand, cnt0, &s_emit);
+        expand_hits<ACC32>(s_acc4, s_hist, min(s_nhits - nhits_base, (uint32_t)kHistBins), ths, doc_base, theta, cand, cnt_adj,
+                           &s_emit);
         __syncthreads();
         DI_PROF_MARK(4);  // fused dense + threshold pass, emission
-        uint32_t n = cnt0 + s_emit;  // <= c0 + tile_docs <= cap
+        uint32_t n = cnt_adj + s_emit;  // <= c0 + tile_docs <= cap
+        if (lean) { emit_base = s_emit; nhits_base = s_nhits; }
+        bool did_cut = false;
         dirty = dirty || n != cnt0 || theta_pre > theta;
         if (n > p.c0) {
             // too many live candidates: keep exactly the k best and raise the threshold to the k-th
             if (n <= (T * (ACC32 ? 4u : 2u)) / 8u) {
                 // the accumulators are idle now: their shared memory stages the whole list (the usual case)
                 theta = block_cut_to_k_staged(cand, n, p.k, reinterpret_cast<uint64_t *>(s_acc4), s_hist, s_tmp,
-                                              &s_emit);
+                                              lean ? &s_cut : &s_emit);
                 if (!ACC32) zero_words16(s_acc4, (n + 1u) / 2u);  // restore the invariant (ordered by the next barrier)
                 n = p.k;
             } else {
                 theta = block_select_kth<true>(cand, n, p.k, s_hist, s_tmp);
                 n = block_compact_ge<true>(cand, n, theta, s_scan);
             }  // theta >= theta_pre: k of the emitted keys are at or above that bound
+            did_cut = true;
         } else if (theta_pre > theta) {
             theta = theta_pre;
         }
         cnt0 = n;
-        if (sub + 1 < n_sub) __syncthreads();  // s_emit / s_hist / the accumulators are free again for the second tile
+        // s_emit / s_hist / the accumulators are free again for the next tile (lean form: the barrier after the hit expansion
+        // already says so, unless a cut just used the accumulator memory as its staging buffer)
+        if ((!lean || did_cut) && sub + 1 < n_sub) __syncthreads();
         DI_PROF_MARK(5);  // cut to k
 #ifdef DI_PROFILE_PHASES
         if (tid == 0 && p.prof) atomicAdd(p.prof + (size_t)tile * 8 + 7, 1ull);  // items that reached the fused pass

@@ -10,7 +10,7 @@ grep -oE "^\s+/\*[0-9a-f]+\*/\s+(@!?U?P[0-9T] )?[A-Z0-9_.]+" /tmp/_k3.sass | awk
 echo
 echo "## fused dense + threshold pass, 2 dense segments, predicate-free form: one step of the loop"
 echo "##   LDG.E.128.CONSTANT (2 segments x 4 units in flight) -> LDS.128 accumulators -> PRMT (alu pipe) + IMAD.IADD (fma pipe)"
-echo "##   -> VIMNMX3.U16x2 / VIMNMX.U16x2 threshold test in registers -> SEL + STS.128 (zero, or the sums of a hit group)"
+echo "##   -> VIMNMX3.U16x2 / VIMNMX.U16x2 threshold test in registers -> STS.128 of zeros, then a predicated STS.128 of the sums of a hit group"
 L=$(grep -n "VIMNMX3" /tmp/_k3.sass | head -1 | cut -d: -f1)
 sed -n "$((L-70)),$((L+30))p" /tmp/_k3.sass | grep -E "^\s+/\*[0-9a-f]{4,5}\*/" | sed -E 's#/\* 0x[0-9a-f]+ \*/##' | cut -c1-100
 echo
