@@ -643,41 +643,55 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
     uint32_t emit_base = 0, nhits_base = 0;              // the counters' values when the current tile started (uniform)
     const uint4 *__restrict__ payload4 = reinterpret_cast<const uint4 *>(p.payload);
 
-    // ---- first-round segment lookup of ALL the item's tiles: warp 0, a lane's descriptor loads in flight together
-    if (tid < kMaxSeg) {
-        SegDesc d[kTilesPerItem];
-        uint32_t mx[kTilesPerItem];   // this term's largest impact in each tile; without the table: unknown (no skipping)
+    // ---- first-round segment lookup of ALL the item's tiles, one query term per lane: warp w takes the tiles w, w + warps, ...
+    //      (round 2: warp 0 did all of them — eight serial ballot / prefix-scan chains), a lane's descriptor loads in flight together
+#ifdef DI_LOOKUP_ONE_WARP
+    constexpr int kLookupWarps = 1;
+#else
+    constexpr int kLookupWarps = kScoreThreads / 32;
+#endif
+    constexpr int kTilesPerWarp = (kTilesPerItem + kLookupWarps - 1) / kLookupWarps;
+    if (tid < kLookupWarps * 32) {
+        const uint32_t ln = tid & 31u, w = tid >> 5;
+        SegDesc d[kTilesPerWarp];
+        uint32_t mx[kTilesPerWarp];   // this term's largest impact in each tile; without the table: unknown (no skipping)
         const bool bounded = BOUNDS && qe - qb <= kMaxSeg;
 #pragma unroll
-        for (int j = 0; j < kTilesPerItem; ++j) { d[j] = SegDesc{0u, 0u}; mx[j] = 0u; }
-        if (qb + tid < qe) {
-            const uint32_t t = tid < kRecInlineTerms ? rec->terms[tid] : p.q_terms[qb + tid];
+        for (int jj = 0; jj < kTilesPerWarp; ++jj) { d[jj] = SegDesc{0u, 0u}; mx[jj] = 0u; }
+        if (qb + ln < qe) {
+            const uint32_t t = ln < kRecInlineTerms ? rec->terms[ln] : p.q_terms[qb + ln];
             if (t < p.n_terms) {  // DI_OOV_TERM and anything out of range: no postings
 #pragma unroll
-                for (int j = 0; j < kTilesPerItem; ++j)
-                    if ((uint32_t)j < n_sub) {
-                        d[j] = p.desc[(uint64_t)(tile0 + j) * p.n_terms + t];
-                        if (bounded) mx[j] = p.seg_max[(uint64_t)(tile0 + j) * p.n_terms + t];
+                for (int jj = 0; jj < kTilesPerWarp; ++jj) {
+                    const uint32_t j = w + jj * kLookupWarps;
+                    if (j < n_sub) {
+                        d[jj] = p.desc[(uint64_t)(tile0 + j) * p.n_terms + t];
+                        if (bounded) mx[jj] = p.seg_max[(uint64_t)(tile0 + j) * p.n_terms + t];
                     }
+                }
             }
         }
         if (!bounded) {
 #pragma unroll
-            for (int j = 0; j < kTilesPerItem; ++j) mx[j] = kNoBound;
+            for (int jj = 0; jj < kTilesPerWarp; ++jj) mx[jj] = kNoBound;
         }
 #ifdef DI_L2_PREFETCH
         // experiment (profiles/README.md): the item's later tiles are needed a few microseconds from now — ask the TMA
         // unit to pull their segments from HBM into L2 meanwhile (cp.async.bulk.prefetch.L2)
 #pragma unroll
-        for (int j = 1; j < kTilesPerItem; ++j)
-            if ((uint32_t)j < n_sub && d[j].n_flag) {
-                const uint32_t units16 = (d[j].n_flag & kDenseFlag) ? (p.tile_docs >> kDenseUnitShift) : (d[j].n_flag & 0xFFFFu);
-                prefetch_l2_bulk(p.payload + (uint64_t)d[j].off16 * 16, units16 * 16);
+        for (int jj = 0; jj < kTilesPerWarp; ++jj) {
+            const uint32_t j = w + jj * kLookupWarps;
+            if (j >= 1 && j < n_sub && d[jj].n_flag) {
+                const uint32_t units16 = (d[jj].n_flag & kDenseFlag) ? (p.tile_docs >> kDenseUnitShift) : (d[jj].n_flag & 0xFFFFu);
+                prefetch_l2_bulk(p.payload + (uint64_t)d[jj].off16 * 16, units16 * 16);
             }
+        }
 #endif
 #pragma unroll
-        for (int j = 0; j < kTilesPerItem; ++j)
-            if ((uint32_t)j < n_sub) fill_seg_lists(s_seg[j], d[j], tid, mx[j]);
+        for (int jj = 0; jj < kTilesPerWarp; ++jj) {
+            const uint32_t j = w + jj * kLookupWarps;  // warp-uniform
+            if (j < n_sub) fill_seg_lists(s_seg[j], d[jj], ln, mx[jj]);
+        }
     }
 
     DI_PROF_DECL;
