@@ -60,6 +60,7 @@ constexpr bool kLean = true;
 #endif
 constexpr int kFuseMax = DI_FUSE_MAX;  // dense segments the fused dense + threshold pass sums in registers (4 .. 8)
 static_assert(kFuseMax >= 4 && kFuseMax <= 8, "fused pass handles 4 to 8 dense segments");
+static_assert(kHistBins % 256 == 0 && kHistBins >= kSelectSmemWords, "s_hist doubles as the radix select's scratch (a 256-bin build corrupts it: measured)");
 static_assert(kTilesPerItem >= 1 && kTilesPerItem * 336 + DI_HIST_BINS * 4 <= 4800,
               "segment lists + hit list must leave room for six CTAs of 32 KB accumulators per SM (static smem <= 5 KB)");
 
@@ -607,6 +608,25 @@ __device__ __forceinline__ void fill_seg_lists(SegLists &L, SegDesc d, uint32_t 
     if (lane == 0) { L.nd = __popc(bd); L.ns = __popc(bs); }
 }
 
+// DI_SPARSE_PREFETCH (variant): the sparse units the NEXT tile of the item will read are asked into L1 (no registers
+// held) right after this tile's fused pass — between here and the next tile's sparse loop there are only the hit
+// expansion and its barriers, no dense streaming that would evict them again.
+__device__ __forceinline__ void sparse_prefetch_l1(const SegLists &L, const uint4 *payload4)
+{
+    const uint32_t ns = L.ns;
+    if (!ns) return;
+    const uint32_t total = L.spref[ns];
+    uint32_t seg = 0, seg_lo = 0, seg_hi = L.spref[1], seg_off = L.soff(0);
+    for (uint32_t u = threadIdx.x; u < total; u += kScoreThreads) {
+        if (u >= seg_hi) {
+            do { ++seg; seg_hi = L.spref[seg + 1]; } while (u >= seg_hi);
+            seg_lo = L.spref[seg];
+            seg_off = L.soff(seg);
+        }
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(payload4 + seg_off + (u - seg_lo)));
+    }
+}
+
 // One work item = one query against n_sub (1 .. kTilesPerItem) ADJACENT tiles starting at tile0; `slot` indexes the
 // batch's launch-ordered query records. Several tiles per item divide the per-item fixed costs (claim, record read,
 // hand-off) and put the descriptor loads of all the tiles in flight together; the query's threshold and count travel
@@ -855,6 +875,9 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
         // ---- phase 2: fused dense + threshold pass (16-bit), or the plain scan (32-bit).
         //      s_hist doubles as the hit-group list; it is free between the pre-selection and the radix select
         uint32_t mask = 0;
+#ifdef DI_SPARSE_PREFETCH_EARLY
+        if (!ACC32 && sub + 1 < n_sub) sparse_prefetch_l1(s_seg[sub + 1], payload4);
+#endif
         if (!ACC32) {
             const uint32_t tm = ths - 1u;
             const uint4 *stage = nullptr;
@@ -870,6 +893,9 @@ __device__ __forceinline__ bool score_item(const SearchArgs &p, uint32_t tile0, 
                                                          (kDensePreload && preloaded) ? &pre : nullptr);
 #endif
             record_hits16(mask, units, s_hist, &s_nhits, nhits_base);
+#ifdef DI_SPARSE_PREFETCH
+            if (sub + 1 < n_sub) sparse_prefetch_l1(s_seg[sub + 1], payload4);
+#endif
         } else {
             scan_groups<ACC32, false>(s_acc4, T, ths, s_hist, &s_nhits, doc_base, theta, cand, cnt0, &s_emit);
         }
@@ -997,8 +1023,12 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
     uint32_t tma_phase = 0;
     __shared__ __align__(8) uint64_t s_mbar;  // DI_DENSE_TMA experiment only
     if (kDenseTma && threadIdx.x == 0) mbar_init(&s_mbar, 1);
+#ifdef DI_CLAIM_SPLIT
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1ull);
+#endif
     for (;;) {
-        __syncthreads();  // everybody is done with the previous item's shared memory
+        __syncthreads();  // everybody is done with the previous item's shared memory (DI_CLAIM_SPLIT: and the next ticket is visible)
+#ifndef DI_CLAIM_SPLIT
         if (threadIdx.x == 0) {
 #ifdef DI_CLAIM_AHEAD   // measured slower (profiles/README.md): the value lives across the whole item and spills
             s_item = next;
@@ -1008,6 +1038,7 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
 #endif
         }
         __syncthreads();
+#endif
         const unsigned long long item = s_item;
         if (item >= n_items) break;
         // step-major: all chains advance together, so the GPU works on `lanes` tile pairs at a time
@@ -1022,14 +1053,25 @@ score_persistent_kernel(SearchArgs p, unsigned long long *counter)
         const uint32_t lane = p.lanes == 1 ? 0u : v / p.n_queries, slot = v - lane * p.n_queries;
         const uint32_t tile0 = lane * p.tiles_per_lane + step * kTilesPerItem;
         const uint32_t lane_end = min((lane + 1) * p.tiles_per_lane, p.n_tiles);
-        if (tile0 >= lane_end) continue;  // the last lane may be shorter; nobody waits on these steps
+        if (tile0 >= lane_end) {  // the last lane may be shorter; nobody waits on these steps
+#ifdef DI_CLAIM_SPLIT
+            __syncthreads();  // everybody has read s_item
+            if (threadIdx.x == 0) s_item = atomicAdd(counter, 1ull);
+#endif
+            continue;
+        }
         const bool synced = score_item<ACC32, BOUNDS>(p, tile0, min((uint32_t)kTilesPerItem, lane_end - tile0), slot, lane, step, tma_phase, &s_mbar);
         // Hand-off: CTA barrier, then ONE thread publishes with a release store (MEMBAR.GPU + store). The
         // barrier orders every thread's candidate / threshold writes before the release (the pattern
         // cooperative-groups grid sync relies on). done[q] must grow one step at a time: an item that had
         // nothing to do in its tiles still waits for the previous step before announcing the next.
         __syncthreads();
+#ifdef DI_CLAIM_SPLIT   // variant: the next ticket (thread 0) and the hand-off (first thread of warp 1) travel at the same time
+        if (threadIdx.x == 0) s_item = atomicAdd(counter, 1ull);  // every thread read s_item before the barrier above
+        if (threadIdx.x == 32) {
+#else
         if (threadIdx.x == 0) {
+#endif
             uint32_t *flag = p.done + lane * p.n_queries + p.recs[slot].q;
             if (!synced && step != 0) {
                 uint32_t spins = 0;
