@@ -18,5 +18,5 @@ for n in ("n1","ref","c4_n1"):
     except Exception as e:
         print(n, "FAILED", e)
 PY
-bash tools/gpu_prof.sh $TAG
+[ -n "${DI_SKIP_PROF:-}" ] || bash tools/gpu_prof.sh $TAG   # DI_SKIP_PROF=1: the captures were taken by an earlier call
 echo total $SECONDS s
