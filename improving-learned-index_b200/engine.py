@@ -196,7 +196,10 @@ class DeviceIndex:
         """queries: list of term-id lists. Returns (docids[Q,k], scores[Q,k], counts[Q]). pinned=True: the arrays
         live in page-locked memory owned by the index (full-rate device-to-host copy of large results) and are
         RECYCLED: two sets per result shape alternate, so a result stays valid until the second next pinned call."""
-        flat, offs = flatten_queries(queries)
+        return self.search_arrays(*flatten_queries(queries), top_k, pinned=pinned)
+
+    def search_arrays(self, flat: np.ndarray, offs: np.ndarray, top_k: int, pinned: bool = False):
+        """search() for queries already flattened: flat uint32 term ids (OOV = 0xFFFFFFFF), uint64 offsets [n + 1]."""
         if flat.size == 0:
             flat = np.zeros(1, dtype=np.uint32)
         if not pinned:

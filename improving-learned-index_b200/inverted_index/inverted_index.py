@@ -94,6 +94,22 @@ class InvertedIndex:
         get = self.vocab.get
         return [get(t, -1) for t in query_terms]
 
+    def _flat_term_ids(self, queries: Sequence[Iterable[str]]):
+        """All queries' terms -> (flat uint32 term ids, uint64 offsets) in ONE pass over the strings (unknown term = OOV,
+        inverted_index.py:43-44): the per-query lists of ids that _term_ids + engine.flatten_queries build cost more
+        Python time than the GPU needs for the search."""
+        from itertools import chain
+        lists = [q if isinstance(q, (list, tuple, set, frozenset)) else list(q) for q in queries]
+        offs = np.zeros(len(lists) + 1, dtype=np.uint64)
+        np.cumsum(np.fromiter(map(len, lists), dtype=np.int64, count=len(lists)), out=offs[1:].view(np.int64))
+        ids = list(map(self.vocab.get, chain.from_iterable(lists)))   # dict.get at C speed; None = not in the vocabulary
+        try:
+            flat = np.array(ids, dtype=np.int64)
+        except TypeError:
+            flat = np.array([engine.N.OOV if t is None else t for t in ids], dtype=np.int64)
+        flat = flat.reshape(-1)
+        return flat.astype(np.uint32), offs
+
     def score_batch(self, queries: Sequence[Iterable[str]], top_k: int = 1000, pinned: bool = False) -> "BatchResults":
         """score() for many queries in one GPU pass; element i is what score(queries[i]) returns."""
         if top_k <= 0 or not len(queries):
@@ -102,7 +118,8 @@ class InvertedIndex:
         k = min(int(top_k), max(int(self._n_docs_hint), 1))
         if k > MAX_TOP_K:
             raise ValueError(f'top_k={top_k} on {self._n_docs_hint} documents exceeds the supported {MAX_TOP_K}')
-        return BatchResults(*self.device_index.search([self._term_ids(q) for q in queries], k, pinned=pinned))
+        flat, offs = self._flat_term_ids(queries)
+        return BatchResults(*self.device_index.search_arrays(flat, offs, k, pinned=pinned))
 
     def score_id_batch(self, term_id_lists: Sequence[Sequence[int]], top_k: int = 1000, pinned: bool = False) -> "BatchResults":
         """score_batch for queries already mapped to term ids (-1 = not in the vocabulary)."""

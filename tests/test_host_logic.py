@@ -160,6 +160,31 @@ def test_trec_metrics_against_scikit_learn():
         assert _map[f"MAP@{k}"] == round(float(np.mean(vals)), 5)
 
 
+def test_score_batch_term_mapping_equals_the_per_query_form():
+    """InvertedIndex.score_batch maps all term strings in one pass; the arrays must be the ones the per-query form
+    (vocab.get per term, then engine.flatten_queries) hands to the same C-ABI call. No GPU: only the host mapping runs."""
+    from improving_learned_index_b200 import engine
+    from improving_learned_index_b200.inverted_index.inverted_index import InvertedIndex
+    ix = InvertedIndex.__new__(InvertedIndex)
+    ix.vocab = {f"t{i:03d}": i for i in range(500)}
+    rng = np.random.default_rng(11)
+    queries = []
+    for qi in range(300):
+        terms = [f"t{int(t):03d}" if t < 500 else f"unknown{int(t)}" for t in rng.integers(0, 560, size=int(rng.integers(0, 9)))]
+        queries.append(terms if qi % 4 else tuple(terms))
+    queries += [[], iter(["t001", "zzz", "t001"]), ["t499"]]           # empty, a one-shot iterator, a duplicate term
+    want_flat, want_offs = engine.flatten_queries([ix._term_ids(q) for q in queries[:-3]] + [[], [1, -1, 1], [499]])
+    flat, offs = ix._flat_term_ids(queries)
+    assert flat.dtype == np.uint32 and offs.dtype == np.uint64
+    assert np.array_equal(flat, want_flat) and np.array_equal(offs, want_offs)
+    assert (flat == 0xFFFFFFFF).sum() > 0 and len(ix.vocab) == 500    # unknown terms became OOV, nothing was added to the vocabulary
+    s = {"t002", "t003", "nope"}                                      # a set, as the reference's process_query returns
+    f2, o2 = ix._flat_term_ids([s])
+    assert sorted(f2.tolist()) == [2, 3, 0xFFFFFFFF] and o2.tolist() == [0, 3]
+    ix.vocab["extra"] = 500                                           # a vocabulary that grew is noticed
+    assert ix._flat_term_ids([["extra"]])[0].tolist() == [500]
+
+
 # ------------------------------------------------------------------ host-side collection parser (no GPU involved)
 def _same(a, b):
     return (a.vocab() == b.vocab() and np.array_equal(a.doc_offsets, b.doc_offsets)
