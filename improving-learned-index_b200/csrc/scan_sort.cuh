@@ -121,6 +121,8 @@ inline int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uin
 //     blocks of its segment (each block first publishes its own digit counts, then sums its predecessors' until it
 //     meets one that already knows its inclusive prefix), sorts the tile by digit in shared memory and writes each
 //     digit's run with consecutive threads.
+//   * optionally the LAST pass takes the keys apart instead of writing them (RsEpilogue below: the inversion's docid /
+//     impact arrays and the start of every term come straight out of the sort).
 // No separate scan kernels, no host synchronisation, no allocation inside (scratch is a caller-owned
 // RadixSortScratch). Which of the two buffers holds the result is device-side state (passes whose digit is uniform are
 // skipped on the device): consumers read it through rs_result().

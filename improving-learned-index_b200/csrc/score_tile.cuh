@@ -19,6 +19,10 @@
 //            threshold (build.cuh, threshold seeds).
 // Accumulators are u16 pairs packed in 32-bit words (ACC32 = false; queries of <= 257 terms cannot
 // overflow 16 bits) or u32 (ACC32 = true: long queries, zeroed at item start, separate scan pass).
+// Per tile the 16-bit form synchronises the CTA three times (after the sparse atomics, after the fused pass —
+// a uniform vote that ends the tile when no group holds a candidate — and after the hit expansion); the segment
+// lookup of all the item's tiles is shared by the four warps. The kernel compiles to exactly 80 registers (six
+// CTAs per SM): anything that keeps one more value alive across a phase has measured slower.
 #pragma once
 
 #include "build.cuh"
